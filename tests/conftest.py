@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # GPU tests are selected with -m gpu; when they are selected on a box without a GPU they must
+    # fail loudly rather than skip (a silent skip would read as "parity green").
+    pass
+
+
+@pytest.fixture(scope="session")
+def repo_root():
+    return ROOT
