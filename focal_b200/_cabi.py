@@ -1,0 +1,106 @@
+"""ctypes binding of libfocal_b200.so (the C ABI declared in include/focal_b200.h).
+
+There is no fallback: if the shared library is missing or does not load, importing the loss fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libfocal_b200.so")
+
+FOCAL_TERM_NCE, FOCAL_TERM_ORTH, FOCAL_TERM_TEMPORAL, FOCAL_TERM_ALL = 1, 2, 4, 7
+FOCAL_PREC_BF16 = 0
+FOCAL_MAX_MODALITIES = 4
+ABI_VERSION = 1
+FOCAL_OK, FOCAL_EINVAL, FOCAL_ESHAPE, FOCAL_ECUDA, FOCAL_EWORKSPACE = 0, -1, -2, -3, -4
+
+EXPORTS = (
+    "focal_b200_abi_version", "focal_b200_strerror", "focal_b200_workspace_info", "focal_b200_prologue",
+    "focal_b200_nce_rowsum", "focal_b200_nce_lse", "focal_b200_nce_grad", "focal_b200_temporal",
+    "focal_b200_finalize", "focal_b200_loss", "focal_b200_debug_umma",
+)
+
+
+class FocalCfg(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("S", C.c_int32), ("M", C.c_int32), ("D", C.c_int32),
+        ("temperature", C.c_float), ("margin", C.c_float),
+        ("w_shared", C.c_float), ("w_private", C.c_float), ("w_orth", C.c_float), ("w_rank", C.c_float),
+        ("no_private", C.c_int32), ("need_grad", C.c_int32), ("terms", C.c_int32), ("precision", C.c_int32),
+        ("seq_begin", C.c_int32), ("seq_end", C.c_int32), ("num_sms", C.c_int32),
+        ("reserved", C.c_int32 * 3),
+    ]
+
+
+class FocalWsInfo(C.Structure):
+    _fields_ = [
+        ("total_bytes", C.c_size_t),
+        ("b", C.c_int32), ("bpad", C.c_int32), ("Bpad", C.c_int32), ("n_problems", C.c_int32),
+        ("n_ops", C.c_int32), ("kb_full", C.c_int32),
+        ("rowsum_off", C.c_size_t), ("rowsum_bytes", C.c_size_t),
+        ("cnt_off", C.c_size_t), ("cnt_bytes", C.c_size_t),
+        ("mintra_off", C.c_size_t), ("lossparts_off", C.c_size_t),
+        ("dz_off", C.c_size_t), ("dz_bytes", C.c_size_t),
+        ("dx_off", C.c_size_t), ("dx_bytes", C.c_size_t),
+    ]
+
+
+class FocalError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        self.code = code
+        super().__init__(f"{what}: {strerror(code)} (code {code})")
+
+
+_lib = None
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """Load the shared library once.  Raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -m focal_b200.build` (nvcc, sm_100a). "
+            "focal_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(path)
+    vp, cfgp = C.c_void_p, C.POINTER(FocalCfg)
+    lib.focal_b200_abi_version.restype = C.c_int
+    lib.focal_b200_strerror.restype = C.c_char_p
+    lib.focal_b200_strerror.argtypes = [C.c_int]
+    lib.focal_b200_workspace_info.argtypes = [cfgp, C.POINTER(FocalWsInfo)]
+    lib.focal_b200_prologue.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp]
+    lib.focal_b200_nce_rowsum.argtypes = [cfgp, vp, C.c_size_t, vp]
+    lib.focal_b200_nce_lse.argtypes = [cfgp, vp, C.c_size_t, C.c_int, vp]
+    lib.focal_b200_nce_grad.argtypes = [cfgp, vp, C.c_size_t, vp]
+    lib.focal_b200_temporal.argtypes = [cfgp, vp, C.c_size_t, vp]
+    lib.focal_b200_finalize.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
+    lib.focal_b200_loss.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
+    lib.focal_b200_debug_umma.argtypes = [vp, C.c_uint32, vp, C.c_uint32] + [C.c_uint32] * 10 + [vp, vp]
+    for name in EXPORTS:
+        if name != "focal_b200_strerror":
+            getattr(lib, name).restype = C.c_int
+    if lib.focal_b200_abi_version() != ABI_VERSION:
+        raise ImportError(f"{path}: ABI version {lib.focal_b200_abi_version()} != expected {ABI_VERSION}")
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def strerror(code: int) -> str:
+    return load().focal_b200_strerror(code).decode()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise FocalError(code, what)
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr

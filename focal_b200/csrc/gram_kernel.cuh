@@ -1,0 +1,447 @@
+// Flash-style Gram kernels on tcgen05 / TMEM (sm_100a).
+//
+// One persistent, warp-specialised kernel template serves the four dense passes of the FOCAL loss:
+//
+//   NCE_FWD   G = Z_I Z_J^T (log2-domain logits)  -> row sums  sum_{j != k} 2^G            (loss.py:74-85)
+//   NCE_BWD   recompute G, W = 2^G (1/r_k + 1/r_j) -> O += W Z_J  (second UMMA, W via smem) (autograd of the above)
+//   TMP_FWD   G = X_I X_J^T -> delta = sqrt(n_i+n_j-2G) -> S x S block means -> hinge        (loss.py:113-135)
+//   TMP_BWD   same pass + r_ij = coef_IJ / delta_ij -> O += R X_J                           (fwd + bwd fused)
+//
+// The N x N logit / distance matrices are never written to memory.  Operands are bf16 tiles that the prologue
+// laid out in HBM exactly as the UMMA wants them in shared memory (K-block-major, 128-byte rows, SWIZZLE_128B),
+// so each tile is a single linear TMA bulk copy.  Roles: warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM
+// owner), warps 2..5 = epilogue (one TMEM lane quarter each).  Row tile = 128 rows (UMMA M), column tile = BN.
+#pragma once
+#include "plan.h"
+#include "ptx.cuh"
+
+namespace fb {
+
+enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
+
+constexpr int kGramThreads = 192;
+constexpr int kNumBStages = 3;
+constexpr int kNumWStages = 2;
+constexpr int kTmemCols = 512;
+
+template <int BN, int KB>
+struct GramSmem {
+  static constexpr uint32_t kABytes = KB * 128 * 128;           // [KB][128 rows][128 B]
+  static constexpr uint32_t kBTile = KB * BN * 128;             // [KB][BN rows][128 B]
+  static constexpr uint32_t kColVec = 2 * BN * 4;               // two per-column fp32 vectors
+  static constexpr uint32_t kBStage = kBTile + 1024;            // tile + column vectors, keeps 1024-B alignment
+  static constexpr uint32_t kWStage = (BN / 64) * 128 * 128;    // [BN/64][128 rows][128 B]  (A operand of UMMA #2)
+  static constexpr uint32_t kAOff = 0;
+  static constexpr uint32_t kBOff = kAOff + kABytes;
+  static constexpr uint32_t kWOff = kBOff + kNumBStages * kBStage;
+  static constexpr uint32_t kBarOff = kWOff + kNumWStages * kWStage;
+  static constexpr uint32_t kTotal = kBarOff + 256;
+  static constexpr uint32_t kDynamic = kTotal + 1024;           // slack for manual 1024-B alignment
+};
+
+struct GramBars {
+  uint64_t a_full, a_empty;
+  uint64_t b_full[kNumBStages], b_empty[kNumBStages];
+  uint64_t s_full[2], s_empty[2];
+  uint64_t w_full[kNumWStages], w_empty[kNumWStages];
+  uint64_t o_full, o_empty;
+  uint32_t tmem_base;
+  float red[4];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// work-item decoding
+// ---------------------------------------------------------------------------------------------------------
+struct Item {
+  const uint8_t* a_src;        // first K block of the A tile; K blocks are a_kstride bytes apart
+  uint64_t a_kstride;
+  const uint8_t* b_src[2];     // column side 0 / 1 operand base (row 0, K block 0)
+  uint64_t b_kstride;
+  const float* colvec0[2];     // per-column vectors of side 0 / 1 (row 0)
+  const float* colvec1[2];
+  int ct_begin, ct_end;        // global column tile range
+  int ntc;                     // column tiles per side
+  int row0;                    // first row (within side / tensor) of the row tile
+  int side;                    // NCE: which half of z the rows come from
+  int ncol_valid;              // valid columns per side (b for NCE, B for TMP)
+  int row_lo, row_hi;          // owned rows [lo, hi) within the side
+  int q, s, c;                 // problem / position / call
+};
+
+template <int MODE, int BN, int KB>
+__device__ __forceinline__ int gram_num_items(const Plan& p) {
+  if (MODE == NCE_FWD || MODE == NCE_BWD) {
+    const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM;
+    const int nsp = (MODE == NCE_FWD) ? p.nsplit_fwd : 1;
+    return p.nProb * p.S * 2 * (t1 - t0) * nsp;
+  } else {
+    const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
+    return p.nT * (t1 - t0);
+  }
+}
+
+template <int MODE, int BN, int KB>
+__device__ __forceinline__ void gram_decode(const Plan& p, const uint8_t* ws, int it, Item& x) {
+  if (MODE == NCE_FWD || MODE == NCE_BWD) {
+    const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM, nrt = t1 - t0;
+    const int nsp = (MODE == NCE_FWD) ? p.nsplit_fwd : 1;
+    int r = it;
+    const int sp = r % nsp; r /= nsp;
+    const int rt = t0 + r % nrt; r /= nrt;
+    const int side = r % 2; r /= 2;
+    const int s = r % p.S; r /= p.S;
+    const int q = r;
+    const ProbDesc& pr = p.probs[q];
+    const OpDesc& oa = p.ops[pr.opA];
+    const OpDesc& ob = p.ops[pr.opB];
+    const uint64_t rowsNce = (uint64_t)p.S * p.bpad;
+    x.b_kstride = x.a_kstride = rowsNce * 128;
+    x.b_src[0] = ws + oa.off + (uint64_t)s * p.bpad * 128;
+    x.b_src[1] = ws + ob.off + (uint64_t)s * p.bpad * 128;
+    x.a_src = x.b_src[side] + (uint64_t)rt * kTileM * 128;
+    const float* rinv = reinterpret_cast<const float*>(ws + p.rinv_off) + ((uint64_t)(q * p.S + s) * 2) * p.bpad;
+    x.colvec0[0] = rinv; x.colvec0[1] = rinv + p.bpad;
+    x.colvec1[0] = x.colvec1[1] = nullptr;
+    x.ntc = (p.b + BN - 1) / BN;
+    const int nct = 2 * x.ntc;
+    x.ct_begin = (int)((long)nct * sp / nsp);
+    x.ct_end = (int)((long)nct * (sp + 1) / nsp);
+    x.row0 = rt * kTileM; x.side = side; x.ncol_valid = p.b;
+    x.row_lo = p.seq0; x.row_hi = p.seq1;
+    x.q = q; x.s = s; x.c = sp;
+  } else {
+    const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM, nrt = t1 - t0;
+    const int rt = t0 + it % nrt;
+    const int c = it / nrt;
+    x.b_kstride = x.a_kstride = (uint64_t)p.Bpad * 128;
+    x.b_src[0] = x.b_src[1] = ws + p.xt_off + (uint64_t)c * p.kbFull * p.Bpad * 128;
+    x.a_src = x.b_src[0] + (uint64_t)rt * kTileM * 128;
+    x.colvec0[0] = x.colvec0[1] = reinterpret_cast<const float*>(ws + p.sq_off) + (uint64_t)c * p.Bpad;
+    x.colvec1[0] = x.colvec1[1] = reinterpret_cast<const float*>(ws + p.mintra_off) + (uint64_t)c * p.Bpad;
+    x.ntc = (p.B + BN - 1) / BN;
+    x.ct_begin = 0; x.ct_end = x.ntc;
+    x.row0 = rt * kTileM; x.side = 0; x.ncol_valid = p.B;
+    x.row_lo = p.seq0 * p.S; x.row_hi = p.seq1 * p.S;
+    x.q = 0; x.s = 0; x.c = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE, int BN, int KB, int SEQ>
+__global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws) {
+  using L = GramSmem<BN, KB>;
+  constexpr bool kIsNce = (MODE == NCE_FWD || MODE == NCE_BWD);
+  constexpr bool kBwd = (MODE == NCE_BWD || MODE == TMP_BWD);
+  constexpr bool kColVec = (MODE != NCE_FWD);
+  constexpr int kON = KB * 64;                       // UMMA #2 N = padded operand width
+  constexpr uint32_t kSCol = 0;                      // TMEM: S stages at columns [0, 2*BN)
+  constexpr uint32_t kOCol = 2 * BN;                 // TMEM: O accumulator at [2*BN, 2*BN + kON)
+  static_assert(2 * BN + kON <= kTmemCols, "TMEM budget");
+  static_assert(L::kDynamic <= 232448, "shared memory budget");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GramBars* bars = reinterpret_cast<GramBars*>(smem + L::kBarOff);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    for (int i = 0; i < kNumBStages; ++i) {
+      mbar_init(&bars->b_full[i], 1);
+      mbar_init(&bars->b_empty[i], kColVec ? 1 + 4 : 1);    // UMMA commit (+ one elected lane per epilogue warp)
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 128); }
+    for (int i = 0; i < kNumWStages; ++i) { mbar_init(&bars->w_full[i], 128); mbar_init(&bars->w_empty[i], 1); }
+    mbar_init(&bars->o_full, 1);
+    mbar_init(&bars->o_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  const int n_items = gram_num_items<MODE, BN, KB>(p);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t nb = 0, ni = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+        Item x;
+        gram_decode<MODE, BN, KB>(p, ws, it, x);
+        mbar_wait(&bars->a_empty, (ni & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->a_full, L::kABytes);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          tma_load_1d(smem + L::kAOff + kb * 16384, x.a_src + kb * x.a_kstride, 16384, &bars->a_full);
+        for (int ct = x.ct_begin; ct < x.ct_end; ++ct, ++nb) {
+          const uint32_t st = nb % kNumBStages;
+          const int cs = ct / x.ntc, tc = ct - cs * x.ntc;
+          mbar_wait(&bars->b_empty[st], ((nb / kNumBStages) & 1) ^ 1);
+          uint8_t* dst = smem + L::kBOff + st * L::kBStage;
+          uint32_t bytes = L::kBTile;
+          if (kColVec) bytes += (kIsNce ? 1 : 2) * BN * 4;
+          mbar_arrive_expect_tx(&bars->b_full[st], bytes);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_1d(dst + kb * (BN * 128), x.b_src[cs] + kb * x.b_kstride + (uint64_t)tc * BN * 128, BN * 128,
+                        &bars->b_full[st]);
+          if (kColVec) {
+            tma_load_1d(dst + L::kBTile, x.colvec0[cs] + tc * BN, BN * 4, &bars->b_full[st]);
+            if (!kIsNce) tma_load_1d(dst + L::kBTile + BN * 4, x.colvec1[cs] + tc * BN, BN * 4, &bars->b_full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== UMMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc(UMMA_BF16, 128, BN, 0, 0);     // S = A(K-major) * B(K-major)^T
+      constexpr uint32_t idesc2 = umma_idesc(UMMA_BF16, 128, kON, 0, 1);    // O += W(K-major) * B(MN-major)
+      const uint32_t a_addr = smem_u32(smem + L::kAOff);
+      uint32_t nb = 0, ni = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+        Item x;
+        gram_decode<MODE, BN, KB>(p, ws, it, x);
+        const int ksteps = kIsNce ? (p.ops[p.probs[x.q].opA].width + 15) / 16 : (p.D + 15) / 16;
+        mbar_wait(&bars->a_full, ni & 1);
+        const int ntiles = x.ct_end - x.ct_begin;
+        for (int t = 0; t <= ntiles; ++t) {
+          if (t < ntiles) {
+            // ---- UMMA #1 of tile t
+            const uint32_t n = nb + t, st = n % kNumBStages, ss = n & 1;
+            mbar_wait(&bars->b_full[st], (n / kNumBStages) & 1);
+            mbar_wait(&bars->s_empty[ss], ((n >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem + L::kBOff + st * L::kBStage);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t ko = (k >> 2) * 16384 + (k & 3) * 32;
+              const uint32_t kob = (k >> 2) * (BN * 128) + (k & 3) * 32;
+              umma_bf16(tmem + kSCol + ss * BN, umma_smem_desc(a_addr + ko, 16, 1024),
+                        umma_smem_desc(b_addr + kob, 16, 1024), idesc1, k > 0);
+            }
+            umma_commit(&bars->s_full[ss]);
+            if (!kBwd) umma_commit(&bars->b_empty[st]);
+          }
+          if (kBwd && t > 0) {
+            // ---- UMMA #2 of tile t-1 (issued after UMMA #1 of tile t so the tensor pipe never waits on the epilogue)
+            const uint32_t n = nb + t - 1, st = n % kNumBStages, wsg = n % kNumWStages;
+            if (t == 1) mbar_wait(&bars->o_empty, (ni & 1) ^ 1);
+            mbar_wait(&bars->w_full[wsg], (n / kNumWStages) & 1);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(smem + L::kWOff + wsg * L::kWStage);
+            const uint32_t b_addr = smem_u32(smem + L::kBOff + st * L::kBStage);
+#pragma unroll
+            for (int k = 0; k < BN / 16; ++k) {
+              umma_bf16(tmem + kOCol, umma_smem_desc(w_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                        umma_smem_desc(b_addr + k * 2048, BN * 128, 1024), idesc2, (t > 1) || (k > 0));
+            }
+            umma_commit(&bars->w_empty[wsg]);
+            umma_commit(&bars->b_empty[st]);
+          }
+        }
+        nb += ntiles;
+        umma_commit(&bars->a_empty);
+        if (kBwd) umma_commit(&bars->o_full);
+      }
+      // commits complete in issue order: once the last one has landed no arrival is still in flight
+      if (ni > 0) mbar_wait(&bars->a_empty, (ni - 1) & 1);
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+    const int trow = quarter * 32 + lane;             // row within the tile == TMEM lane
+    const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+    uint32_t nb = 0, ni = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+      Item x;
+      gram_decode<MODE, BN, KB>(p, ws, it, x);
+      const int row = x.row0 + trow;                  // row within side (NCE: sequence index k) / tensor (TMP: i)
+      const bool row_ok = row < x.ncol_valid && row >= x.row_lo && row < x.row_hi;
+      float rowacc = 0.f;                             // NCE_FWD: row sum; TMP: rho_i
+      float ck = 0.f, n_i = 0.f, m_ii = 0.f, hinge_acc = 0.f;
+      int cnt_i = 0;
+      if (MODE == NCE_BWD && row_ok) ck = x.colvec0[x.side][row];
+      if (!kIsNce && row_ok) { n_i = x.colvec0[0][row]; m_ii = x.colvec1[0][row]; }
+      constexpr int SQ = SEQ > 0 ? SEQ : 1;
+      const float inv_cnt = 1.f / (float)(SQ * SQ);
+      const float coef_scale = -1.f / ((float)p.b * (float)(p.b - 1) * (float)(SQ * SQ));
+      const int seq_i = row / SQ;
+      const int ntiles = x.ct_end - x.ct_begin;
+      for (int t = 0; t < ntiles; ++t) {
+        const uint32_t n = nb + t, st = n % kNumBStages, ss = n & 1, wsg = n % kNumWStages;
+        const int ct = x.ct_begin + t;
+        const int cs = ct / x.ntc, tc = ct - cs * x.ntc;
+        const int col0 = tc * BN;                     // first column (within side) of this tile
+        const float* cv = reinterpret_cast<const float*>(smem + L::kBOff + st * L::kBStage + L::kBTile);
+        uint8_t* wbuf = smem + L::kWOff + wsg * L::kWStage;
+        if (kColVec) mbar_wait(&bars->b_full[st], (n / kNumBStages) & 1);
+        mbar_wait(&bars->s_full[ss], (n >> 1) & 1);
+        tc_fence_after();
+        if (kBwd) mbar_wait(&bars->w_empty[wsg], ((n / kNumWStages) & 1) ^ 1);
+        const bool tail = col0 + BN > x.ncol_valid;
+        const bool diag = kIsNce ? (cs == x.side && col0 < x.row0 + kTileM && col0 + BN > x.row0)
+                                 : (col0 < x.row0 + kTileM && col0 + BN > x.row0);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          float v[32];
+          tmem_ld32(tmem + tlane + kSCol + ss * BN + ch * 32, v);
+          tmem_ld_wait();
+          const int cbase = col0 + ch * 32;           // column (within side) of v[0]
+          if (kIsNce) {
+            // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]);
+            if (MODE == NCE_BWD) {
+              // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 cj = *reinterpret_cast<const float4*>(cv + ch * 32 + j);
+                v[j] *= ck + cj.x; v[j + 1] *= ck + cj.y; v[j + 2] *= ck + cj.z; v[j + 3] *= ck + cj.w;
+              }
+            }
+            if (diag || tail) {      // j != k (loss.py:35-44) and the zero-padded tail columns
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = cbase + j;
+                if ((diag && col == row) || col >= x.ncol_valid) v[j] = 0.f;
+              }
+            }
+            if (MODE == NCE_FWD) {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
+              rowacc += (s0 + s1) + (s2 + s3);
+            }
+          } else {
+            // ---------------- temporal: delta_ij, S x S block means, hinge, r_ij
+            float nj[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(cv + ch * 32 + j);
+              nj[j] = t4.x; nj[j + 1] = t4.y; nj[j + 2] = t4.z; nj[j + 3] = t4.w;
+            }
+#pragma unroll
+            for (int g0 = 0; g0 < 32; g0 += SEQ) {
+              float gsum = 0.f;
+#pragma unroll
+              for (int j = 0; j < SEQ; ++j) {
+                const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], n_i + nj[g0 + j]), 0.f);     // cdist mm form
+                const float rs = d2 > 0.f ? rsqrt_approx(d2) : 0.f;   // 1/delta; 0 where delta == 0
+                v[g0 + j] = rs;
+                gsum = fmaf(d2, rs, gsum);                            // delta = d2 / delta
+              }
+#pragma unroll
+              for (int o = 1; o < SEQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+              const int colg = cbase + g0;
+              const float m_ij = gsum * inv_cnt;
+              const float m_jj = cv[BN + ch * 32 + g0];
+              const bool pair_ok = row_ok && colg < x.ncol_valid && (colg / SQ) != seq_i;
+              const float h = m_ii - m_ij + p.margin;
+              const bool a_ij = pair_ok && (h >= 0.f);                       // hinge active at equality
+              const bool a_ji = pair_ok && (m_jj - m_ij + p.margin >= 0.f);
+              if ((lane & (SEQ - 1)) == 0 && a_ij) { hinge_acc += h; cnt_i += 1; }
+              const float coef = coef_scale * ((a_ij ? 1.f : 0.f) + (a_ji ? 1.f : 0.f));
+#pragma unroll
+              for (int j = 0; j < SEQ; ++j) v[g0 + j] *= coef;
+            }
+          }
+          if (kBwd) {
+            // ---------------- W tile: bf16, K-major SWIZZLE_128B, row = trow (A operand of UMMA #2)
+            const int kb2 = (ch * 32) / 64, c0 = ((ch * 32) % 64) / 8;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 pk;
+              pk.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]);
+              pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+              pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
+              pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+              if (!kIsNce) {
+                // rho_i = sum_j r_ij must use the same rounded r_ij the tensor core multiplies with x_j
+                rowacc += (__uint_as_float(pk.x << 16) + __uint_as_float(pk.x & 0xffff0000u)) +
+                          (__uint_as_float(pk.y << 16) + __uint_as_float(pk.y & 0xffff0000u)) +
+                          (__uint_as_float(pk.z << 16) + __uint_as_float(pk.z & 0xffff0000u)) +
+                          (__uint_as_float(pk.w << 16) + __uint_as_float(pk.w & 0xffff0000u));
+              }
+              *reinterpret_cast<uint4*>(wbuf + kb2 * 16384 + swz128(trow, c0 + c)) = pk;
+            }
+          }
+        }
+        // S stage drained (all tcgen05.ld of this thread completed above)
+        tc_fence_before();
+        mbar_arrive(&bars->s_empty[ss]);
+        if (kBwd) {
+          fence_proxy_async_smem();
+          mbar_arrive(&bars->w_full[wsg]);
+        }
+        if (kColVec) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->b_empty[st]);
+        }
+      }
+      nb += ntiles;
+
+      // ---------------- item epilogue
+      if (MODE == NCE_FWD) {
+        float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) +
+                       ((((uint64_t)x.c * p.nProb + x.q) * p.S + x.s) * 2 + x.side) * p.bpad;
+        if (row < p.bpad) rpart[row] = row_ok ? rowacc : 0.f;
+      }
+      if (kBwd) {
+        mbar_wait(&bars->o_full, ni & 1);
+        tc_fence_after();
+        float* out;
+        if (kIsNce) {
+          out = reinterpret_cast<float*>(ws + p.probs[x.q].dz_off) +
+                ((uint64_t)x.side * p.S * p.bpad + (uint64_t)x.s * p.bpad + row) * kON;
+        } else {
+          out = reinterpret_cast<float*>(ws + p.dx_off) + ((uint64_t)x.c * p.Bpad + row) * kON;
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < kON / 32; ++ch) {
+          float v[32];
+          tmem_ld32(tmem + tlane + kOCol + ch * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(out + ch * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->o_empty);
+      }
+      if (!kIsNce) {
+        if (kBwd && row_ok) reinterpret_cast<float*>(ws + p.rho_off)[(uint64_t)x.c * p.Bpad + row] = rowacc;
+        if (row_ok && (lane & (SQ - 1)) == 0)
+          reinterpret_cast<int32_t*>(ws + p.cnt_off)[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
+        // hinge partial of this item: 128 threads -> one float
+        float hs = warp_sum(hinge_acc);
+        if (lane == 0) bars->red[quarter] = hs;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (trow == 0) {
+          const int t0 = (p.seq0 * p.S) / kTileM;
+          const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
+          const int slot = x.c * nrt + (x.row0 / kTileM - t0);
+          reinterpret_cast<float*>(ws + p.part3_off)[slot] =
+              ((bars->red[0] + bars->red[1]) + (bars->red[2] + bars->red[3])) / ((float)p.b * (float)(p.b - 1));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace fb

@@ -1,0 +1,171 @@
+// Host-side plan: problem topology (loss.py:162-209 loop structure) and workspace layout in HBM.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/focal_b200.h"
+
+namespace fb {
+
+constexpr int kMaxM = FOCAL_MAX_MODALITIES;
+constexpr int kMaxT = 2 * kMaxM;                         // feature tensors: t = view * M + mod
+constexpr int kMaxOps = 6 * kMaxM;                       // shared + private (+ full when noPrivate) per tensor
+constexpr int kMaxProb = kMaxM * kMaxM;                  // M^2 InfoNCE problems
+constexpr int kMaxOrth = 2 * (kMaxM + kMaxM * (kMaxM - 1) / 2);
+constexpr int kTileM = 128;                              // rows of a Gram tile (UMMA M, TMEM lanes)
+constexpr int kKBlk = 64;                                // bf16 elements per 128-byte swizzle row
+
+struct OpDesc {          // one normalised InfoNCE operand = a column slice of one feature tensor
+  int32_t tensor, col0, width, kb;   // kb = ceil(width / 64) K blocks
+  uint64_t off;                      // bytes from ws base: bf16 [kb][S*bpad][64], position-major rows, swizzled
+};
+struct ProbDesc {        // one InfoNCE problem: z = [opA ; opB] per position (loss.py:66-73)
+  int32_t opA, opB, kind;            // kind 0 = shared (modal matching), 1 = private (transformation invariant)
+  float weight;
+  uint64_t dz_off;                   // fp32 [2][S*bpad][kb*64] operand-gradient accumulators
+};
+struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
+  int32_t tu, cu, tv, cv, width;
+};
+
+struct Plan {
+  // dims
+  int32_t B, S, M, D, d, b, bpad, Bpad, nT, nOps, nProb, nOrth, kbFull, seq0, seq1, need_grad, terms, num_sms;
+  int32_t nsplit_fwd;                                   // column splits of the row-sum pass
+  float T, margin, w_shared, w_private, w_orth, w_rank;
+  float alpha;                                          // sqrt(log2(e)/T): operand pre-scale, Gram = log2-domain logit
+  OpDesc ops[kMaxOps];
+  ProbDesc probs[kMaxProb];
+  OrthDesc orth[kMaxOrth];
+  // workspace offsets (bytes)
+  uint64_t xt_off;      // bf16 [2M][kbFull][Bpad][64] temporal operands (natural row order, swizzled)
+  uint64_t sq_off;      // fp32 [2M][Bpad] squared norms of the rounded temporal operands
+  uint64_t mintra_off;  // fp32 [2M][Bpad] m_II of the row's sequence (exact fp32)
+  uint64_t rpart_off;   // fp32 [nsplit_fwd][nProb][S][2][bpad]
+  uint64_t rsum_off;    // fp32 [nProb][S][2][bpad]
+  uint64_t rinv_off;    // fp32 [nProb][S][2][bpad]
+  uint64_t dx_off;      // fp32 [2M][Bpad][kbFull*64]
+  uint64_t rho_off;     // fp32 [2M][Bpad] sum_j r_ij
+  uint64_t cnt_off;     // int32 [2M][bpad]  active hinges per sequence
+  uint64_t part1_off;   // fp32 [nblk1][4]  prologue partials: orth, pos_shared, pos_private
+  uint64_t part2_off;   // fp32 [nblk2][2]  log-row-sum partials: shared, private
+  uint64_t part3_off;   // fp32 [nitems3]   hinge partials
+  uint64_t lossd_off;   // double [8]
+  uint64_t dz_off, dz_bytes, dx_bytes;
+  uint64_t total_bytes;
+  int32_t nblk1, nblk2, nitems3;
+};
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// rows of the prologue / finalize kernels handled per 128-thread block (one warp per row)
+constexpr int kRowsPerBlock = 4;
+
+inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
+  std::memset(&p, 0, sizeof(p));
+  if (c.B <= 0 || c.S <= 0 || c.M <= 0 || c.D <= 0) return FOCAL_EINVAL;
+  if (c.M < 1 || c.M > kMaxM) return FOCAL_ESHAPE;
+  if (c.B % c.S) return FOCAL_ESHAPE;                    // loss.py:154 reshape(-1, S, D) would raise
+  if (c.S > 32 || (c.S & (c.S - 1))) return FOCAL_ESHAPE;  // sequence = power-of-two rows of one warp
+  if (c.D < 2 || c.D > 256) return FOCAL_ESHAPE;
+  if (!(c.temperature > 0.f)) return FOCAL_EINVAL;
+  if (c.precision != FOCAL_PREC_BF16) return FOCAL_EINVAL;
+  p.B = c.B; p.S = c.S; p.M = c.M; p.D = c.D; p.d = c.D / 2;
+  p.b = c.B / c.S;
+  p.bpad = (int32_t)align_up(p.b, kTileM);
+  p.Bpad = (int32_t)align_up(p.B, kTileM);
+  p.nT = 2 * c.M;
+  p.kbFull = (c.D + kKBlk - 1) / kKBlk;
+  p.seq0 = c.seq_begin; p.seq1 = c.seq_end;
+  if (p.seq0 < 0 || p.seq1 > p.b || p.seq0 >= p.seq1) return FOCAL_EINVAL;
+  p.need_grad = c.need_grad; p.terms = c.terms ? c.terms : FOCAL_TERM_ALL;
+  p.num_sms = num_sms;
+  p.T = c.temperature; p.margin = c.margin;
+  p.w_shared = c.w_shared; p.w_private = c.w_private; p.w_orth = c.w_orth; p.w_rank = c.w_rank;
+  p.alpha = sqrtf(1.4426950408889634f / c.temperature);
+  // log2-domain logits are bounded by log2(e)/T; without a running max the row sum must fit fp32
+  if (1.4426950408889634f / c.temperature > 96.f) return FOCAL_ESHAPE;
+
+  // ---- operands: per tensor [shared, private] (+ full when noPrivate)
+  const int M = c.M, d = p.d;
+  auto op_shared = [&](int t) { return 2 * t; };
+  auto op_private = [&](int t) { return 2 * t + 1; };
+  auto op_full = [&](int t) { return 2 * p.nT + t; };
+  for (int t = 0; t < p.nT; ++t) {
+    p.ops[op_shared(t)] = OpDesc{t, 0, d, (d + kKBlk - 1) / kKBlk, 0};
+    p.ops[op_private(t)] = OpDesc{t, d, d, (d + kKBlk - 1) / kKBlk, 0};
+  }
+  p.nOps = 2 * p.nT;
+  if (c.no_private) {
+    for (int t = 0; t < p.nT; ++t) p.ops[op_full(t)] = OpDesc{t, 0, c.D, p.kbFull, 0};
+    p.nOps = 3 * p.nT;
+  }
+  // ---- problems in reference order (loss.py:162-186)
+  int np = 0;
+  for (int v = 0; v < 2; ++v)
+    for (int i = 0; i < M; ++i)
+      for (int j = i + 1; j < M; ++j) {
+        int ta = v * M + i, tb = v * M + j;
+        p.probs[np++] = ProbDesc{c.no_private ? op_full(ta) : op_shared(ta), c.no_private ? op_full(tb) : op_shared(tb),
+                                 0, c.w_shared, 0};
+      }
+  for (int m = 0; m < M; ++m) p.probs[np++] = ProbDesc{op_private(m), op_private(M + m), 1, c.w_private, 0};
+  p.nProb = np;
+  // ---- orthogonality pairs (loss.py:195-209)
+  int no = 0;
+  for (int v = 0; v < 2; ++v)
+    for (int i = 0; i < M; ++i) {
+      int t = v * M + i;
+      p.orth[no++] = OrthDesc{t, 0, t, d, d};
+      for (int j = i + 1; j < M; ++j) p.orth[no++] = OrthDesc{t, d, v * M + j, d, d};
+    }
+  p.nOrth = no;
+
+  // ---- column split of the row-sum pass: pick the split with the best wave quantisation
+  {
+    const int nt = p.bpad / kTileM;
+    const long items = (long)p.nProb * p.S * 2 * nt;   // upper bound (all row tiles)
+    int best = 1; double best_eff = 0;
+    for (int sp = 1; sp <= 4; ++sp) {
+      if (2 * nt % sp) continue;
+      long it = items * sp;
+      long waves = (it + num_sms - 1) / num_sms;
+      double eff = (double)it / (double)(waves * num_sms);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
+    }
+    p.nsplit_fwd = best;
+  }
+
+  // ---- workspace
+  uint64_t off = 0;
+  auto take = [&](uint64_t bytes) { uint64_t o = off; off = align_up(off + bytes, 1024); return o; };
+  const uint64_t rowsNce = (uint64_t)p.S * p.bpad;
+  for (int o = 0; o < p.nOps; ++o) p.ops[o].off = take((uint64_t)p.ops[o].kb * rowsNce * 128);
+  p.xt_off = take((uint64_t)p.nT * p.kbFull * p.Bpad * 128);
+  p.sq_off = take((uint64_t)p.nT * p.Bpad * 4);
+  p.mintra_off = take((uint64_t)p.nT * p.Bpad * 4);
+  const uint64_t rs = (uint64_t)p.nProb * p.S * 2 * p.bpad * 4;
+  p.rpart_off = take(rs * p.nsplit_fwd);
+  p.rsum_off = take(rs);
+  p.rinv_off = take(rs);
+  p.dz_off = off;
+  for (int q = 0; q < p.nProb; ++q)
+    p.probs[q].dz_off = take((uint64_t)2 * rowsNce * p.ops[p.probs[q].opA].kb * kKBlk * 4);
+  p.dz_bytes = off - p.dz_off;
+  p.dx_bytes = (uint64_t)p.nT * p.Bpad * p.kbFull * kKBlk * 4;
+  p.dx_off = take(p.dx_bytes);
+  p.rho_off = take((uint64_t)p.nT * p.Bpad * 4);
+  p.cnt_off = take((uint64_t)p.nT * p.bpad * 4);
+  p.nblk1 = (p.B + kRowsPerBlock - 1) / kRowsPerBlock;
+  p.nblk2 = (int32_t)((rowsNce * 2 * p.nProb + 255) / 256);
+  p.nitems3 = p.nT * (p.Bpad / kTileM);
+  p.part1_off = take((uint64_t)p.nblk1 * 4 * 4);
+  p.part2_off = take((uint64_t)p.nblk2 * 2 * 4);
+  p.part3_off = take((uint64_t)p.nitems3 * 4);
+  p.lossd_off = take(8 * 8);
+  p.total_bytes = off;
+  return FOCAL_OK;
+}
+
+}  // namespace fb

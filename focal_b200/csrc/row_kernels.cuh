@@ -1,0 +1,450 @@
+// Single-pass row kernels (HBM-bound): prologue, intra-sequence distances, log-row-sums, gradient assembly,
+// loss reduction.  One warp per row, rows staged in shared memory, warp-shuffle reductions, coalesced stores.
+#pragma once
+#include "plan.h"
+#include "ptx.cuh"
+
+namespace fb {
+
+struct FeatPtrs {
+  const float* x[kMaxT];
+};
+struct GradPtrs {
+  float* g[kMaxT];
+};
+
+constexpr float kNceEps = 1e-8f;    // nn.CosineSimilarity eps (loss.py:15)
+constexpr float kOrthEps = 1e-12f;  // cosine_embedding_loss EPSILON (loss.py:16)
+
+// Cooperative (one warp) load of the nT rows `i` into shared memory: xs[t * D + c].
+__device__ __forceinline__ void load_rows(const Plan& p, const FeatPtrs& f, int i, float* xs, int lane) {
+  const int D = p.D;
+  if ((D & 3) == 0) {
+    const int nv = D >> 2;
+    for (int t = 0; t < p.nT; ++t) {
+      const float4* src = reinterpret_cast<const float4*>(f.x[t] + (size_t)i * D);
+      float4* dst = reinterpret_cast<float4*>(xs + t * D);
+      for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
+    }
+  } else {
+    for (int t = 0; t < p.nT; ++t)
+      for (int c = lane; c < D; c += 32) xs[t * D + c] = __ldg(f.x[t] + (size_t)i * D + c);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ float warp_dot(const float* a, const float* b, int n, int lane) {
+  float s = 0.f;
+  for (int c = lane; c < n; c += 32) s = fmaf(a[c], b[c], s);
+  return warp_sum(s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K0: zero the padding rows of the operand tiles and per-row vectors (only launched when padding exists)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void zero_pad_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws) {
+  const int padN = p.bpad - p.b;      // per (op, kb, s)
+  const int padT = p.Bpad - p.B;      // per (tensor, kb)
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  if (padN > 0) {
+    for (int o = 0; o < p.nOps; ++o) {
+      const long chunks = (long)p.ops[o].kb * p.S * padN * 8;
+      for (long e = tid; e < chunks; e += stride) {
+        const int c = e & 7;
+        long r = e >> 3;
+        const int pr = r % padN; r /= padN;
+        const int s = r % p.S; r /= p.S;
+        const int kb = (int)r;
+        const uint64_t row = (uint64_t)s * p.bpad + p.b + pr;
+        *reinterpret_cast<uint4*>(ws + p.ops[o].off + ((uint64_t)kb * p.S * p.bpad + row) * 128 + c * 16) = z;
+      }
+    }
+    float* rinv = reinterpret_cast<float*>(ws + p.rinv_off);
+    float* rsum = reinterpret_cast<float*>(ws + p.rsum_off);
+    const long nr = (long)p.nProb * p.S * 2 * padN;
+    for (long e = tid; e < nr; e += stride) {
+      const long grp = e / padN;
+      const int pr = e % padN;
+      rinv[grp * p.bpad + p.b + pr] = 0.f;
+      rsum[grp * p.bpad + p.b + pr] = 1.f;
+    }
+  }
+  if (padT > 0) {
+    const long chunks = (long)p.nT * p.kbFull * padT * 8;
+    for (long e = tid; e < chunks; e += stride) {
+      const int c = e & 7;
+      long r = e >> 3;
+      const int pr = r % padT; r /= padT;
+      const uint64_t tk = r;      // t * kbFull + kb
+      *reinterpret_cast<uint4*>(ws + p.xt_off + (tk * p.Bpad + p.B + pr) * 128 + c * 16) = z;
+    }
+    float* sq = reinterpret_cast<float*>(ws + p.sq_off);
+    float* mi = reinterpret_cast<float*>(ws + p.mintra_off);
+    for (long e = tid; e < (long)p.nT * padT; e += stride) {
+      const long t = e / padT;
+      const int pr = e % padT;
+      sq[t * p.Bpad + p.B + pr] = 0.f;
+      mi[t * p.Bpad + p.B + pr] = 0.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: prologue.  One warp per row i of the batch, all 2M tensors of that row.
+//   - normalised, pre-scaled bf16 InfoNCE operands (position-major rows, swizzled 128-B K blocks)
+//   - bf16 temporal operands (natural rows) + squared norms of the ROUNDED values
+//   - owned rows: positive-pair logits (loss.py:75-79) and orthogonality terms (loss.py:89-106)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __grid_constant__ Plan p,
+                                                                      const __grid_constant__ FeatPtrs f,
+                                                                      uint8_t* __restrict__ ws) {
+  extern __shared__ float smem_f[];
+  __shared__ float red[kRowsPerBlock][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kRowsPerBlock + warp;
+  float* xs = smem_f + (size_t)warp * p.nT * p.D;
+  float acc_orth = 0.f, acc_ps = 0.f, acc_pp = 0.f;
+  if (i < p.B) {
+    load_rows(p, f, i, xs, lane);
+    const int D = p.D, d = p.d;
+    const int I = i / p.S, s = i % p.S;
+    const uint64_t rowN = (uint64_t)s * p.bpad + I;          // position-major row of the InfoNCE operands
+    const uint64_t rowsNce = (uint64_t)p.S * p.bpad;
+
+    // squared norms of the shared half, the private half and the odd leftover column
+    float ssh[kMaxT], spr[kMaxT], sfull[kMaxT];
+    for (int t = 0; t < p.nT; ++t) {
+      const float* x = xs + t * D;
+      float a = 0.f, b = 0.f, c = 0.f;
+      for (int k = lane; k < d; k += 32) { a = fmaf(x[k], x[k], a); b = fmaf(x[d + k], x[d + k], b); }
+      if ((D & 1) && lane == 0) c = x[D - 1] * x[D - 1];
+      a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+      ssh[t] = a; spr[t] = b; sfull[t] = a + b + c;
+    }
+
+    // ---- InfoNCE operands
+    if (p.terms & FOCAL_TERM_NCE) {
+      for (int o = 0; o < p.nOps; ++o) {
+        const OpDesc& op = p.ops[o];
+        const float ss = (op.width == D) ? sfull[op.tensor] : (op.col0 == 0 ? ssh[op.tensor] : spr[op.tensor]);
+        const float scale = p.alpha / fmaxf(sqrtf(ss), kNceEps);
+        const float* x = xs + op.tensor * D + op.col0;
+        for (int kb = 0; kb < op.kb; ++kb) {
+          const int e = kb * 64 + 2 * lane;
+          const float v0 = (e < op.width) ? x[e] * scale : 0.f;
+          const float v1 = (e + 1 < op.width) ? x[e + 1] * scale : 0.f;
+          uint8_t* dst = ws + op.off + ((uint64_t)kb * rowsNce + rowN) * 128;
+          const uint32_t ch = lane >> 2;                       // 16-byte chunk of the 128-byte row
+          *reinterpret_cast<uint32_t*>(dst + ((ch ^ (uint32_t)(rowN & 7)) << 4) + (lane & 3) * 4) = pack_bf16x2(v0, v1);
+        }
+      }
+    }
+    // ---- temporal operands
+    if (p.terms & FOCAL_TERM_TEMPORAL) {
+      for (int t = 0; t < p.nT; ++t) {
+        const float* x = xs + t * D;
+        float sq = 0.f;
+        for (int kb = 0; kb < p.kbFull; ++kb) {
+          const int e = kb * 64 + 2 * lane;
+          const float v0 = (e < D) ? x[e] : 0.f;
+          const float v1 = (e + 1 < D) ? x[e + 1] : 0.f;
+          const uint32_t pk = pack_bf16x2(v0, v1);
+          const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+          sq = fmaf(r0, r0, fmaf(r1, r1, sq));
+          uint8_t* dst = ws + p.xt_off + (((uint64_t)t * p.kbFull + kb) * p.Bpad + i) * 128;
+          const uint32_t ch = lane >> 2;
+          *reinterpret_cast<uint32_t*>(dst + ((ch ^ (uint32_t)(i & 7)) << 4) + (lane & 3) * 4) = pk;
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
+      }
+    }
+    // ---- loss terms of the owned rows
+    if (I >= p.seq0 && I < p.seq1) {
+      if (p.terms & FOCAL_TERM_NCE) {
+        const float sc = -2.f / (p.T * (float)p.S * (float)(2 * p.b));      // -2 cos / (T S N)
+        for (int q = 0; q < p.nProb; ++q) {
+          const OpDesc& a = p.ops[p.probs[q].opA];
+          const OpDesc& b = p.ops[p.probs[q].opB];
+          const float dot = warp_dot(xs + a.tensor * D + a.col0, xs + b.tensor * D + b.col0, a.width, lane);
+          const float sa = (a.width == D) ? sfull[a.tensor] : (a.col0 == 0 ? ssh[a.tensor] : spr[a.tensor]);
+          const float sb = (b.width == D) ? sfull[b.tensor] : (b.col0 == 0 ? ssh[b.tensor] : spr[b.tensor]);
+          const float cs = dot / (fmaxf(sqrtf(sa), kNceEps) * fmaxf(sqrtf(sb), kNceEps));
+          if (p.probs[q].kind == 0) acc_ps += sc * cs; else acc_pp += sc * cs;
+        }
+      }
+      if (p.terms & FOCAL_TERM_ORTH) {
+        for (int k = 0; k < p.nOrth; ++k) {
+          const OrthDesc& od = p.orth[k];
+          const float dot = warp_dot(xs + od.tu * D + od.cu, xs + od.tv * D + od.cv, od.width, lane);
+          const float nu = (od.cu == 0 ? ssh[od.tu] : spr[od.tu]) + kOrthEps;
+          const float nv = (od.cv == 0 ? ssh[od.tv] : spr[od.tv]) + kOrthEps;
+          const float cs = dot / sqrtf(nu * nv);
+          acc_orth += fmaxf(cs, 0.f);
+        }
+      }
+    }
+  }
+  if (lane == 0) { red[warp][0] = acc_orth; red[warp][1] = acc_ps; red[warp][2] = acc_pp; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int w = 0; w < kRowsPerBlock; ++w) s += red[w][threadIdx.x];
+    if (threadIdx.x == 0) s /= (float)p.B;
+    reinterpret_cast<float*>(ws + p.part1_off)[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1b: exact fp32 intra-sequence mean distance m_II (loss.py:118-124, block diagonal of the block means).
+// One warp per (tensor, sequence); written per row so the Gram kernel can TMA it as a column vector.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan p, const __grid_constant__ FeatPtrs f,
+                                                    uint8_t* __restrict__ ws) {
+  const int lane = threadIdx.x & 31;
+  const long w = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= (long)p.nT * p.b) return;
+  const int t = (int)(w / p.b), I = (int)(w % p.b);
+  const int S = p.S, D = p.D;
+  const float* x = f.x[t] + (size_t)I * S * D;
+  float tot = 0.f;
+  for (int a = 0; a < S; ++a)
+    for (int b2 = a + 1; b2 < S; ++b2) {
+      float d2 = 0.f;
+      for (int c = lane; c < D; c += 32) {
+        const float df = __ldg(x + a * D + c) - __ldg(x + b2 * D + c);
+        d2 = fmaf(df, df, d2);
+      }
+      d2 = warp_sum(d2);
+      tot += sqrtf(d2);
+    }
+  const float m = 2.f * tot / (float)(S * S - S);
+  float* mi = reinterpret_cast<float*>(ws + p.mintra_off) + (uint64_t)t * p.Bpad + (uint64_t)I * S;
+  for (int a = lane; a < S; a += 32) mi[a] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2r: reduce the column-split row sums of the owned rows, publish r, 1/r and the log-sum partials.
+// all_rows != 0: only rebuild 1/r for every valid row from r (after the multi-GPU exchange of r).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws,
+                                                      int all_rows) {
+  __shared__ float red[8][2];
+  const long n = (long)p.nProb * p.S * 2 * p.bpad;
+  const long e = (long)blockIdx.x * 256 + threadIdx.x;
+  float ls = 0.f, lp = 0.f;
+  if (e < n) {
+    const int k = (int)(e % p.bpad);
+    const int q = (int)(e / ((long)p.S * 2 * p.bpad));
+    float* rsum = reinterpret_cast<float*>(ws + p.rsum_off);
+    float* rinv = reinterpret_cast<float*>(ws + p.rinv_off);
+    if (all_rows) {
+      if (k < p.b) rinv[e] = 1.f / rsum[e];
+    } else if (k >= p.seq0 && k < p.seq1) {
+      const float* rp = reinterpret_cast<const float*>(ws + p.rpart_off);
+      float r = 0.f;
+      for (int sp = 0; sp < p.nsplit_fwd; ++sp) r += rp[(long)sp * n + e];
+      rsum[e] = r;
+      rinv[e] = 1.f / r;
+      const float lg = logf(r) / ((float)p.S * (float)(2 * p.b));          // ln sum_{j != k} exp(s_kj) / (S N)
+      if (p.probs[q].kind == 0) ls = lg; else lp = lg;
+    }
+  }
+  if (!all_rows) {
+    ls = warp_sum(ls); lp = warp_sum(lp);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = ls; red[threadIdx.x >> 5][1] = lp; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+      reinterpret_cast<float*>(ws + p.part2_off)[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: gradient assembly.  One warp per owned row i; everything that is O(B D) happens here in fp32:
+//   InfoNCE: d/dz of the normalisation (I - zh zh^T)/n applied to the accumulated W Z_J, positive-pair term
+//   temporal: x_i rho_i - (R X)_i  +  exact intra-sequence part
+//   orthogonality: closed form
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __grid_constant__ Plan p,
+                                                                      const __grid_constant__ FeatPtrs f,
+                                                                      const __grid_constant__ GradPtrs g,
+                                                                      const uint8_t* __restrict__ ws) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = p.seq0 * p.S + blockIdx.x * kRowsPerBlock + warp;
+  if (i >= p.seq1 * p.S) return;
+  const int D = p.D, d = p.d, S = p.S;
+  float* xs = smem_f + (size_t)warp * (2 * p.nT + 1) * D;
+  float* gs = xs + (size_t)p.nT * D;
+  float* tmp = gs + (size_t)p.nT * D;
+  load_rows(p, f, i, xs, lane);
+  for (int c = lane; c < p.nT * D; c += 32) gs[c] = 0.f;
+  const int I = i / S, s = i % S;
+  const uint64_t rowN = (uint64_t)s * p.bpad + I;
+
+  float ssh[kMaxT], spr[kMaxT], sfull[kMaxT];
+  for (int t = 0; t < p.nT; ++t) {
+    const float* x = xs + t * D;
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int k = lane; k < d; k += 32) { a = fmaf(x[k], x[k], a); b = fmaf(x[d + k], x[d + k], b); }
+    if ((D & 1) && lane == 0) c = x[D - 1] * x[D - 1];
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    ssh[t] = a; spr[t] = b; sfull[t] = a + b + c;
+  }
+  __syncwarp();
+
+  // ---- temporal
+  if ((p.terms & FOCAL_TERM_TEMPORAL) && p.b > 1 && S > 1) {
+    const float bb = (float)p.b * (float)(p.b - 1);
+    const int Dp = p.kbFull * 64;
+    for (int t = 0; t < p.nT; ++t) {
+      const float* x = xs + t * D;
+      const float rho = reinterpret_cast<const float*>(ws + p.rho_off)[(uint64_t)t * p.Bpad + i];
+      const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
+      const int cnt = reinterpret_cast<const int32_t*>(ws + p.cnt_off)[(uint64_t)t * p.bpad + I];
+      for (int c = lane; c < D; c += 32) gs[t * D + c] = p.w_rank * (x[c] * rho - y[c]);
+      // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
+      const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
+      if (cnt > 0) {
+        const float* base = f.x[t] + (size_t)I * S * D;
+        for (int j = 0; j < S; ++j) {
+          if (j == s) continue;
+          float d2 = 0.f;
+          for (int c = lane; c < D; c += 32) {
+            const float df = x[c] - __ldg(base + (size_t)j * D + c);
+            d2 = fmaf(df, df, d2);
+          }
+          d2 = warp_sum(d2);
+          if (d2 > 0.f) {
+            const float r = coef * rsqrtf(d2);
+            for (int c = lane; c < D; c += 32) gs[t * D + c] += r * (x[c] - __ldg(base + (size_t)j * D + c));
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- InfoNCE
+  if (p.terms & FOCAL_TERM_NCE) {
+    const float inv_tsn = 1.f / (p.T * (float)S * (float)(2 * p.b));
+    const float inv_alpha = 1.f / p.alpha;
+    for (int o = 0; o < p.nOps; ++o) {
+      const OpDesc& op = p.ops[o];
+      const int w = op.width, wp = op.kb * 64;
+      const float ss = (w == D) ? sfull[op.tensor] : (op.col0 == 0 ? ssh[op.tensor] : spr[op.tensor]);
+      const float nrm = fmaxf(sqrtf(ss), kNceEps);
+      const float* x = xs + op.tensor * D + op.col0;
+      bool used = false;
+      for (int c = lane; c < w; c += 32) tmp[c] = 0.f;
+      for (int q = 0; q < p.nProb; ++q) {
+        const ProbDesc& pr = p.probs[q];
+        int side = -1;
+        if (pr.opA == o) side = 0; else if (pr.opB == o) side = 1;
+        if (side < 0) continue;
+        used = true;
+        const OpDesc& po = p.ops[side == 0 ? pr.opB : pr.opA];            // partner operand: positive row p(k)
+        const float pss = (po.width == D) ? sfull[po.tensor] : (po.col0 == 0 ? ssh[po.tensor] : spr[po.tensor]);
+        const float pinv = 1.f / fmaxf(sqrtf(pss), kNceEps);
+        const float* px = xs + po.tensor * D + po.col0;
+        const float* acc = reinterpret_cast<const float*>(ws + pr.dz_off) +
+                           ((uint64_t)side * S * p.bpad + rowN) * wp;
+        const float wq = pr.weight * inv_tsn;
+        for (int c = lane; c < w; c += 32) tmp[c] += wq * (acc[c] * inv_alpha - 2.f * px[c] * pinv);
+      }
+      if (!used) continue;
+      // d zh / d z = (I - zh zh^T) / n
+      float dot = 0.f;
+      for (int c = lane; c < w; c += 32) dot = fmaf(tmp[c], x[c], dot);
+      dot = warp_sum(dot) / (nrm * nrm);
+      float* go = gs + op.tensor * D + op.col0;
+      for (int c = lane; c < w; c += 32) go[c] += (tmp[c] - dot * x[c]) / nrm;
+      __syncwarp();
+    }
+  }
+
+  // ---- orthogonality
+  if (p.terms & FOCAL_TERM_ORTH) {
+    for (int k = 0; k < p.nOrth; ++k) {
+      const OrthDesc& od = p.orth[k];
+      const float* u = xs + od.tu * D + od.cu;
+      const float* v = xs + od.tv * D + od.cv;
+      const float dot = warp_dot(u, v, od.width, lane);
+      const float nu = (od.cu == 0 ? ssh[od.tu] : spr[od.tu]) + kOrthEps;
+      const float nv = (od.cv == 0 ? ssh[od.tv] : spr[od.tv]) + kOrthEps;
+      const float den = sqrtf(nu * nv);
+      const float cs = dot / den;
+      if (cs >= 0.f) {                                    // clamp_min passes gradient at equality
+        const float a = p.w_orth / (float)p.B;
+        float* gu = gs + od.tu * D + od.cu;
+        float* gv = gs + od.tv * D + od.cv;
+        for (int c = lane; c < od.width; c += 32) {
+          const float uc = u[c], vc = v[c];
+          gu[c] += a * (vc / den - cs * uc / nu);
+          gv[c] += a * (uc / den - cs * vc / nv);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  for (int t = 0; t < p.nT; ++t) {
+    float* out = g.g[t] + (size_t)i * D;
+    for (int c = lane; c < D; c += 32) out[c] = gs[t * D + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: deterministic reduction of the per-block partials -> {total, shared, private, orth, temporal}
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws,
+                                                          float* __restrict__ loss5, int nce_blocks_valid,
+                                                          int temporal_nan) {
+  __shared__ double red[256];
+  const float* p1 = reinterpret_cast<const float*>(ws + p.part1_off);
+  const float* p2 = reinterpret_cast<const float*>(ws + p.part2_off);
+  const float* p3 = reinterpret_cast<const float*>(ws + p.part3_off);
+  double acc[4] = {0, 0, 0, 0};     // shared, private, orth, temporal
+  for (int k = threadIdx.x; k < p.nblk1; k += 256) {
+    acc[2] += p1[(size_t)k * 4 + 0];
+    acc[0] += p1[(size_t)k * 4 + 1];
+    acc[1] += p1[(size_t)k * 4 + 2];
+  }
+  if (p.terms & FOCAL_TERM_NCE)
+    for (int k = threadIdx.x; k < nce_blocks_valid; k += 256) {
+      acc[0] += p2[(size_t)k * 2 + 0];
+      acc[1] += p2[(size_t)k * 2 + 1];
+    }
+  if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_nan) {
+    const int t0 = (p.seq0 * p.S) / kTileM;
+    const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
+    for (int k = threadIdx.x; k < p.nT * nrt; k += 256) acc[3] += p3[k];
+  }
+  double out[4];
+  for (int a = 0; a < 4; ++a) {
+    red[threadIdx.x] = acc[a];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    out[a] = red[0];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (temporal_nan && (p.terms & FOCAL_TERM_TEMPORAL)) out[3] = __longlong_as_double(0x7ff8000000000000LL);
+    const double total = (double)p.w_shared * out[0] + (double)p.w_private * out[1] + (double)p.w_orth * out[2] +
+                         (double)p.w_rank * out[3];
+    loss5[0] = (float)total; loss5[1] = (float)out[0]; loss5[2] = (float)out[1];
+    loss5[3] = (float)out[2]; loss5[4] = (float)out[3];
+    double* ld = reinterpret_cast<double*>(ws + p.lossd_off);
+    ld[0] = total; ld[1] = out[0]; ld[2] = out[1]; ld[3] = out[2]; ld[4] = out[3];
+  }
+}
+
+}  // namespace fb

@@ -1,0 +1,200 @@
+"""Host side of the FOCAL loss hot path: shape checks, workspace, stage sequencing, row-sharded multi-GPU.
+
+Everything numerical happens in ``libfocal_b200.so`` (hand-written sm_100a kernels behind a C ABI,
+``include/focal_b200.h``); PyTorch is used for device memory, streams and ``torch.distributed`` only.
+There is no CPU path and no PyTorch fallback: inputs that are not CUDA tensors raise.
+
+Multi-GPU: R ranks each hold B/R rows (whole sequences) of every feature tensor.  The
+result equals the single-GPU loss on the rank-major concatenation; every rank gets the global scalar and
+d loss_global / d (its own rows).  Exchange steps: one all-gather of the raw features (operands are then
+rebuilt bit-identically on every rank), one all-gather of the InfoNCE row sums (because logits are
+symmetric, a rank that knows every row sum can form P_kj + P_jk for its own rows -- no gradient
+reduce-scatter is needed), one all-reduce of the five loss partials.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+
+
+@dataclass(frozen=True)
+class FocalHyper:
+    """What FOCALLoss reads from args (reference loss.py:11-23,149,163,211-215)."""
+    modalities: Tuple[str, ...]
+    seq_len: int
+    temperature: float
+    margin: float
+    w_shared: float
+    w_private: float
+    w_orth: float
+    w_rank: float
+    no_private: bool = False
+    terms: int = _cabi.FOCAL_TERM_ALL
+
+
+def shard_sequences(b: int, world: int, rank: int) -> Tuple[int, int]:
+    """Sequences owned by ``rank`` when b sequences are split rank-major into equal blocks."""
+    if b % world:
+        raise ValueError(f"{b} sequences do not split evenly over {world} ranks (need B % (S*R) == 0)")
+    per = b // world
+    return rank * per, (rank + 1) * per
+
+
+class CudaBackend:
+    """Runs the stages of include/focal_b200.h on the current CUDA stream."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _cabi.load()          # raises ImportError when the extension is missing -- no fallback
+        self._ws: Dict[tuple, Tuple[torch.Tensor, torch.Tensor, _cabi.FocalWsInfo]] = {}
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _cfg(self, hp: FocalHyper, B: int, D: int, need_grad: bool, seq: Tuple[int, int]) -> _cabi.FocalCfg:
+        return _cabi.FocalCfg(
+            B=B, S=hp.seq_len, M=len(hp.modalities), D=D, temperature=hp.temperature, margin=hp.margin,
+            w_shared=hp.w_shared, w_private=hp.w_private, w_orth=hp.w_orth, w_rank=hp.w_rank,
+            no_private=int(hp.no_private), need_grad=int(need_grad), terms=hp.terms,
+            precision=_cabi.FOCAL_PREC_BF16, seq_begin=seq[0], seq_end=seq[1], num_sms=0)
+
+    def workspace(self, cfg: _cabi.FocalCfg, device: torch.device):
+        key = (cfg.B, cfg.S, cfg.M, cfg.D, cfg.no_private, cfg.terms, cfg.precision, device.index)
+        hit = self._ws.get(key)
+        info = _cabi.FocalWsInfo()
+        rc = self.lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info))
+        if rc == _cabi.FOCAL_ESHAPE:
+            raise ValueError(f"focal_b200: {_cabi.strerror(rc)} (got B={cfg.B}, S={cfg.S}, M={cfg.M}, D={cfg.D}, "
+                             f"T={cfg.temperature})")
+        _cabi.check(rc, "focal_b200_workspace_info")
+        if hit is None or hit[0].numel() < info.total_bytes + 1024:
+            raw = torch.empty(info.total_bytes + 1024, dtype=torch.uint8, device=device)
+            off = (-raw.data_ptr()) % 1024
+            ws = raw[off: off + info.total_bytes]
+            self._ws[key] = (raw, ws, info)
+            hit = self._ws[key]
+        return hit[1], info
+
+    @staticmethod
+    def _view(ws: torch.Tensor, off: int, nbytes: int, dtype: torch.dtype, shape) -> torch.Tensor:
+        return ws[off: off + nbytes].view(dtype).view(*shape)
+
+    # -- the whole path -----------------------------------------------------------------------------
+    def run(self, hp: FocalHyper, feats: Sequence[torch.Tensor], seq: Tuple[int, int], need_grad: bool,
+            exchange_rowsum=None):
+        """feats: 2M full [B, D] fp32 CUDA tensors (view-major).  Returns (loss5 [5] fp32 device tensor with the
+        partial sums of the owned rows, grads: list of 2M [B, D] tensors with the owned rows filled, or None)."""
+        x0 = feats[0]
+        B, D = x0.shape
+        dev = x0.device
+        cfg = self._cfg(hp, B, D, need_grad, seq)
+        ws, info = self.workspace(cfg, dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        wsp, wsn = C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel())
+        fptr = _cabi.ptr_array([t.data_ptr() for t in feats])
+        loss5 = torch.empty(5, dtype=torch.float32, device=dev)
+        grads = [torch.empty_like(t) for t in feats] if need_grad else None
+        gptr = _cabi.ptr_array([g.data_ptr() for g in grads]) if need_grad else None
+        lib, ref = self.lib, C.byref(cfg)
+        if exchange_rowsum is None:
+            _cabi.check(lib.focal_b200_loss(ref, fptr, wsp, wsn, C.c_void_p(loss5.data_ptr()), gptr, stream),
+                        "focal_b200_loss")
+        else:
+            _cabi.check(lib.focal_b200_prologue(ref, fptr, wsp, wsn, stream), "focal_b200_prologue")
+            _cabi.check(lib.focal_b200_nce_rowsum(ref, wsp, wsn, stream), "focal_b200_nce_rowsum")
+            _cabi.check(lib.focal_b200_nce_lse(ref, wsp, wsn, 0, stream), "focal_b200_nce_lse")
+            if need_grad and (hp.terms & _cabi.FOCAL_TERM_NCE):
+                rs = self._view(ws, info.rowsum_off, info.rowsum_bytes, torch.float32,
+                                (info.n_problems, hp.seq_len, 2, info.bpad))
+                exchange_rowsum(rs)            # fills in the other ranks' rows (all-gather)
+                _cabi.check(lib.focal_b200_nce_lse(ref, wsp, wsn, 1, stream), "focal_b200_nce_lse(all)")
+            _cabi.check(lib.focal_b200_nce_grad(ref, wsp, wsn, stream), "focal_b200_nce_grad")
+            _cabi.check(lib.focal_b200_temporal(ref, wsp, wsn, stream), "focal_b200_temporal")
+            _cabi.check(lib.focal_b200_finalize(ref, fptr, wsp, wsn, C.c_void_p(loss5.data_ptr()), gptr, stream),
+                        "focal_b200_finalize")
+        return loss5, grads
+
+
+class FocalEngine:
+    """Validates inputs, shards rows over the process group, drives a backend."""
+
+    def __init__(self, hp: FocalHyper, process_group=None, backend=None):
+        self.hp = hp
+        self.group = process_group
+        self.backend = backend if backend is not None else CudaBackend()
+
+    # ---------------------------------------------------------------------------------------------
+    def _world(self) -> Tuple[int, int]:
+        if self.group is None:
+            return 1, 0
+        import torch.distributed as dist
+        return dist.get_world_size(self.group), dist.get_rank(self.group)
+
+    def _check(self, f1: Dict[str, torch.Tensor], f2: Dict[str, torch.Tensor]) -> List[torch.Tensor]:
+        hp = self.hp
+        feats: List[torch.Tensor] = []
+        for f in (f1, f2):
+            for m in hp.modalities:
+                if m not in f:
+                    raise KeyError(f"modality {m!r} missing from the feature dict")
+                feats.append(f[m])
+        x0 = feats[0]
+        if x0.dim() != 2:
+            raise ValueError(f"features must be [B, D], got {tuple(x0.shape)}")
+        for t in feats:
+            if t.shape != x0.shape or t.device != x0.device:
+                raise ValueError("all feature tensors must share shape and device")
+            if t.dtype != torch.float32:
+                raise TypeError(f"features must be float32 (the reference computes in fp32), got {t.dtype}")
+        if x0.shape[0] % hp.seq_len:
+            # same condition under which the reference's reshape(-1, seq_len, D) raises (loss.py:154)
+            raise ValueError(f"batch of {x0.shape[0]} rows is not a multiple of seq_len={hp.seq_len}")
+        if getattr(self.backend, "name", "") == "cuda" and not x0.is_cuda:
+            raise RuntimeError("focal_b200 runs on CUDA tensors only (no CPU fallback); move the features to the GPU")
+        return [t.detach().contiguous() for t in feats]
+
+    # ---------------------------------------------------------------------------------------------
+    def loss_and_grads(self, f1: Dict[str, torch.Tensor], f2: Dict[str, torch.Tensor], need_grad: bool):
+        """Returns (loss5, grads): loss5 = [total, shared, private, orth, temporal] of the GLOBAL batch,
+        grads = 2M tensors shaped like the (local) inputs, or None."""
+        hp = self.hp
+        local = self._check(f1, f2)
+        world, rank = self._world()
+        if world == 1:
+            b = local[0].shape[0] // hp.seq_len
+            loss5, grads = self.backend.run(hp, local, (0, b), need_grad, None)
+            return loss5, grads
+        import torch.distributed as dist
+        Bl, D = local[0].shape
+        nT = len(local)
+        # (1) all-gather the raw features: [R, 2M, Bl, D] -> per tensor [R*Bl, D] rank-major
+        mine = torch.stack(local, dim=0)
+        gathered = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        full = [gathered[:, t].reshape(world * Bl, D) for t in range(nT)]
+        b = world * Bl // hp.seq_len
+        seq = shard_sequences(b, world, rank)
+
+        def exchange_rowsum(rs: torch.Tensor):
+            # rs: [P, S, 2, bpad]; every rank computed the k-range [seq0, seq1) -- all-gather the slices
+            k0, k1 = seq
+            part = rs[..., k0:k1].contiguous()
+            allp = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
+            dist.all_gather_into_tensor(allp, part, group=self.group)
+            per = k1 - k0
+            for r in range(world):
+                if r != rank:
+                    rs[..., r * per:(r + 1) * per] = allp[r]
+
+        loss5, gfull = self.backend.run(hp, full, seq, need_grad, exchange_rowsum)
+        # (3) loss partials of the owned rows -> global loss on every rank
+        dist.all_reduce(loss5, op=dist.ReduceOp.SUM, group=self.group)
+        grads = None
+        if need_grad:
+            r0 = seq[0] * hp.seq_len
+            grads = [g[r0: r0 + Bl] for g in gfull]
+        return loss5, grads

@@ -1,0 +1,125 @@
+/*
+ * focal_b200 -- C ABI of the B200-native FOCAL contrastive-loss hot path.
+ *
+ * The reference (tomoyoshki/focal) has no FFI: its hot path is the Python class
+ * FOCALLoss (/root/reference/src/models/loss.py:8-218) called from
+ * calc_contrastive_loss (/root/reference/src/train_utils/loss_calc_utils.py:9).  These entry
+ * points are what a binding for that class would call; INTEGRATION.md shows the ctypes stub and the
+ * drop-in `models/loss.py`.  Conventions: plain pointers and sizes only; every function returns 0 or a
+ * negative FOCAL_E* code and never throws; nothing here allocates device memory or synchronises the
+ * stream; all device pointers are caller-owned, 16-byte aligned, row-major contiguous fp32 unless
+ * stated; all mutable state lives in the caller's workspace, so calls are re-entrant per workspace.
+ */
+#ifndef FOCAL_B200_H_
+#define FOCAL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOCAL_B200_ABI_VERSION 1
+#define FOCAL_MAX_MODALITIES 4
+
+enum {
+  FOCAL_OK = 0,
+  FOCAL_EINVAL = -1,      /* bad argument (null pointer, negative size, ...) */
+  FOCAL_ESHAPE = -2,      /* B % S != 0, unsupported S / D / M (see focal_b200_strerror) */
+  FOCAL_ECUDA = -3,       /* a CUDA runtime call failed (launch error, wrong arch, ...) */
+  FOCAL_EWORKSPACE = -4   /* workspace too small / misaligned */
+};
+
+/* terms bit mask: which parts of loss.py:139-218 to evaluate */
+enum { FOCAL_TERM_NCE = 1, FOCAL_TERM_ORTH = 2, FOCAL_TERM_TEMPORAL = 4, FOCAL_TERM_ALL = 7 };
+/* precision of the Gram tiles (everything outside the tiles is fp32) */
+enum { FOCAL_PREC_BF16 = 0 };
+
+/*
+ * The values FOCALLoss reads from `args` (loss.py:11-23, 149, 163, 211-215) plus build-side options.
+ *   B      rows of every feature tensor (= b sequences x S neighbouring windows; loss.py:152-155)
+ *   S      dataset_config["seq_len"]           M  len(dataset_config["modality_names"])
+ *   D      embedding width; shared = [0, D/2), private = [D/2, 2*(D/2))   (FOCALModules.py:51-57)
+ *   seq_begin/seq_end   sequences whose rows this call owns (multi-GPU row shard); [0, B/S) on one GPU.
+ *          Operands are always built for all B rows; losses and gradients only for the owned rows.
+ */
+typedef struct FocalCfg {
+  int32_t B, S, M, D;
+  float temperature;     /* FOCAL.temperature (already resolved for args.model) */
+  float margin;          /* FOCAL.inter_rank_margin */
+  float w_shared, w_private, w_orth, w_rank; /* the four loss weights, loss.py:211-215 */
+  int32_t no_private;    /* args.tag == "noPrivate": shared InfoNCE on full-width features (loss.py:163-170) */
+  int32_t need_grad;     /* 0: forward only (eval_functions.py:72-80 runs under no_grad) */
+  int32_t terms;         /* FOCAL_TERM_* mask; FOCAL_TERM_ALL for the reference loss */
+  int32_t precision;     /* FOCAL_PREC_* */
+  int32_t seq_begin, seq_end;
+  int32_t num_sms;       /* 0 = query the current device */
+  int32_t reserved[3];
+} FocalCfg;
+
+/* Byte offsets (from the workspace base) and extents of the buffers a host may need to look at:
+ * the InfoNCE row sums exchanged between ranks, and intermediates the parity tests compare. */
+typedef struct FocalWsInfo {
+  size_t total_bytes;
+  int32_t b, bpad, Bpad, n_problems, n_ops, kb_full;
+  size_t rowsum_off;     /* fp32 [n_problems][S][2][bpad]  sum_{j != k} exp(s_kj), position-major          */
+  size_t rowsum_bytes;
+  size_t cnt_off;        /* int32 [2M][bpad_seq]: active hinge count per sequence (temporal)               */
+  size_t cnt_bytes;
+  size_t mintra_off;     /* fp32 [2M][Bpad]: m_II of the row's sequence                                    */
+  size_t lossparts_off;  /* double [8]: total, shared, private, orth, temporal (un-weighted sums) ...      */
+  size_t dz_off, dz_bytes;     /* fp32 InfoNCE operand-gradient accumulators                               */
+  size_t dx_off, dx_bytes;     /* fp32 [2M][Bpad][kb_full*64] temporal gradient accumulators               */
+} FocalWsInfo;
+
+int focal_b200_abi_version(void);
+const char* focal_b200_strerror(int code);
+
+/* Validates cfg and reports workspace size + layout.  Replaces nothing in the reference (which allocates
+ * its [S,N,N,d] temporaries per call, loss.py:74); the caller allocates once and re-uses. */
+int focal_b200_workspace_info(const FocalCfg* cfg, FocalWsInfo* info);
+
+/* Stage 1 -- row prologue over ALL rows: L2 norms (eps 1e-8, loss.py:15/74), normalised + pre-scaled bf16
+ * InfoNCE operands in position-major swizzled tiles (loss.py:66-73), bf16 temporal operands + squared norms
+ * (loss.py:117), exact intra-sequence mean distances m_II (loss.py:118-124), orthogonality terms
+ * (loss.py:89-106) and positive-pair logits (loss.py:75-79) of the owned rows.
+ * feats: 2M device pointers, order view-major then modality: [v0m0, v0m1, ..., v1m0, ...], each fp32 [B, D]. */
+int focal_b200_prologue(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, void* stream);
+
+/* Stage 2 -- InfoNCE row sums sum_{j != k} exp(s_kj) of the owned rows (loss.py:74-85), tcgen05 Gram + exp2. */
+int focal_b200_nce_rowsum(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* stream);
+
+/* Stage 2b -- reduce column-split partial sums, take logs, publish 1/rowsum.  When `all_rows` is non-zero the
+ * reciprocal table is rebuilt for every row (after a multi-GPU exchange filled in the other ranks' row sums). */
+int focal_b200_nce_lse(const FocalCfg* cfg, void* ws, size_t ws_bytes, int all_rows, void* stream);
+
+/* Stage 3 -- InfoNCE backward of the owned rows (autograd of loss.py:74-85): recompute logit tiles,
+ * W = E (1/r_k + 1/r_j), second UMMA W @ Z_J into TMEM. */
+int focal_b200_nce_grad(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* stream);
+
+/* Stage 4 -- temporal ranking term (loss.py:108-137), forward and backward fused in one pass over the
+ * B x B distance tiles of the owned rows. */
+int focal_b200_temporal(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* stream);
+
+/* Stage 5 -- assemble: loss5 = {total, shared, private, orth, temporal} (device, fp32[5], un-weighted parts,
+ * weighted total; partial over the owned rows) and, when cfg->need_grad, d total / d feats into grads
+ * (2M device pointers, fp32 [B, D]; only the owned rows are written). */
+int focal_b200_finalize(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,
+                        float* const* grads, void* stream);
+
+/* All stages in order on one stream (single-GPU call of FOCALLoss.forward + backward). */
+int focal_b200_loss(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,
+                    float* const* grads, void* stream);
+
+/* Bring-up probe: runs `ksteps` tcgen05.mma (M=128) on caller-provided shared-memory images and returns
+ * the 128 x ncols fp32 accumulator.  Used by tests to pin the descriptor encodings on real hardware. */
+int focal_b200_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t idesc,
+                          uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep_bytes, uint32_t b_lbo, uint32_t b_sbo,
+                          uint32_t b_kstep_bytes, uint32_t ksteps, uint32_t ncols, uint32_t a_via_st, float* d_out,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOCAL_B200_H_ */

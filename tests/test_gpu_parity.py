@@ -1,0 +1,240 @@
+"""GPU parity: the CUDA path (through the module API -> ctypes -> C ABI -> sm_100a kernels) against the oracle
+and the golden fixtures of the live reference.
+
+Tolerances are north_star's: loss 1e-4 relative; gradients (bf16 tile mode) 1e-2 relative per tensor, norm-wise.
+Integer results (active hinge counts' index sets on well-separated inputs, positive indices) are exact.
+"""
+import math
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import focal_oracle as fo
+from tests._golden import CASE_BY_NAME, FINITE_CASES, config_of, golden_grads, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_RTOL_BF16 = 1e-2
+
+
+def _require_cuda():
+    assert torch.cuda.is_available(), "GPU tests selected (-m gpu) but no CUDA device is visible"
+
+
+def make_args(cfg: fo.FocalConfig, model="DeepSense", scalar_temp=True):
+    temp = cfg.temperature if scalar_temp else {model: cfg.temperature}
+    return types.SimpleNamespace(
+        device="cuda", model=model, tag="noPrivate" if cfg.no_private else None,
+        dataset_config={"modality_names": list(cfg.modalities), "seq_len": cfg.seq_len,
+                        "FOCAL": {"temperature": temp, "inter_rank_margin": cfg.margin,
+                                  "shared_contrastive_loss_weight": cfg.w_shared,
+                                  "private_contrastive_loss_weight": cfg.w_private,
+                                  "orthogonal_loss_weight": cfg.w_orth, "rank_loss_weight": cfg.w_rank}})
+
+
+def run_module(f1, f2, cfg, need_grad=True):
+    from focal_b200 import FOCALLoss
+    mod = FOCALLoss(make_args(cfg)).to("cuda")
+    g1 = {m: v.cuda().requires_grad_(need_grad) for m, v in f1.items()}
+    g2 = {m: v.cuda().requires_grad_(need_grad) for m, v in f2.items()}
+    if need_grad:
+        loss = mod(g1, g2)
+        loss.backward()
+    else:
+        with torch.no_grad():
+            loss = mod(g1, g2)
+    torch.cuda.synchronize()
+    return mod, loss.detach().cpu(), g1, g2
+
+
+@pytest.mark.parametrize("name", FINITE_CASES)
+def test_golden_cases(name):
+    """Every fixture of the live reference: loss, the four sub-losses, all gradients."""
+    _require_cuda()
+    case, rec, f1, f2 = load_case(name)
+    cfg = config_of(case)
+    mod, loss, g1, g2 = run_module(f1, f2, cfg)
+    ref_loss = float(rec["loss_f64"])
+    assert abs(float(loss) - ref_loss) / abs(ref_loss) < LOSS_RTOL, (float(loss), ref_loss)
+    parts = mod.last_parts.cpu().double().numpy()[1:]
+    assert np.allclose(parts, rec["parts_f64"], rtol=2e-4, atol=1e-6), (parts, rec["parts_f64"])
+    r1, r2 = golden_grads(case, rec)
+    for m in case["mods"]:
+        e1, e2 = rel_err(g1[m].grad.cpu(), r1[m]), rel_err(g2[m].grad.cpu(), r2[m])
+        assert e1 < GRAD_RTOL_BF16 and e2 < GRAD_RTOL_BF16, (name, m, e1, e2)
+
+
+@pytest.mark.parametrize("name", ["edge_b1_nan", "edge_seq1_nan"])
+def test_degenerate_batches(name):
+    """b == 1 or S == 1: NaN loss like the reference, finite InfoNCE / orthogonality parts and gradients."""
+    _require_cuda()
+    case, rec, f1, f2 = load_case(name)
+    mod, loss, g1, g2 = run_module(f1, f2, config_of(case))
+    assert math.isnan(float(loss))
+    parts = mod.last_parts.cpu().double().numpy()[1:]
+    assert np.allclose(parts[:3], rec["parts_f64"][:3], rtol=2e-4, atol=1e-6)
+    r1, r2 = golden_grads(case, rec)
+    for m in case["mods"]:
+        assert torch.isfinite(g1[m].grad).all()
+        assert rel_err(g1[m].grad.cpu(), r1[m]) < GRAD_RTOL_BF16
+
+
+@pytest.mark.parametrize("gen,B,D,mods,T,seed", [
+    ("iid", 1024, 256, ["seismic", "audio"], 0.5, 0),            # cfg 2 shape
+    ("structured", 1024, 256, ["seismic", "audio"], 0.5, 1),
+    ("structured", 2048, 256, ["acc", "gyr", "mag"], 0.07, 2),     # cfg 3 shape (3 modalities, T = 0.07)
+    ("iid", 1536, 128, ["seismic", "audio"], 0.5, 3),            # b = 384: three row tiles, K blocks = 1 / 2
+    ("structured", 4 * 333, 192, ["a", "b"], 0.2, 4),             # ragged: b = 333, D = 192 (3 K blocks, BN = 64)
+    ("iid", 2048, 64, ["m0", "m1", "m2", "m3"], 0.5, 5),          # 4 modalities
+])
+def test_against_fp64_oracle(gen, B, D, mods, T, seed):
+    """Sizes the reference cannot hold in memory comfortably: compare with the fp64 closed-form oracle (on the GPU)."""
+    _require_cuda()
+    cfg = fo.FocalConfig(modalities=mods, seq_len=4, temperature=T)
+    f1, f2 = (fo.make_iid(seed, mods, B, D) if gen == "iid" else fo.make_structured(seed, mods, B, D, 4))
+    mod, loss, g1, g2 = run_module(f1, f2, cfg)
+    ref = fo.focal_closed_form({m: v.cuda() for m, v in f1.items()}, {m: v.cuda() for m, v in f2.items()}, cfg,
+                               dtype=torch.float64)
+    assert abs(float(loss) - float(ref.loss)) / abs(float(ref.loss)) < LOSS_RTOL
+    for m in mods:
+        e1, e2 = rel_err(g1[m].grad, ref.grads1[m]), rel_err(g2[m].grad, ref.grads2[m])
+        assert e1 < GRAD_RTOL_BF16 and e2 < GRAD_RTOL_BF16, (m, e1, e2)
+
+
+def test_headline_size_against_fp64_oracle():
+    """BASELINE.json's metric configuration: B = 8192, M = 2, S = 4, D = 256, T = 0.5."""
+    _require_cuda()
+    mods = ["seismic", "audio"]
+    cfg = fo.FocalConfig(modalities=mods, seq_len=4, temperature=0.5)
+    f1, f2 = fo.make_structured(0, mods, 8192, 256, 4)
+    mod, loss, g1, g2 = run_module(f1, f2, cfg)
+    ref = fo.focal_closed_form({m: v.cuda() for m, v in f1.items()}, {m: v.cuda() for m, v in f2.items()}, cfg,
+                               dtype=torch.float64)
+    assert abs(float(loss) - float(ref.loss)) / abs(float(ref.loss)) < LOSS_RTOL
+    for m in mods:
+        assert rel_err(g1[m].grad, ref.grads1[m]) < GRAD_RTOL_BF16
+        assert rel_err(g2[m].grad, ref.grads2[m]) < GRAD_RTOL_BF16
+
+
+def test_intermediates_rowsum_and_hinge_counts():
+    """Index-exactness: row sums exclude exactly j == k; active hinge sets match the oracle on separated inputs."""
+    _require_cuda()
+    import ctypes as C
+    from focal_b200 import _cabi
+    from focal_b200.engine import CudaBackend, FocalHyper
+    mods = ["seismic", "audio"]
+    B, D, S = 640, 128, 4
+    f1, f2 = fo.make_structured(3, mods, B, D, S)
+    cfg = fo.FocalConfig(modalities=mods, seq_len=S, temperature=0.5)
+    hp = FocalHyper(tuple(mods), S, 0.5, 1.0, 1.0, 1.0, 3.0, 5.0)
+    be = CudaBackend()
+    feats = [f1[m].cuda() for m in mods] + [f2[m].cuda() for m in mods]
+    b = B // S
+    loss5, grads = be.run(hp, feats, (0, b), True, None)
+    torch.cuda.synchronize()
+    ws, info = be.workspace(be._cfg(hp, B, D, True, (0, b)), feats[0].device)
+    rs = be._view(ws, info.rowsum_off, info.rowsum_bytes, torch.float32, (info.n_problems, S, 2, info.bpad)).cpu()
+    ref = fo.focal_closed_form(f1, f2, cfg, dtype=torch.float64)
+    for q in range(info.n_problems):
+        want = ref.aux["nce_rowsum"][q] * math.exp(1.0 / 0.5)          # oracle sums exp(s - 1/T)
+        got = torch.cat((rs[q, :, 0, :b], rs[q, :, 1, :b]), dim=1).double()
+        assert torch.allclose(got, want, rtol=3e-3), (q, float((got / want - 1).abs().max()))
+    cnt = be._view(ws, info.cnt_off, info.cnt_bytes, torch.int32, (2 * len(mods), info.bpad)).cpu()
+    for t in range(2 * len(mods)):
+        act = ref.aux["temporal"][t]["active"]
+        m = ref.aux["temporal"][t]["m"]
+        h = ref.aux["temporal"][t]["mII"][:, None] - m + 1.0
+        want = act.sum(dim=1)
+        got = cnt[t, :b].long()
+        # pairs whose hinge is within bf16-tile noise of the kink may flip; all others must agree exactly
+        border = ((h.abs() < 2e-3) & ~torch.eye(b, dtype=torch.bool)).sum(dim=1)
+        assert ((got - want).abs() <= border).all(), (t, int((got - want).abs().max()))
+
+
+def test_forward_only_matches_and_skips_gradients():
+    _require_cuda()
+    case, rec, f1, f2 = load_case("skat1")
+    cfg = config_of(case)
+    _, loss_ng, g1, _ = run_module(f1, f2, cfg, need_grad=False)
+    _, loss_g, _, _ = run_module(f1, f2, cfg, need_grad=True)
+    assert float(loss_ng) == pytest.approx(float(loss_g), rel=1e-6)
+    assert all(v.grad is None for v in g1.values())
+
+
+def test_backward_scales_with_upstream_gradient_and_partial_requires_grad():
+    _require_cuda()
+    from focal_b200 import FOCALLoss
+    case, rec, f1, f2 = load_case("kat1_cfg1")
+    cfg = config_of(case)
+    mod = FOCALLoss(make_args(cfg, scalar_temp=False)).to("cuda")
+    assert len(mod.state_dict()) == 0 and sum(p.numel() for p in mod.parameters()) == 0
+    a = {m: v.cuda().requires_grad_(True) for m, v in f1.items()}
+    b2 = {m: v.cuda() for m, v in f2.items()}                      # view 2 does not require grad
+    (mod(a, b2) * 3.0).backward()
+    r1, _ = golden_grads(case, rec)
+    for m in case["mods"]:
+        assert rel_err(a[m].grad.cpu() / 3.0, r1[m]) < GRAD_RTOL_BF16
+
+
+def test_determinism_bitwise():
+    _require_cuda()
+    case, rec, f1, f2 = load_case("skat3")
+    cfg = config_of(case)
+    _, l1, a1, _ = run_module(f1, f2, cfg)
+    _, l2, a2, _ = run_module(f1, f2, cfg)
+    assert float(l1) == float(l2)
+    for m in case["mods"]:
+        assert torch.equal(a1[m].grad, a2[m].grad)
+
+
+def test_error_behaviour():
+    _require_cuda()
+    from focal_b200 import FOCALLoss
+    cfg = fo.FocalConfig(modalities=["a", "b"], seq_len=4)
+    mod = FOCALLoss(make_args(cfg))
+    x = {m: torch.randn(30, 16, device="cuda") for m in ("a", "b")}
+    with pytest.raises(ValueError):                       # B % S != 0: the reference's reshape raises too
+        mod(x, x)
+    y = {m: torch.randn(32, 16) for m in ("a", "b")}      # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        mod(y, y)
+    z = {m: torch.randn(32, 300, device="cuda") for m in ("a", "b")}
+    with pytest.raises(ValueError):                       # D > 256 not supported by the tile configurations yet
+        mod(z, z)
+
+
+def test_row_shards_on_one_gpu_sum_to_global():
+    """The multi-GPU row sharding, exercised on one device: shard results add up to the unsharded result."""
+    _require_cuda()
+    from focal_b200.engine import CudaBackend, FocalHyper
+    mods = ["seismic", "audio"]
+    B, D, S = 1024, 128, 4
+    f1, f2 = fo.make_structured(5, mods, B, D, S)
+    hp = FocalHyper(tuple(mods), S, 0.5, 1.0, 1.0, 1.0, 3.0, 5.0)
+    be = CudaBackend()
+    feats = [f1[m].cuda() for m in mods] + [f2[m].cuda() for m in mods]
+    b = B // S
+    full5, fullg = be.run(hp, feats, (0, b), True, None)
+    full5, fullg = full5.clone(), [g.clone() for g in fullg]
+    acc5 = torch.zeros_like(full5)
+    cuts = [0, 64, 128, 192, b]                            # 4 "ranks" (64 sequences = 256 rows each)
+    sums = {}
+
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        def exch(rs, lo=lo, hi=hi):
+            sums[(lo, hi)] = rs[..., lo:hi].clone()
+        be.run(hp, feats, (lo, hi), True, exch)
+    allrs = None
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        def exch(rs, lo=lo, hi=hi):
+            for (a, c), v in sums.items():
+                rs[..., a:c] = v
+        l5, g = be.run(hp, feats, (lo, hi), True, exch)
+        acc5 += l5
+        for t in range(len(feats)):
+            rows = slice(lo * S, hi * S)
+            assert rel_err(g[t][rows], fullg[t][rows]) < 1e-5
+    assert torch.allclose(acc5, full5, rtol=1e-5)
