@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
         tc_fence_after();
         if (kBwd) mbar_wait(&bars->w_empty[wsg], ((n / kNumWStages) & 1) ^ 1);
         const bool tail = col0 + BN > x.ncol_valid;
-        const bool diag = kIsNce ? (cs == x.side && col0 < x.row0 + kTileM && col0 + BN > x.row0)
-                                 : (col0 < x.row0 + kTileM && col0 + BN > x.row0);
+        // columns to drop: j == k (same side) always; in the backward pass also the positive p(k) (other side,
+        // same sequence index), whose contribution the finalize kernel adds in fp32
+        const bool overlap = col0 < x.row0 + kTileM && col0 + BN > x.row0;
+        const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == x.side)) : overlap;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           float v[32];

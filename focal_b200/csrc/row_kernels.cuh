@@ -33,6 +33,11 @@ __device__ __forceinline__ void load_rows(const Plan& p, const FeatPtrs& f, int 
   __syncwarp();
 }
 
+// fp32 -> bf16 (round to nearest even) -> fp32: the value the tensor core sees for an operand element
+__device__ __forceinline__ float bf16_round(float v) {
+  return __uint_as_float(pack_bf16x2(v, 0.f) << 16);
+}
+
 __device__ __forceinline__ float warp_dot(const float* a, const float* b, int n, int lane) {
   float s = 0.f;
   for (int c = lane; c < n; c += 32) s = fmaf(a[c], b[c], s);
@@ -164,15 +169,21 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
     // ---- loss terms of the owned rows
     if (I >= p.seq0 && I < p.seq1) {
       if (p.terms & FOCAL_TERM_NCE) {
-        const float sc = -2.f / (p.T * (float)p.S * (float)(2 * p.b));      // -2 cos / (T S N)
+        // s_{k,p(k)} is taken from the same bf16-rounded, pre-scaled operands the Gram tiles use, so that
+        // ln(sum_j exp s_kj) - s_{k,p(k)} cancels exactly where the positive dominates the row (small T)
+        const float sc = -2.f * 0.6931471805599453f / ((float)p.S * (float)(2 * p.b));   // -2 ln2 G~ / (S N)
         for (int q = 0; q < p.nProb; ++q) {
           const OpDesc& a = p.ops[p.probs[q].opA];
           const OpDesc& b = p.ops[p.probs[q].opB];
-          const float dot = warp_dot(xs + a.tensor * D + a.col0, xs + b.tensor * D + b.col0, a.width, lane);
           const float sa = (a.width == D) ? sfull[a.tensor] : (a.col0 == 0 ? ssh[a.tensor] : spr[a.tensor]);
           const float sb = (b.width == D) ? sfull[b.tensor] : (b.col0 == 0 ? ssh[b.tensor] : spr[b.tensor]);
-          const float cs = dot / (fmaxf(sqrtf(sa), kNceEps) * fmaxf(sqrtf(sb), kNceEps));
-          if (p.probs[q].kind == 0) acc_ps += sc * cs; else acc_pp += sc * cs;
+          const float fa = p.alpha / fmaxf(sqrtf(sa), kNceEps), fb2 = p.alpha / fmaxf(sqrtf(sb), kNceEps);
+          const float* xa = xs + a.tensor * D + a.col0;
+          const float* xb = xs + b.tensor * D + b.col0;
+          float dot = 0.f;
+          for (int c = lane; c < a.width; c += 32) dot = fmaf(bf16_round(xa[c] * fa), bf16_round(xb[c] * fb2), dot);
+          dot = warp_sum(dot);
+          if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
         }
       }
       if (p.terms & FOCAL_TERM_ORTH) {
@@ -198,7 +209,9 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1b: exact fp32 intra-sequence mean distance m_II (loss.py:118-124, block diagonal of the block means).
+// K1b: intra-sequence mean distance m_II (loss.py:118-124, block diagonal of the block means), direct
+// differences in fp32 of the SAME bf16-rounded rows the distance tiles use: the whole temporal term is then the
+// exact loss of the rounded features, and rounding noise that is coherent per row cancels between m_II and m_IJ.
 // One warp per (tensor, sequence); written per row so the Gram kernel can TMA it as a column vector.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan p, const __grid_constant__ FeatPtrs f,
@@ -214,7 +227,7 @@ __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan
     for (int b2 = a + 1; b2 < S; ++b2) {
       float d2 = 0.f;
       for (int c = lane; c < D; c += 32) {
-        const float df = __ldg(x + a * D + c) - __ldg(x + b2 * D + c);
+        const float df = bf16_round(__ldg(x + a * D + c)) - bf16_round(__ldg(x + b2 * D + c));
         d2 = fmaf(df, df, d2);
       }
       d2 = warp_sum(d2);
@@ -307,7 +320,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
       const float rho = reinterpret_cast<const float*>(ws + p.rho_off)[(uint64_t)t * p.Bpad + i];
       const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
       const int cnt = reinterpret_cast<const int32_t*>(ws + p.cnt_off)[(uint64_t)t * p.bpad + I];
-      for (int c = lane; c < D; c += 32) gs[t * D + c] = p.w_rank * (x[c] * rho - y[c]);
+      for (int c = lane; c < D; c += 32) gs[t * D + c] = p.w_rank * (bf16_round(x[c]) * rho - y[c]);
       // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
       const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
       if (cnt > 0) {
@@ -316,13 +329,14 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
           if (j == s) continue;
           float d2 = 0.f;
           for (int c = lane; c < D; c += 32) {
-            const float df = x[c] - __ldg(base + (size_t)j * D + c);
+            const float df = bf16_round(x[c]) - bf16_round(__ldg(base + (size_t)j * D + c));
             d2 = fmaf(df, df, d2);
           }
           d2 = warp_sum(d2);
           if (d2 > 0.f) {
             const float r = coef * rsqrtf(d2);
-            for (int c = lane; c < D; c += 32) gs[t * D + c] += r * (x[c] - __ldg(base + (size_t)j * D + c));
+            for (int c = lane; c < D; c += 32)
+              gs[t * D + c] += r * (bf16_round(x[c]) - bf16_round(__ldg(base + (size_t)j * D + c)));
           }
         }
       }
@@ -350,12 +364,21 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
         used = true;
         const OpDesc& po = p.ops[side == 0 ? pr.opB : pr.opA];            // partner operand: positive row p(k)
         const float pss = (po.width == D) ? sfull[po.tensor] : (po.col0 == 0 ? ssh[po.tensor] : spr[po.tensor]);
-        const float pinv = 1.f / fmaxf(sqrtf(pss), kNceEps);
+        const float pinv = p.alpha / fmaxf(sqrtf(pss), kNceEps);
         const float* px = xs + po.tensor * D + po.col0;
         const float* acc = reinterpret_cast<const float*>(ws + pr.dz_off) +
                            ((uint64_t)side * S * p.bpad + rowN) * wp;
         const float wq = pr.weight * inv_tsn;
-        for (int c = lane; c < w; c += 32) tmp[c] += wq * (acc[c] * inv_alpha - 2.f * px[c] * pinv);
+        // The positive column p(k) is masked out of the tiles and handled here in fp32: where the positive
+        // dominates the row (small T, aligned views) W_kp - 2 is a tiny difference that bf16 W would destroy.
+        const float fk = p.alpha / nrm;
+        float gpos = 0.f;
+        for (int c = lane; c < w; c += 32) gpos = fmaf(bf16_round(x[c] * fk), bf16_round(px[c] * pinv), gpos);
+        gpos = warp_sum(gpos);
+        const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
+        const float wkp = exp2f(gpos) * (1.f / rs[(uint64_t)side * p.bpad + I] + 1.f / rs[(uint64_t)(1 - side) * p.bpad + I]);
+        for (int c = lane; c < w; c += 32)
+          tmp[c] += wq * inv_alpha * (acc[c] + (wkp - 2.f) * bf16_round(px[c] * pinv));
       }
       if (!used) continue;
       // d zh / d z = (I - zh zh^T) / n
