@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the FOCAL contrastive-loss hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path -- ``loss = FOCALLoss(f1, f2); loss.backward()`` w.r.t. all 2M feature
+tensors -- over one batch of synthetic MOD-shaped embeddings: B = 8192 rows (2048 sequences of S = 4 windows),
+M = 2 modalities, D = 256 (128 shared + 128 private), T = 0.5.  For N > 1 the same global batch is row-sharded
+over the ranks (strong scaling; launched by torchrun, one rank per GPU, NCCL).
+
+``--impl reference`` times the reference's CPU implementation of the path on the host cores.  The reference is a
+pure-Python/PyTorch module that cannot travel to the GPU box, so its op-for-op port ``oracle/focal_ref_port.py``
+is timed (same ATen operators in the same order, autograd backward) on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FOCAL loss fwd+bwd samples/s @B=8192"
+UNIT = "samples/s"
+WORKLOAD = dict(B=8192, S=4, M=2, D=256, T=0.5, margin=1.0, weights=(1.0, 1.0, 3.0, 5.0),
+                mods=("seismic", "audio"))
+L2_BYTES = 126 * 2 ** 20
+
+
+def f_alg(B, M, D, S):
+    """Algorithmic FLOPs of one step, SURVEY.md §8d: 12 B^2 D (M^2/S + M)."""
+    return 12.0 * B * B * D * (M * M / S + M)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(tflops=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1413.7))),
+                    tflops_burst=float(p.get("bf16_tflops", 1662.8)), hbm=float(p.get("hbm_gbs", 6541.1)),
+                    source="measured")
+    return dict(tflops=1590.0, tflops_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference) -- bounded sample of the workload
+# -------------------------------------------------------------------------------------------------
+def cpu_reference_time(B_sample: int, steps: int, warmup: int):
+    import torch
+    from oracle.focal_oracle import FocalConfig, make_iid
+    from oracle.focal_ref_port import focal_loss_port
+    w = WORKLOAD
+    cfg = FocalConfig(modalities=list(w["mods"]), seq_len=w["S"], temperature=w["T"], margin=w["margin"])
+    f1, f2 = make_iid(0, w["mods"], B_sample, w["D"])
+    f1 = {m: v.requires_grad_(True) for m, v in f1.items()}
+    f2 = {m: v.requires_grad_(True) for m, v in f2.items()}
+    times = []
+    for it in range(warmup + steps):
+        for v in list(f1.values()) + list(f2.values()):
+            v.grad = None
+        t0 = time.perf_counter()
+        loss = focal_loss_port(f1, f2, cfg)
+        loss.backward()
+        float(loss.detach())
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    return times
+
+
+def pick_cpu_sample(budget_s: float, steps: int, warmup: int) -> int:
+    """Largest B in {128, 256, 512} whose (steps + warmup) run fits the budget; cost grows ~ B^2."""
+    t128 = min(cpu_reference_time(128, 2, 1))
+    best = 128
+    for B in (256, 512):
+        if (steps + warmup) * t128 * (B / 128) ** 2 * 1.3 < budget_s:
+            best = B
+    return best
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = pick_cpu_sample(150.0, args.steps, args.warmup)
+    times = cpu_reference_time(Bs, args.steps, args.warmup)
+    t = statistics.mean(times)
+    value = Bs / t
+    w = WORKLOAD
+    sample = (f"op-for-op port of reference FOCALLoss (oracle/focal_ref_port.py), fwd+bwd on CPU, B={Bs} rows of the "
+              f"B={w['B']} workload (D={w['D']}, M={w['M']}, S={w['S']}); cost grows ~B^2 (the reference materialises "
+              f"[S,2b,2b,d]; at B=8192 that is 34 GB per call and cannot run)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "global_batch": w["B"], "cpu_sample_batch": Bs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name():
+    w = WORKLOAD
+    return (f"FOCAL loss fwd+bwd, synthetic MOD-shaped embeddings: B={w['B']} (b={w['B'] // w['S']} sequences x S={w['S']}), "
+            f"M={w['M']} modalities, D={w['D']} (shared {w['D'] // 2} + private {w['D'] // 2}), T={w['T']}, "
+            f"weights {w['weights']}")
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import focal_b200
+    from focal_b200 import _cabi
+    from focal_b200.engine import FocalEngine, FocalHyper
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    w = WORKLOAD
+    B, S, M, D = w["B"], w["S"], w["M"], w["D"]
+    mods = list(w["mods"])
+    if B % (S * world):
+        raise SystemExit("global batch does not shard over the ranks")
+    Bl = B // world
+    hp = FocalHyper(tuple(mods), S, w["T"], w["margin"], *w["weights"])
+    engine = FocalEngine(hp, process_group=group)
+
+    # synthetic inputs: NSETS different batches so that consecutive steps read their inputs from HBM, not L2
+    nsets = max(2, math.ceil(2 * L2_BYTES / (2 * M * B * D * 4)))
+    gen = torch.Generator(device="cpu").manual_seed(1234)
+    host_sets, dev_sets = [], []
+    for s_ in range(nsets):
+        full = [torch.randn(B, D, generator=gen, dtype=torch.float32) for _ in range(2 * M)]
+        mine = [t[rank * Bl:(rank + 1) * Bl].contiguous().pin_memory() for t in full]
+        host_sets.append(mine)
+        dev_sets.append([t.to(dev) for t in mine])
+
+    def as_dicts(tensors):
+        return ({m: tensors[i] for i, m in enumerate(mods)}, {m: tensors[M + i] for i, m in enumerate(mods)})
+
+    def step(k):
+        f1, f2 = as_dicts(dev_sets[k % nsets])
+        return engine.loss_and_grads(f1, f2, True)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    sync_all()
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.__enter__()
+    sync_all()
+    ev0.record()
+    for k in range(args.steps):
+        loss5, grads = step(k)
+    ev1.record()
+    sync_all()
+    if sampler:
+        sampler.__exit__()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = B / (ms_step * 1e-3)
+
+    # ---- end-to-end: pinned host inputs -> H2D -> loss + grads -> D2H of the loss, through the module API
+    args_ns = make_args(mods, S, w, group)
+    module = focal_b200.FOCALLoss(args_ns).to(dev)
+    stage = [torch.empty(Bl, D, device=dev) for _ in range(2 * M)]
+
+    def e2e_step(k):
+        hs = host_sets[k % nsets]
+        for dst, src in zip(stage, hs):
+            dst.copy_(src, non_blocking=True)
+        xs = [t.requires_grad_(True) for t in (s_.detach() for s_ in stage)]
+        f1, f2 = as_dicts(xs)
+        loss = module(f1, f2)
+        loss.backward()
+        return float(loss.detach().cpu())          # D2H read of the step's result (host sync, like pretrain.py:74)
+
+    for k in range(3):
+        e2e_step(k)
+    sync_all()
+    ev0.record()
+    for k in range(args.steps):
+        e2e_step(k)
+    ev1.record()
+    sync_all()
+    te = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item()) / args.steps
+    e2e = {"value": B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": 2 * M * Bl * D * 4 * world, "d2h_bytes_per_step": 4 * world}
+
+    # ---- per-stage device times (separate pass; events between the C-ABI stages on the launching stream)
+    stages = stage_breakdown(engine, dev_sets, mods, M, args.steps, world, group) if world == 1 else None
+
+    out = None
+    if rank == 0:
+        peaks = measured_peaks()
+        F = f_alg(B, M, D, S)
+        roof = None
+        if stages is not None:
+            # dominant kernel: the fused temporal distance/ranking pass (2M calls, fwd+bwd in one launch)
+            F_tmp = 12.0 * M * B * B * D
+            t_tmp = stages["temporal"] * 1e-3
+            roof = {"bound": "tensor", "kernel": "gram_kernel<TMP_BWD> (temporal ranking fwd+bwd, fused)",
+                    "achieved": F_tmp / t_tmp / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": F_tmp / t_tmp / 1e12 / peaks["tflops"], "peak_source": peaks["source"] + " (sustained bf16)",
+                    "traffic": None, "alg_flops_per_launch": F_tmp, "launch_ms": stages["temporal"]}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            Bs = pick_cpu_sample(20.0, 3, 1)
+            ts = cpu_reference_time(Bs, 3, 1)
+            cpu = {"value": Bs / statistics.mean(ts), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"op-for-op port of the reference loss on CPU, fwd+bwd, B={Bs} of the B={B} workload "
+                             f"(D={D}, M={M}, S={S}); the reference cannot run B=8192 (34 GB per InfoNCE call)"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(), "global_batch": B, "rows_per_gpu": Bl,
+                       "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": f"inputs rotate over {nsets} batches ({nsets * 2 * M * B * D * 4 / 2 ** 20:.0f} MiB > 126 MiB L2)",
+                       "tiles": "bf16 operands, fp32 accumulation (tcgen05 kind::f16)"},
+            "tensor_roofline_frac": F / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+            "alg_tflops": F / (ms_step * 1e-3) / 1e12,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": args.steps * launches_per_step(B, S, world),
+            "stages_ms": stages,
+            "clocks": sampler.summary() if sampler else None,
+            "loss": float(loss5[0].item()),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def launches_per_step(B, S, world):
+    b = B // S
+    pad = 1 if (b % 128 or B % 128) else 0
+    # prologue, intra, nce_rowsum, nce_lse, nce_grad, temporal, finalize, loss_reduce (+ nce_lse(all) when sharded)
+    return pad + 8 + (1 if world > 1 else 0)
+
+
+def make_args(mods, S, w, group):
+    import types
+    return types.SimpleNamespace(
+        device="cuda", model="DeepSense", tag=None, focal_process_group=group,
+        dataset_config={"modality_names": list(mods), "seq_len": S,
+                        "FOCAL": {"temperature": {"DeepSense": w["T"], "SW_Transformer": 0.07},
+                                  "inter_rank_margin": w["margin"],
+                                  "shared_contrastive_loss_weight": w["weights"][0],
+                                  "private_contrastive_loss_weight": w["weights"][1],
+                                  "orthogonal_loss_weight": w["weights"][2], "rank_loss_weight": w["weights"][3]}})
+
+
+def stage_breakdown(engine, dev_sets, mods, M, steps, world, group):
+    """Mean device time of each C-ABI stage over `steps` steps (events on the launching stream)."""
+    import ctypes as C
+
+    import torch
+
+    from focal_b200 import _cabi
+    be = engine.backend
+    hp = engine.hp
+    names = ["prologue", "nce_rowsum", "nce_lse", "nce_grad", "temporal", "finalize"]
+    acc = {n: 0.0 for n in names}
+    lib = be.lib
+    for k in range(steps):
+        feats = dev_sets[k % len(dev_sets)]
+        B, D = feats[0].shape
+        cfg = be._cfg(hp, B, D, True, (0, B // hp.seq_len))
+        ws, info = be.workspace(cfg, feats[0].device)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        wsp, wsn, ref = C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), C.byref(cfg)
+        fptr = _cabi.ptr_array([t.data_ptr() for t in feats])
+        loss5 = torch.empty(5, device=feats[0].device)
+        grads = [torch.empty_like(t) for t in feats]
+        gptr = _cabi.ptr_array([g.data_ptr() for g in grads])
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        evs[0].record()
+        _cabi.check(lib.focal_b200_prologue(ref, fptr, wsp, wsn, stream), "prologue"); evs[1].record()
+        _cabi.check(lib.focal_b200_nce_rowsum(ref, wsp, wsn, stream), "nce_rowsum"); evs[2].record()
+        _cabi.check(lib.focal_b200_nce_lse(ref, wsp, wsn, 0, stream), "nce_lse"); evs[3].record()
+        _cabi.check(lib.focal_b200_nce_grad(ref, wsp, wsn, stream), "nce_grad"); evs[4].record()
+        _cabi.check(lib.focal_b200_temporal(ref, wsp, wsn, stream), "temporal"); evs[5].record()
+        _cabi.check(lib.focal_b200_finalize(ref, fptr, wsp, wsn, C.c_void_p(loss5.data_ptr()), gptr, stream),
+                    "finalize"); evs[6].record()
+        torch.cuda.synchronize()
+        for i, n in enumerate(names):
+            acc[n] += evs[i].elapsed_time(evs[i + 1])
+    return {n: v / steps for n, v in acc.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
