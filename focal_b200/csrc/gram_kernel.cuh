@@ -10,7 +10,10 @@
 // The N x N logit / distance matrices are never written to memory.  Operands are bf16 tiles that the prologue
 // laid out in HBM exactly as the UMMA wants them in shared memory (K-block-major, 128-byte rows, SWIZZLE_128B),
 // so each tile is a single linear TMA bulk copy.  Roles: warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM
-// owner), warps 2..5 = epilogue (one TMEM lane quarter each).  Row tile = 128 rows (UMMA M), column tile = BN.
+// owner), warps 2..9 = two epilogue warpgroups that alternate column tiles (each owns one S stage in TMEM and one
+// W buffer in shared memory; within a warpgroup each warp owns one TMEM lane quarter).  Two warpgroups put two
+// epilogue warps on every SM sub-partition so the MUFU / FMA chains of one hide behind the other.
+// Row tile = 128 rows (UMMA M), column tile = BN.
 #pragma once
 #include "plan.h"
 #include "ptx.cuh"
@@ -19,7 +22,8 @@ namespace fb {
 
 enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 
-constexpr int kGramThreads = 192;
+constexpr int kGramThreads = 64 + 256;
+constexpr int kEpiThreads = 256;
 constexpr int kNumBStages = 3;
 constexpr int kNumWStages = 2;
 constexpr int kTmemCols = 512;
@@ -35,7 +39,7 @@ struct GramSmem {
   static constexpr uint32_t kBOff = kAOff + kABytes;
   static constexpr uint32_t kWOff = kBOff + kNumBStages * kBStage;
   static constexpr uint32_t kBarOff = kWOff + kNumWStages * kWStage;
-  static constexpr uint32_t kTotal = kBarOff + 256;
+  static constexpr uint32_t kTotal = kBarOff + 2048;
   static constexpr uint32_t kDynamic = kTotal + 1024;           // slack for manual 1024-B alignment
 };
 
@@ -47,7 +51,11 @@ struct GramBars {
   uint64_t o_full, o_empty;
   uint32_t tmem_base;
   float red[4];
+  float part_acc[128];     // per-row partials of epilogue warpgroup 1, folded into warpgroup 0 at the end of an item
+  float part_hinge[128];
+  int32_t part_cnt[128];
 };
+static_assert(sizeof(GramBars) <= 2048, "barrier block");
 
 // ---------------------------------------------------------------------------------------------------------
 // work-item decoding
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 128); }
     for (int i = 0; i < kNumWStages; ++i) { mbar_init(&bars->w_full[i], 128); mbar_init(&bars->w_empty[i], 1); }
     mbar_init(&bars->o_full, 1);
-    mbar_init(&bars->o_empty, 128);
+    mbar_init(&bars->o_empty, kEpiThreads);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -257,9 +265,15 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     }
   } else {
     // =============================== epilogue warps ===============================
+    static_assert(kNumWStages == 2, "one W buffer per epilogue warpgroup");
+    const int wg = (warp - 2) >> 2;                   // epilogue warpgroup: handles tiles with (tile counter & 1) == wg
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;             // row within the tile == TMEM lane
     const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+    constexpr int SQ = SEQ > 0 ? SEQ : 1;
+    const float inv_cnt = 1.f / (float)(SQ * SQ);
+    const float coef1 = -1.f / ((float)p.b * (float)(p.b - 1) * (float)(SQ * SQ));
+    const float coef2 = 2.f * coef1;
     uint32_t nb = 0, ni = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
       Item x;
@@ -267,17 +281,15 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       const int row = x.row0 + trow;                  // row within side (NCE: sequence index k) / tensor (TMP: i)
       const bool row_ok = row < x.ncol_valid && row >= x.row_lo && row < x.row_hi;
       float rowacc = 0.f;                             // NCE_FWD: row sum; TMP: rho_i
-      float ck = 0.f, n_i = 0.f, m_ii = 0.f, hinge_acc = 0.f;
+      float ck = 0.f, n_i = 0.f, mim = -1e30f, hinge_acc = 0.f;
       int cnt_i = 0;
       if (MODE == NCE_BWD && row_ok) ck = x.colvec0[x.side][row];
-      if (!kIsNce && row_ok) { n_i = x.colvec0[0][row]; m_ii = x.colvec1[0][row]; }
-      constexpr int SQ = SEQ > 0 ? SEQ : 1;
-      const float inv_cnt = 1.f / (float)(SQ * SQ);
-      const float coef_scale = -1.f / ((float)p.b * (float)(p.b - 1) * (float)(SQ * SQ));
+      if (!kIsNce && row_ok) { n_i = x.colvec0[0][row]; mim = x.colvec1[0][row] + p.margin; }   // m_II + margin
       const int seq_i = row / SQ;
       const int ntiles = x.ct_end - x.ct_begin;
-      for (int t = 0; t < ntiles; ++t) {
-        const uint32_t n = nb + t, st = n % kNumBStages, ss = n & 1, wsg = n % kNumWStages;
+      for (int t = (wg - (int)nb) & 1; t < ntiles; t += 2) {
+        const uint32_t n = nb + t, st = n % kNumBStages;
+        const uint32_t ss = wg, wsg = wg;             // (n & 1) == wg
         const int ct = x.ct_begin + t;
         const int cs = ct / x.ntc, tc = ct - cs * x.ntc;
         const int col0 = tc * BN;                     // first column (within side) of this tile
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
         if (kColVec) mbar_wait(&bars->b_full[st], (n / kNumBStages) & 1);
         mbar_wait(&bars->s_full[ss], (n >> 1) & 1);
         tc_fence_after();
-        if (kBwd) mbar_wait(&bars->w_empty[wsg], ((n / kNumWStages) & 1) ^ 1);
+        if (kBwd) mbar_wait(&bars->w_empty[wsg], ((n >> 1) & 1) ^ 1);
         const bool tail = col0 + BN > x.ncol_valid;
         // columns to drop: j == k (same side) always; in the backward pass also the positive p(k) (other side,
         // same sequence index), whose contribution the finalize kernel adds in fp32
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
                 v[j] *= ck + cj.x; v[j + 1] *= ck + cj.y; v[j + 2] *= ck + cj.z; v[j + 3] *= ck + cj.w;
               }
             }
-            if (diag || tail) {      // j != k (loss.py:35-44) and the zero-padded tail columns
+            if (diag || tail) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int col = cbase + j;
@@ -332,28 +344,32 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
               nj[j] = t4.x; nj[j + 1] = t4.y; nj[j + 2] = t4.z; nj[j + 3] = t4.w;
             }
 #pragma unroll
-            for (int g0 = 0; g0 < 32; g0 += SEQ) {
+            for (int g0 = 0; g0 < 32; g0 += SQ) {
               float gsum = 0.f;
 #pragma unroll
-              for (int j = 0; j < SEQ; ++j) {
-                const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], n_i + nj[g0 + j]), 0.f);     // cdist mm form
-                const float rs = d2 > 0.f ? rsqrt_approx(d2) : 0.f;   // 1/delta; 0 where delta == 0
+              for (int j = 0; j < SQ; ++j) {
+                // cdist mm form; the floor keeps 1/delta finite for coincident rows (their r_ij (x_i - x_j) is 0)
+                const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], n_i + nj[g0 + j]), 1e-12f);
+                const float rs = rsqrt_approx(d2);                    // 1 / delta
                 v[g0 + j] = rs;
                 gsum = fmaf(d2, rs, gsum);                            // delta = d2 / delta
               }
 #pragma unroll
-              for (int o = 1; o < SEQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+              for (int o = 1; o < SQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
               const int colg = cbase + g0;
               const float m_ij = gsum * inv_cnt;
-              const float m_jj = cv[BN + ch * 32 + g0];
-              const bool pair_ok = row_ok && colg < x.ncol_valid && (colg / SQ) != seq_i;
-              const float h = m_ii - m_ij + p.margin;
-              const bool a_ij = pair_ok && (h >= 0.f);                       // hinge active at equality
-              const bool a_ji = pair_ok && (m_jj - m_ij + p.margin >= 0.f);
-              if ((lane & (SEQ - 1)) == 0 && a_ij) { hinge_acc += h; cnt_i += 1; }
-              const float coef = coef_scale * ((a_ij ? 1.f : 0.f) + (a_ji ? 1.f : 0.f));
+              const float mjm = cv[BN + ch * 32 + g0] + p.margin;     // m_JJ + margin
+              bool pair_ok = row_ok;
+              if (tail) pair_ok = pair_ok && colg < x.ncol_valid;
+              if (diag) pair_ok = pair_ok && (colg / SQ) != seq_i;    // the block diagonal is done exactly elsewhere
+              const float h = pair_ok ? mim - m_ij : -1.f;           // hinge argument; active at equality
+              const bool a_ij = h >= 0.f;
+              const bool a_ji = pair_ok && (mjm - m_ij >= 0.f);
+              hinge_acc += fmaxf(h, 0.f);
+              cnt_i += a_ij ? 1 : 0;
+              const float coef = a_ij ? (a_ji ? coef2 : coef1) : (a_ji ? coef1 : 0.f);
 #pragma unroll
-              for (int j = 0; j < SEQ; ++j) v[g0 + j] *= coef;
+              for (int j = 0; j < SQ; ++j) { v[g0 + j] *= coef; rowacc += v[g0 + j]; }
             }
           }
           if (kBwd) {
@@ -366,13 +382,6 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
               pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
               pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
               pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-              if (!kIsNce) {
-                // rho_i = sum_j r_ij must use the same rounded r_ij the tensor core multiplies with x_j
-                rowacc += (__uint_as_float(pk.x << 16) + __uint_as_float(pk.x & 0xffff0000u)) +
-                          (__uint_as_float(pk.y << 16) + __uint_as_float(pk.y & 0xffff0000u)) +
-                          (__uint_as_float(pk.z << 16) + __uint_as_float(pk.z & 0xffff0000u)) +
-                          (__uint_as_float(pk.w << 16) + __uint_as_float(pk.w & 0xffff0000u));
-              }
               *reinterpret_cast<uint4*>(wbuf + kb2 * 16384 + swz128(trow, c0 + c)) = pk;
             }
           }
@@ -391,11 +400,30 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       }
       nb += ntiles;
 
-      // ---------------- item epilogue
-      if (MODE == NCE_FWD) {
-        float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) +
-                       ((((uint64_t)x.c * p.nProb + x.q) * p.S + x.s) * 2 + x.side) * p.bpad;
-        if (row < p.bpad) rpart[row] = row_ok ? rowacc : 0.f;
+      // ---------------- item epilogue: fold warpgroup 1's per-row partials into warpgroup 0
+      if (MODE != NCE_BWD) {
+        if (wg == 1) {
+          bars->part_acc[trow] = rowacc;
+          if (!kIsNce) { bars->part_hinge[trow] = hinge_acc; bars->part_cnt[trow] = cnt_i; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (wg == 0) {
+          rowacc += bars->part_acc[trow];
+          if (MODE == NCE_FWD) {
+            float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) +
+                           ((((uint64_t)x.c * p.nProb + x.q) * p.S + x.s) * 2 + x.side) * p.bpad;
+            rpart[row] = row_ok ? rowacc : 0.f;
+          } else {
+            hinge_acc += bars->part_hinge[trow];
+            cnt_i += bars->part_cnt[trow];
+            if (kBwd && row_ok) reinterpret_cast<float*>(ws + p.rho_off)[(uint64_t)x.c * p.Bpad + row] = rowacc;
+            if (row_ok && (lane & (SQ - 1)) == 0)
+              reinterpret_cast<int32_t*>(ws + p.cnt_off)[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
+            // every lane of a sequence accumulated the same hinge values: count each (I, J) once
+            const float hs = warp_sum(((lane & (SQ - 1)) == 0) ? hinge_acc : 0.f);
+            if (lane == 0) bars->red[quarter] = hs;
+          }
+        }
       }
       if (kBwd) {
         mbar_wait(&bars->o_full, ni & 1);
@@ -408,7 +436,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
           out = reinterpret_cast<float*>(ws + p.dx_off) + ((uint64_t)x.c * p.Bpad + row) * kON;
         }
 #pragma unroll 1
-        for (int ch = 0; ch < kON / 32; ++ch) {
+        for (int ch = wg; ch < kON / 32; ch += 2) {     // the two warpgroups split the columns of O
           float v[32];
           tmem_ld32(tmem + tlane + kOCol + ch * 32, v);
           tmem_ld_wait();
@@ -421,22 +449,15 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
         tc_fence_before();
         mbar_arrive(&bars->o_empty);
       }
-      if (!kIsNce) {
-        if (kBwd && row_ok) reinterpret_cast<float*>(ws + p.rho_off)[(uint64_t)x.c * p.Bpad + row] = rowacc;
-        if (row_ok && (lane & (SQ - 1)) == 0)
-          reinterpret_cast<int32_t*>(ws + p.cnt_off)[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
-        // hinge partial of this item: 128 threads -> one float
-        float hs = warp_sum(hinge_acc);
-        if (lane == 0) bars->red[quarter] = hs;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (trow == 0) {
+      if (MODE != NCE_BWD) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // partial arrays / red[] may be reused after this point
+        if (!kIsNce && wg == 0 && trow == 0) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
           const int slot = x.c * nrt + (x.row0 / kTileM - t0);
           reinterpret_cast<float*>(ws + p.part3_off)[slot] =
               ((bars->red[0] + bars->red[1]) + (bars->red[2] + bars->red[3])) / ((float)p.b * (float)(p.b - 1));
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
   }

@@ -45,14 +45,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of burning issue slots that the epilogue warps on the same SM sub-partition need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
-#ifndef FB_WAIT_LIMIT
-#define FB_WAIT_LIMIT (1u << 20)
+#ifndef FB_WAIT_TIMEOUT_NS
+#define FB_WAIT_TIMEOUT_NS 2000000000ull
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > FB_WAIT_LIMIT) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+    if (global_timer_ns() - t0 > FB_WAIT_TIMEOUT_NS) {
       printf("focal_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
       __trap();
