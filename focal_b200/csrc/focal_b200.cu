@@ -42,8 +42,9 @@ int cuda_ok(const char* what) {
 
 bool temporal_degenerate(const Plan& p) { return p.b <= 1 || p.S <= 1; }
 
-template <int MODE, int BN, int KB, int SEQ>
-int launch_gram(const Plan& p, uint8_t* ws, cudaStream_t st, int n_items) {
+template <int MODE, int KB, int SEQ>
+int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int n_items) {
+  constexpr int BN = tile_bn(KB);
   using L = GramSmem<BN, KB>;
   auto kfn = gram_kernel<MODE, BN, KB, SEQ>;
   static bool configured = false;     // per instantiation; the attribute is sticky per context
@@ -54,48 +55,54 @@ int launch_gram(const Plan& p, uint8_t* ws, cudaStream_t st, int n_items) {
   }
   if (n_items <= 0) return FOCAL_OK;
   const int grid = n_items < p.num_sms ? n_items : p.num_sms;     // persistent: one CTA per SM
-  kfn<<<grid, kGramThreads, L::kDynamic, st>>>(p, ws);
+  kfn<<<grid, kGramThreads, L::kDynamic, st>>>(p, sel, ws);
   return cuda_ok("gram_kernel launch");
 }
 
 template <int MODE, int SEQ>
-int launch_gram_kb(const Plan& p, uint8_t* ws, cudaStream_t st, int kb, int n_items) {
+int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int n_items) {
   switch (kb) {
-    case 1: return launch_gram<MODE, 128, 1, SEQ>(p, ws, st, n_items);
-    case 2: return launch_gram<MODE, 128, 2, SEQ>(p, ws, st, n_items);
-    case 3: return launch_gram<MODE, 64, 3, SEQ>(p, ws, st, n_items);
-    case 4: return launch_gram<MODE, 64, 4, SEQ>(p, ws, st, n_items);
+    case 1: return launch_gram<MODE, 1, SEQ>(p, sel, ws, st, n_items);
+    case 2: return launch_gram<MODE, 2, SEQ>(p, sel, ws, st, n_items);
+    case 3: return launch_gram<MODE, 3, SEQ>(p, sel, ws, st, n_items);
+    case 4: return launch_gram<MODE, 4, SEQ>(p, sel, ws, st, n_items);
   }
   return FOCAL_ESHAPE;
 }
 
 template <int MODE>
 int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int n_items) {
+  ProbSel sel{};
   switch (p.S) {
-    case 2: return launch_gram_kb<MODE, 2>(p, ws, st, p.kbFull, n_items);
-    case 4: return launch_gram_kb<MODE, 4>(p, ws, st, p.kbFull, n_items);
-    case 8: return launch_gram_kb<MODE, 8>(p, ws, st, p.kbFull, n_items);
-    case 16: return launch_gram_kb<MODE, 16>(p, ws, st, p.kbFull, n_items);
-    case 32: return launch_gram_kb<MODE, 32>(p, ws, st, p.kbFull, n_items);
+    case 2: return launch_gram_kb<MODE, 2>(p, sel, ws, st, p.kbFull, n_items);
+    case 4: return launch_gram_kb<MODE, 4>(p, sel, ws, st, p.kbFull, n_items);
+    case 8: return launch_gram_kb<MODE, 8>(p, sel, ws, st, p.kbFull, n_items);
+    case 16: return launch_gram_kb<MODE, 16>(p, sel, ws, st, p.kbFull, n_items);
+    case 32: return launch_gram_kb<MODE, 32>(p, sel, ws, st, p.kbFull, n_items);
   }
   return FOCAL_ESHAPE;
 }
 
-int nce_items(const Plan& p, bool fwd) {
+// InfoNCE problems are launched in groups of equal operand width (they differ only under noPrivate, where the
+// shared problems use the full D columns and the private ones D/2).
+template <int MODE>
+int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st) {
   const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM;
-  return p.nProb * p.S * 2 * (t1 - t0) * (fwd ? p.nsplit_fwd : 1);
+  for (int kb = 1; kb <= 4; ++kb) {
+    ProbSel sel{};
+    for (int q = 0; q < p.nProb; ++q)
+      if (p.ops[p.probs[q].opA].kb == kb) sel.idx[sel.n++] = q;
+    if (!sel.n) continue;
+    const int items = sel.n * p.S * 2 * (t1 - t0) * (MODE == NCE_FWD ? p.nsplit_fwd : 1);
+    const int rc = launch_gram_kb<MODE, 0>(p, sel, ws, st, kb, items);
+    if (rc) return rc;
+  }
+  return FOCAL_OK;
 }
+
 int tmp_items(const Plan& p) {
   const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
   return p.nT * (t1 - t0);
-}
-
-// InfoNCE launches are grouped by operand width (all problems share it unless noPrivate mixes D and D/2)
-int nce_kb(const Plan& p) { return p.ops[p.probs[0].opA].kb; }
-bool nce_uniform(const Plan& p) {
-  for (int q = 1; q < p.nProb; ++q)
-    if (p.ops[p.probs[q].opA].kb != nce_kb(p)) return false;
-  return true;
 }
 
 int fill_feats(const Plan& p, const float* const* feats, FeatPtrs& f) {
@@ -182,9 +189,7 @@ int focal_b200_nce_rowsum(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* 
   if (rc) return rc;
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
   if (!(p.terms & FOCAL_TERM_NCE)) return FOCAL_OK;
-  if (!nce_uniform(p)) return FOCAL_ESHAPE;
-  return launch_gram_kb<NCE_FWD, 0>(p, static_cast<uint8_t*>(ws), static_cast<cudaStream_t>(stream), nce_kb(p),
-                                    nce_items(p, true));
+  return launch_nce<NCE_FWD>(p, static_cast<uint8_t*>(ws), static_cast<cudaStream_t>(stream));
 }
 
 int focal_b200_nce_lse(const FocalCfg* cfg, void* ws, size_t ws_bytes, int all_rows, void* stream) {
@@ -203,9 +208,7 @@ int focal_b200_nce_grad(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* st
   if (rc) return rc;
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
   if (!(p.terms & FOCAL_TERM_NCE) || !p.need_grad) return FOCAL_OK;
-  if (!nce_uniform(p)) return FOCAL_ESHAPE;
-  return launch_gram_kb<NCE_BWD, 0>(p, static_cast<uint8_t*>(ws), static_cast<cudaStream_t>(stream), nce_kb(p),
-                                    nce_items(p, false));
+  return launch_nce<NCE_BWD>(p, static_cast<uint8_t*>(ws), static_cast<cudaStream_t>(stream));
 }
 
 int focal_b200_temporal(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* stream) {
@@ -295,10 +298,21 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (a_via_st) {
+  const uint32_t a_tmem_col = 256;                 // A operand columns when it lives in tensor memory
+  if (a_via_st == 1) {
     for (uint32_t o = threadIdx.x * 16; o < a_bytes; o += blockDim.x * 16)
       *reinterpret_cast<uint4*>(sa + o) = *reinterpret_cast<const uint4*>(a_img + o);
     fence_proxy_async_smem();
+  } else if (a_via_st == 2) {
+    const uint32_t K = a_bytes / 256;               // bf16 elements per row
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(a_img) + (size_t)threadIdx.x * (K / 2);
+    for (uint32_t g = 0; g < K / 64; ++g) {
+      uint32_t r[32];
+      for (int j = 0; j < 32; ++j) r[j] = rowp[g * 32 + j];
+      tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + a_tmem_col + g * 32, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -307,9 +321,11 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
     tma_load_1d(sb, b_img, b_bytes, &bar_load);
     mbar_wait(&bar_load, 0);
     tc_fence_after();
-    for (uint32_t k = 0; k < ksteps; ++k)
-      umma_bf16(tmem, umma_smem_desc(smem_u32(sa) + k * a_kstep, a_lbo, a_sbo),
-                umma_smem_desc(smem_u32(sb) + k * b_kstep, b_lbo, b_sbo), idesc, k > 0);
+    for (uint32_t k = 0; k < ksteps; ++k) {
+      const uint64_t db = umma_smem_desc(smem_u32(sb) + k * b_kstep, b_lbo, b_sbo);
+      if (a_via_st == 2) umma_bf16_ts(tmem, tmem + a_tmem_col + k * 8, db, idesc, k > 0);
+      else umma_bf16(tmem, umma_smem_desc(smem_u32(sa) + k * a_kstep, a_lbo, a_sbo), db, idesc, k > 0);
+    }
     umma_commit(&bar_mma);
   }
   mbar_wait(&bar_mma, 0);
@@ -341,4 +357,79 @@ extern "C" int focal_b200_debug_umma(const void* a_img, uint32_t a_bytes, const 
       static_cast<const uint8_t*>(a_img), a_bytes, static_cast<const uint8_t*>(b_img), b_bytes, idesc, a_lbo, a_sbo,
       a_kstep_bytes, b_lbo, b_sbo, b_kstep_bytes, ksteps, ncols, a_via_st, d_out);
   return cuda_ok("umma_probe_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bring-up micro-benchmark: cycles per tcgen05.mma (M = 128) for a given N / operand placement.
+// The issue loop is fully unrolled with precomputed descriptors so that the tensor pipe, not the issuing
+// thread, is what is measured.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+template <int N, int B_MN, int A_TMEM>
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(uint32_t iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t o = threadIdx.x * 16; o < 64 * 1024 + 128 * 1024; o += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 64 * 1024);
+    constexpr uint32_t idesc = umma_idesc(UMMA_BF16, 128, N, 0, B_MN);
+    const uint64_t da0 = umma_smem_desc(a_addr, 16, 1024);
+    const uint64_t db0 = B_MN ? umma_smem_desc(b_addr, 128 * 128, 1024) : umma_smem_desc(b_addr, 16, 1024);
+    const long long t0 = clock64();
+    for (uint32_t it = 0; it < iters; ++it) {
+      const uint32_t d = tmem + (it & 1) * (A_TMEM ? 128 : 256) * (N > 128 && A_TMEM ? 0 : 1);
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) {
+        const uint64_t da = da0 + (((k >> 2) * 16384 + (k & 3) * 32) >> 4);
+        const uint64_t db = db0 + ((B_MN ? k * 2048 : (k >> 2) * (N * 128) + (k & 3) * 32) >> 4);
+        if (A_TMEM) umma_bf16_ts(d, tmem + 384 + k * 8, db, idesc, k > 0);
+        else umma_bf16(d, da, db, idesc, k > 0);
+      }
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+template <int N, int B_MN, int A_TMEM>
+int launch_rate(uint32_t iters, uint32_t grid, long long* cycles, cudaStream_t st) {
+  const uint32_t smem = 64 * 1024 + 128 * 1024 + 1024;
+  auto k = umma_rate_kernel<N, B_MN, A_TMEM>;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return cuda_ok("cudaFuncSetAttribute(umma_rate_kernel)");
+  k<<<grid, 128, smem, st>>>(iters, cycles);
+  return cuda_ok("umma_rate_kernel");
+}
+}  // namespace
+
+// 8 MMAs (K = 16 each) per iteration; returns per-CTA cycles for `iters` iterations.
+extern "C" int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t iters, uint32_t /*unused*/, uint32_t grid,
+                                          long long* cycles, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t b_mn = flags & 1, a_tmem = (flags >> 1) & 1;
+#define FB_RATE(NN)                                                                      \
+  if (N == NN) {                                                                         \
+    if (!b_mn && !a_tmem) return launch_rate<NN, 0, 0>(iters, grid, cycles, st);         \
+    if (b_mn && !a_tmem) return launch_rate<NN, 1, 0>(iters, grid, cycles, st);          \
+    if (!b_mn && a_tmem) return launch_rate<NN, 0, 1>(iters, grid, cycles, st);          \
+    return launch_rate<NN, 1, 1>(iters, grid, cycles, st);                               \
+  }
+  FB_RATE(32) FB_RATE(64) FB_RATE(96) FB_RATE(128) FB_RATE(192) FB_RATE(256)
+#undef FB_RATE
+  return FOCAL_EINVAL;
 }

@@ -3,17 +3,26 @@
 // One persistent, warp-specialised kernel template serves the four dense passes of the FOCAL loss:
 //
 //   NCE_FWD   G = Z_I Z_J^T (log2-domain logits)  -> row sums  sum_{j != k} 2^G            (loss.py:74-85)
-//   NCE_BWD   recompute G, W = 2^G (1/r_k + 1/r_j) -> O += W Z_J  (second UMMA, W via smem) (autograd of the above)
+//   NCE_BWD   recompute G, W = 2^G (1/r_k + 1/r_j) -> O += W Z_J  (second UMMA, W from TMEM) (autograd of the above)
 //   TMP_FWD   G = X_I X_J^T -> delta = sqrt(n_i+n_j-2G) -> S x S block means -> hinge        (loss.py:113-135)
 //   TMP_BWD   same pass + r_ij = coef_IJ / delta_ij -> O += R X_J                           (fwd + bwd fused)
 //
 // The N x N logit / distance matrices are never written to memory.  Operands are bf16 tiles that the prologue
 // laid out in HBM exactly as the UMMA wants them in shared memory (K-block-major, 128-byte rows, SWIZZLE_128B),
-// so each tile is a single linear TMA bulk copy.  Roles: warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM
-// owner), warps 2..9 = two epilogue warpgroups that alternate column tiles (each owns one S stage in TMEM and one
-// W buffer in shared memory; within a warpgroup each warp owns one TMEM lane quarter).  Two warpgroups put two
-// epilogue warps on every SM sub-partition so the MUFU / FMA chains of one hide behind the other.
-// Row tile = 128 rows (UMMA M), column tile = BN.
+// so each tile is a single linear TMA bulk copy per K block.
+//
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM owner), warps 2..9 = two epilogue
+// warpgroups that alternate column tiles (each owns one S stage in TMEM; within a warpgroup each warp owns one
+// TMEM lane quarter).  Two warpgroups put two epilogue warps on every SM sub-partition so the MUFU / FMA chains of
+// one hide behind the other.
+//
+// Tensor memory (512 columns): O accumulator [0, KB*64), S stages at KB*64 + {0, BN}.  In the backward modes the
+// epilogue overwrites the S stage it just consumed with W as packed bf16 (tcgen05.st) and UMMA #2 reads its A
+// operand straight from TMEM -- W never touches shared memory.
+//
+// Measured on B200 (tools/umma_rate.py): one thread can issue a tcgen05.mma about every 45 clk and an M=128, K=16
+// instruction occupies the tensor pipe N/2 clk, so N >= 96 is needed to stay tensor-bound; the issue loop below is
+// fully unrolled with precomputed descriptors for that reason.  Row tile = 128 rows (UMMA M), column tile = BN.
 #pragma once
 #include "plan.h"
 #include "ptx.cuh"
@@ -25,29 +34,27 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 constexpr int kGramThreads = 64 + 256;
 constexpr int kEpiThreads = 256;
 constexpr int kNumBStages = 3;
-constexpr int kNumWStages = 2;
 constexpr int kTmemCols = 512;
 
 template <int BN, int KB>
 struct GramSmem {
   static constexpr uint32_t kABytes = KB * 128 * 128;           // [KB][128 rows][128 B]
   static constexpr uint32_t kBTile = KB * BN * 128;             // [KB][BN rows][128 B]
-  static constexpr uint32_t kColVec = 2 * BN * 4;               // two per-column fp32 vectors
-  static constexpr uint32_t kBStage = kBTile + 1024;            // tile + column vectors, keeps 1024-B alignment
-  static constexpr uint32_t kWStage = (BN / 64) * 128 * 128;    // [BN/64][128 rows][128 B]  (A operand of UMMA #2)
+  static constexpr uint32_t kBStage = kBTile + 1024;            // tile + two per-column fp32 vectors
   static constexpr uint32_t kAOff = 0;
   static constexpr uint32_t kBOff = kAOff + kABytes;
-  static constexpr uint32_t kWOff = kBOff + kNumBStages * kBStage;
-  static constexpr uint32_t kBarOff = kWOff + kNumWStages * kWStage;
+  static constexpr uint32_t kBarOff = kBOff + kNumBStages * kBStage;
   static constexpr uint32_t kTotal = kBarOff + 2048;
   static constexpr uint32_t kDynamic = kTotal + 1024;           // slack for manual 1024-B alignment
+  static_assert(2 * BN * 4 <= 1024, "column vectors fit the stage tail");
+  static_assert((BN * 128) % 1024 == 0, "K blocks of a B tile stay 1024-B aligned");
 };
 
 struct GramBars {
   uint64_t a_full, a_empty;
   uint64_t b_full[kNumBStages], b_empty[kNumBStages];
   uint64_t s_full[2], s_empty[2];
-  uint64_t w_full[kNumWStages], w_empty[kNumWStages];
+  uint64_t w_full[2];
   uint64_t o_full, o_empty;
   uint32_t tmem_base;
   float red[4];
@@ -58,38 +65,39 @@ struct GramBars {
 static_assert(sizeof(GramBars) <= 2048, "barrier block");
 
 // ---------------------------------------------------------------------------------------------------------
-// work-item decoding
+// work-item decoding (everything a role needs about one 128-row block; no arrays, lives in registers)
 // ---------------------------------------------------------------------------------------------------------
 struct Item {
-  const uint8_t* a_src;        // first K block of the A tile; K blocks are a_kstride bytes apart
-  uint64_t a_kstride;
-  const uint8_t* b_src[2];     // column side 0 / 1 operand base (row 0, K block 0)
-  uint64_t b_kstride;
-  const float* colvec0[2];     // per-column vectors of side 0 / 1 (row 0)
-  const float* colvec1[2];
+  const uint8_t* a_src;        // first K block of the A tile
+  const uint8_t* b_src0;       // column side 0 / 1 operand base (row 0, K block 0)
+  const uint8_t* b_src1;
+  uint64_t kstride;            // bytes between K blocks of the operand arrays
+  const float* cv0_0;          // per-column vector #0 of side 0 / 1 (NCE: 1/rowsum, TMP: squared norms)
+  const float* cv0_1;
+  const float* cv1;            // per-column vector #1 (TMP: m_JJ); same for both sides
   int ct_begin, ct_end;        // global column tile range
   int ntc;                     // column tiles per side
   int row0;                    // first row (within side / tensor) of the row tile
   int side;                    // NCE: which half of z the rows come from
   int ncol_valid;              // valid columns per side (b for NCE, B for TMP)
   int row_lo, row_hi;          // owned rows [lo, hi) within the side
-  int q, s, c;                 // problem / position / call
+  int q, s, c;                 // problem / position / (split or call)
 };
 
-template <int MODE, int BN, int KB>
-__device__ __forceinline__ int gram_num_items(const Plan& p) {
+template <int MODE>
+__device__ __forceinline__ int gram_num_items(const Plan& p, const ProbSel& sel) {
   if (MODE == NCE_FWD || MODE == NCE_BWD) {
     const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM;
     const int nsp = (MODE == NCE_FWD) ? p.nsplit_fwd : 1;
-    return p.nProb * p.S * 2 * (t1 - t0) * nsp;
+    return sel.n * p.S * 2 * (t1 - t0) * nsp;
   } else {
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
     return p.nT * (t1 - t0);
   }
 }
 
-template <int MODE, int BN, int KB>
-__device__ __forceinline__ void gram_decode(const Plan& p, const uint8_t* ws, int it, Item& x) {
+template <int MODE, int BN>
+__device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, const uint8_t* ws, int it, Item& x) {
   if (MODE == NCE_FWD || MODE == NCE_BWD) {
     const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM, nrt = t1 - t0;
     const int nsp = (MODE == NCE_FWD) ? p.nsplit_fwd : 1;
@@ -98,18 +106,14 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const uint8_t* ws, in
     const int rt = t0 + r % nrt; r /= nrt;
     const int side = r % 2; r /= 2;
     const int s = r % p.S; r /= p.S;
-    const int q = r;
+    const int q = sel.idx[r];
     const ProbDesc& pr = p.probs[q];
-    const OpDesc& oa = p.ops[pr.opA];
-    const OpDesc& ob = p.ops[pr.opB];
-    const uint64_t rowsNce = (uint64_t)p.S * p.bpad;
-    x.b_kstride = x.a_kstride = rowsNce * 128;
-    x.b_src[0] = ws + oa.off + (uint64_t)s * p.bpad * 128;
-    x.b_src[1] = ws + ob.off + (uint64_t)s * p.bpad * 128;
-    x.a_src = x.b_src[side] + (uint64_t)rt * kTileM * 128;
+    x.kstride = (uint64_t)p.S * p.bpad * 128;
+    x.b_src0 = ws + p.ops[pr.opA].off + (uint64_t)s * p.bpad * 128;
+    x.b_src1 = ws + p.ops[pr.opB].off + (uint64_t)s * p.bpad * 128;
+    x.a_src = (side ? x.b_src1 : x.b_src0) + (uint64_t)rt * kTileM * 128;
     const float* rinv = reinterpret_cast<const float*>(ws + p.rinv_off) + ((uint64_t)(q * p.S + s) * 2) * p.bpad;
-    x.colvec0[0] = rinv; x.colvec0[1] = rinv + p.bpad;
-    x.colvec1[0] = x.colvec1[1] = nullptr;
+    x.cv0_0 = rinv; x.cv0_1 = rinv + p.bpad; x.cv1 = rinv;
     x.ntc = (p.b + BN - 1) / BN;
     const int nct = 2 * x.ntc;
     x.ct_begin = (int)((long)nct * sp / nsp);
@@ -121,11 +125,11 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const uint8_t* ws, in
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM, nrt = t1 - t0;
     const int rt = t0 + it % nrt;
     const int c = it / nrt;
-    x.b_kstride = x.a_kstride = (uint64_t)p.Bpad * 128;
-    x.b_src[0] = x.b_src[1] = ws + p.xt_off + (uint64_t)c * p.kbFull * p.Bpad * 128;
-    x.a_src = x.b_src[0] + (uint64_t)rt * kTileM * 128;
-    x.colvec0[0] = x.colvec0[1] = reinterpret_cast<const float*>(ws + p.sq_off) + (uint64_t)c * p.Bpad;
-    x.colvec1[0] = x.colvec1[1] = reinterpret_cast<const float*>(ws + p.mintra_off) + (uint64_t)c * p.Bpad;
+    x.kstride = (uint64_t)p.Bpad * 128;
+    x.b_src0 = x.b_src1 = ws + p.xt_off + (uint64_t)c * p.kbFull * p.Bpad * 128;
+    x.a_src = x.b_src0 + (uint64_t)rt * kTileM * 128;
+    x.cv0_0 = x.cv0_1 = reinterpret_cast<const float*>(ws + p.sq_off) + (uint64_t)c * p.Bpad;
+    x.cv1 = reinterpret_cast<const float*>(ws + p.mintra_off) + (uint64_t)c * p.Bpad;
     x.ntc = (p.B + BN - 1) / BN;
     x.ct_begin = 0; x.ct_end = x.ntc;
     x.row0 = rt * kTileM; x.side = 0; x.ncol_valid = p.B;
@@ -134,19 +138,33 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const uint8_t* ws, in
   }
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
 template <int MODE, int BN, int KB, int SEQ>
-__global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws) {
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel, uint8_t* __restrict__ ws) {
   using L = GramSmem<BN, KB>;
   constexpr bool kIsNce = (MODE == NCE_FWD || MODE == NCE_BWD);
   constexpr bool kBwd = (MODE == NCE_BWD || MODE == TMP_BWD);
   constexpr bool kColVec = (MODE != NCE_FWD);
   constexpr int kON = KB * 64;                       // UMMA #2 N = padded operand width
-  constexpr uint32_t kSCol = 0;                      // TMEM: S stages at columns [0, 2*BN)
-  constexpr uint32_t kOCol = 2 * BN;                 // TMEM: O accumulator at [2*BN, 2*BN + kON)
-  static_assert(2 * BN + kON <= kTmemCols, "TMEM budget");
+  constexpr int kKSteps = KB * 4;                    // UMMA #1 K steps (K padded to 64 with zeros)
+  constexpr uint32_t kOCol = 0;                      // TMEM: O accumulator at [0, kON)
+  constexpr uint32_t kSCol = kON;                    // TMEM: S stages at kON + {0, BN}
+  static_assert(kON + 2 * BN <= kTmemCols, "TMEM budget");
+  static_assert(BN % 32 == 0 && BN % 16 == 0, "column tile");
   static_assert(L::kDynamic <= 232448, "shared memory budget");
 
   extern __shared__ uint8_t smem_raw[];
@@ -161,8 +179,11 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       mbar_init(&bars->b_full[i], 1);
       mbar_init(&bars->b_empty[i], kColVec ? 1 + 4 : 1);    // UMMA commit (+ one elected lane per epilogue warp)
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 128); }
-    for (int i = 0; i < kNumWStages; ++i) { mbar_init(&bars->w_full[i], 128); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_empty[i], 128);
+      mbar_init(&bars->w_full[i], 128);
+    }
     mbar_init(&bars->o_full, 1);
     mbar_init(&bars->o_empty, kEpiThreads);
     fence_mbar_init();
@@ -175,8 +196,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-
-  const int n_items = gram_num_items<MODE, BN, KB>(p);
+  const int n_items = gram_num_items<MODE>(p, sel);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -184,27 +204,26 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       uint32_t nb = 0, ni = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
         Item x;
-        gram_decode<MODE, BN, KB>(p, ws, it, x);
+        gram_decode<MODE, BN>(p, sel, ws, it, x);
         mbar_wait(&bars->a_empty, (ni & 1) ^ 1);
         mbar_arrive_expect_tx(&bars->a_full, L::kABytes);
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
-          tma_load_1d(smem + L::kAOff + kb * 16384, x.a_src + kb * x.a_kstride, 16384, &bars->a_full);
+          tma_load_1d(smem + L::kAOff + kb * 16384, x.a_src + kb * x.kstride, 16384, &bars->a_full);
         for (int ct = x.ct_begin; ct < x.ct_end; ++ct, ++nb) {
           const uint32_t st = nb % kNumBStages;
-          const int cs = ct / x.ntc, tc = ct - cs * x.ntc;
+          const int cs = ct >= x.ntc ? 1 : 0, tc = ct - cs * x.ntc;
+          const uint8_t* src = (cs ? x.b_src1 : x.b_src0) + (uint64_t)tc * BN * 128;
           mbar_wait(&bars->b_empty[st], ((nb / kNumBStages) & 1) ^ 1);
           uint8_t* dst = smem + L::kBOff + st * L::kBStage;
-          uint32_t bytes = L::kBTile;
-          if (kColVec) bytes += (kIsNce ? 1 : 2) * BN * 4;
+          constexpr uint32_t bytes = L::kBTile + (kColVec ? (kIsNce ? 1 : 2) * BN * 4 : 0);
           mbar_arrive_expect_tx(&bars->b_full[st], bytes);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb)
-            tma_load_1d(dst + kb * (BN * 128), x.b_src[cs] + kb * x.b_kstride + (uint64_t)tc * BN * 128, BN * 128,
-                        &bars->b_full[st]);
+            tma_load_1d(dst + kb * (BN * 128), src + kb * x.kstride, BN * 128, &bars->b_full[st]);
           if (kColVec) {
-            tma_load_1d(dst + L::kBTile, x.colvec0[cs] + tc * BN, BN * 4, &bars->b_full[st]);
-            if (!kIsNce) tma_load_1d(dst + L::kBTile + BN * 4, x.colvec1[cs] + tc * BN, BN * 4, &bars->b_full[st]);
+            tma_load_1d(dst + L::kBTile, (cs ? x.cv0_1 : x.cv0_0) + tc * BN, BN * 4, &bars->b_full[st]);
+            if (!kIsNce) tma_load_1d(dst + L::kBTile + BN * 4, x.cv1 + tc * BN, BN * 4, &bars->b_full[st]);
           }
         }
       }
@@ -213,13 +232,14 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     // =============================== UMMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc(UMMA_BF16, 128, BN, 0, 0);     // S = A(K-major) * B(K-major)^T
-      constexpr uint32_t idesc2 = umma_idesc(UMMA_BF16, 128, kON, 0, 1);    // O += W(K-major) * B(MN-major)
-      const uint32_t a_addr = smem_u32(smem + L::kAOff);
+      constexpr uint32_t idesc2 = umma_idesc(UMMA_BF16, 128, kON, 0, 1);    // O += W(TMEM) * B(MN-major)
+      const uint64_t da0 = umma_smem_desc(smem_u32(smem + L::kAOff), 16, 1024);
+      const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
+      const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
       uint32_t nb = 0, ni = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
         Item x;
-        gram_decode<MODE, BN, KB>(p, ws, it, x);
-        const int ksteps = kIsNce ? (p.ops[p.probs[x.q].opA].width + 15) / 16 : (p.D + 15) / 16;
+        gram_decode<MODE, BN>(p, sel, ws, it, x);
         mbar_wait(&bars->a_full, ni & 1);
         const int ntiles = x.ct_end - x.ct_begin;
         for (int t = 0; t <= ntiles; ++t) {
@@ -227,32 +247,31 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
             // ---- UMMA #1 of tile t
             const uint32_t n = nb + t, st = n % kNumBStages, ss = n & 1;
             mbar_wait(&bars->b_full[st], (n / kNumBStages) & 1);
-            mbar_wait(&bars->s_empty[ss], ((n >> 1) & 1) ^ 1);
+            // backward modes: the S stage is free once UMMA #2 of tile t-2 has been issued (program order);
+            // forward modes: once the epilogue has drained it
+            if (!kBwd) mbar_wait(&bars->s_empty[ss], ((n >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(smem + L::kBOff + st * L::kBStage);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t ko = (k >> 2) * 16384 + (k & 3) * 32;
-              const uint32_t kob = (k >> 2) * (BN * 128) + (k & 3) * 32;
-              umma_bf16(tmem + kSCol + ss * BN, umma_smem_desc(a_addr + ko, 16, 1024),
-                        umma_smem_desc(b_addr + kob, 16, 1024), idesc1, k > 0);
-            }
+            const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
+            const uint32_t d = tmem + kSCol + ss * BN;
+#pragma unroll
+            for (int k = 0; k < kKSteps; ++k)
+              umma_bf16(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                        db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
             umma_commit(&bars->s_full[ss]);
             if (!kBwd) umma_commit(&bars->b_empty[st]);
           }
           if (kBwd && t > 0) {
             // ---- UMMA #2 of tile t-1 (issued after UMMA #1 of tile t so the tensor pipe never waits on the epilogue)
-            const uint32_t n = nb + t - 1, st = n % kNumBStages, wsg = n % kNumWStages;
+            const uint32_t n = nb + t - 1, st = n % kNumBStages, ss = n & 1;
             if (t == 1) mbar_wait(&bars->o_empty, (ni & 1) ^ 1);
-            mbar_wait(&bars->w_full[wsg], (n / kNumWStages) & 1);
+            mbar_wait(&bars->w_full[ss], (n >> 1) & 1);
             tc_fence_after();
-            const uint32_t w_addr = smem_u32(smem + L::kWOff + wsg * L::kWStage);
-            const uint32_t b_addr = smem_u32(smem + L::kBOff + st * L::kBStage);
+            const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4));
+            const uint32_t a = tmem + kSCol + ss * BN;        // W: packed bf16 over the consumed S stage
+            const uint32_t acc = (t > 1) ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < BN / 16; ++k) {
-              umma_bf16(tmem + kOCol, umma_smem_desc(w_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                        umma_smem_desc(b_addr + k * 2048, BN * 128, 1024), idesc2, (t > 1) || (k > 0));
-            }
-            umma_commit(&bars->w_empty[wsg]);
+            for (int k = 0; k < BN / 16; ++k)
+              umma_bf16_ts(tmem + kOCol, a + k * 8, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
             umma_commit(&bars->b_empty[st]);
           }
         }
@@ -265,7 +284,6 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     }
   } else {
     // =============================== epilogue warps ===============================
-    static_assert(kNumWStages == 2, "one W buffer per epilogue warpgroup");
     const int wg = (warp - 2) >> 2;                   // epilogue warpgroup: handles tiles with (tile counter & 1) == wg
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;             // row within the tile == TMEM lane
@@ -274,40 +292,42 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     const float inv_cnt = 1.f / (float)(SQ * SQ);
     const float coef1 = -1.f / ((float)p.b * (float)(p.b - 1) * (float)(SQ * SQ));
     const float coef2 = 2.f * coef1;
+    const float margin = p.margin;
+    const uint32_t cv_base = smem_u32(smem + L::kBOff + L::kBTile);
     uint32_t nb = 0, ni = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
       Item x;
-      gram_decode<MODE, BN, KB>(p, ws, it, x);
-      const int row = x.row0 + trow;                  // row within side (NCE: sequence index k) / tensor (TMP: i)
-      const bool row_ok = row < x.ncol_valid && row >= x.row_lo && row < x.row_hi;
+      gram_decode<MODE, BN>(p, sel, ws, it, x);
+      const int row0 = x.row0, ncol_valid = x.ncol_valid, side = x.side, ntc = x.ntc, ct_begin = x.ct_begin;
+      const int row = row0 + trow;                    // row within side (NCE: sequence index k) / tensor (TMP: i)
+      const bool row_ok = row < ncol_valid && row >= x.row_lo && row < x.row_hi;
       float rowacc = 0.f;                             // NCE_FWD: row sum; TMP: rho_i
       float ck = 0.f, n_i = 0.f, mim = -1e30f, hinge_acc = 0.f;
       int cnt_i = 0;
-      if (MODE == NCE_BWD && row_ok) ck = x.colvec0[x.side][row];
-      if (!kIsNce && row_ok) { n_i = x.colvec0[0][row]; mim = x.colvec1[0][row] + p.margin; }   // m_II + margin
+      if (MODE == NCE_BWD && row_ok) ck = (side ? x.cv0_1 : x.cv0_0)[row];
+      if (!kIsNce && row_ok) { n_i = x.cv0_0[row]; mim = x.cv1[row] + margin; }   // m_II + margin
       const int seq_i = row / SQ;
-      const int ntiles = x.ct_end - x.ct_begin;
+      const int ntiles = x.ct_end - ct_begin;
       for (int t = (wg - (int)nb) & 1; t < ntiles; t += 2) {
         const uint32_t n = nb + t, st = n % kNumBStages;
-        const uint32_t ss = wg, wsg = wg;             // (n & 1) == wg
-        const int ct = x.ct_begin + t;
-        const int cs = ct / x.ntc, tc = ct - cs * x.ntc;
+        const uint32_t ss = wg;                       // (n & 1) == wg
+        const int ct = ct_begin + t;
+        const int cs = ct >= ntc ? 1 : 0, tc = ct - cs * ntc;
         const int col0 = tc * BN;                     // first column (within side) of this tile
-        const float* cv = reinterpret_cast<const float*>(smem + L::kBOff + st * L::kBStage + L::kBTile);
-        uint8_t* wbuf = smem + L::kWOff + wsg * L::kWStage;
+        const uint32_t cv = cv_base + st * L::kBStage;
         if (kColVec) mbar_wait(&bars->b_full[st], (n / kNumBStages) & 1);
         mbar_wait(&bars->s_full[ss], (n >> 1) & 1);
         tc_fence_after();
-        if (kBwd) mbar_wait(&bars->w_empty[wsg], ((n >> 1) & 1) ^ 1);
-        const bool tail = col0 + BN > x.ncol_valid;
+        const bool tail = col0 + BN > ncol_valid;
         // columns to drop: j == k (same side) always; in the backward pass also the positive p(k) (other side,
         // same sequence index), whose contribution the finalize kernel adds in fp32
-        const bool overlap = col0 < x.row0 + kTileM && col0 + BN > x.row0;
-        const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == x.side)) : overlap;
+        const bool overlap = col0 < row0 + kTileM && col0 + BN > row0;
+        const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == side)) : overlap;
+        const uint32_t s_addr = tmem + tlane + kSCol + ss * BN;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           float v[32];
-          tmem_ld32(tmem + tlane + kSCol + ss * BN + ch * 32, v);
+          tmem_ld32(s_addr + ch * 32, v);
           tmem_ld_wait();
           const int cbase = col0 + ch * 32;           // column (within side) of v[0]
           if (kIsNce) {
@@ -318,7 +338,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
               // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 cj = *reinterpret_cast<const float4*>(cv + ch * 32 + j);
+                const float4 cj = lds128(cv + (ch * 32 + j) * 4);
                 v[j] *= ck + cj.x; v[j + 1] *= ck + cj.y; v[j + 2] *= ck + cj.z; v[j + 3] *= ck + cj.w;
               }
             }
@@ -326,7 +346,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int col = cbase + j;
-                if ((diag && col == row) || col >= x.ncol_valid) v[j] = 0.f;
+                if ((diag && col == row) || col >= ncol_valid) v[j] = 0.f;
               }
             }
             if (MODE == NCE_FWD) {
@@ -340,8 +360,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
             float nj[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(cv + ch * 32 + j);
-              nj[j] = t4.x; nj[j + 1] = t4.y; nj[j + 2] = t4.z; nj[j + 3] = t4.w;
+              const float4 t4 = lds128(cv + (ch * 32 + j) * 4);
+              nj[j] = n_i + t4.x; nj[j + 1] = n_i + t4.y; nj[j + 2] = n_i + t4.z; nj[j + 3] = n_i + t4.w;
             }
 #pragma unroll
             for (int g0 = 0; g0 < 32; g0 += SQ) {
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < SQ; ++j) {
                 // cdist mm form; the floor keeps 1/delta finite for coincident rows (their r_ij (x_i - x_j) is 0)
-                const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], n_i + nj[g0 + j]), 1e-12f);
+                const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], nj[g0 + j]), 1e-12f);
                 const float rs = rsqrt_approx(d2);                    // 1 / delta
                 v[g0 + j] = rs;
                 gsum = fmaf(d2, rs, gsum);                            // delta = d2 / delta
@@ -358,9 +378,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
               for (int o = 1; o < SQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
               const int colg = cbase + g0;
               const float m_ij = gsum * inv_cnt;
-              const float mjm = cv[BN + ch * 32 + g0] + p.margin;     // m_JJ + margin
+              const float mjm = lds32(cv + (BN + ch * 32 + g0) * 4) + margin;   // m_JJ + margin
               bool pair_ok = row_ok;
-              if (tail) pair_ok = pair_ok && colg < x.ncol_valid;
+              if (tail) pair_ok = pair_ok && colg < ncol_valid;
               if (diag) pair_ok = pair_ok && (colg / SQ) != seq_i;    // the block diagonal is done exactly elsewhere
               const float h = pair_ok ? mim - m_ij : -1.f;           // hinge argument; active at equality
               const bool a_ij = h >= 0.f;
@@ -373,25 +393,20 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
             }
           }
           if (kBwd) {
-            // ---------------- W tile: bf16, K-major SWIZZLE_128B, row = trow (A operand of UMMA #2)
-            const int kb2 = (ch * 32) / 64, c0 = ((ch * 32) % 64) / 8;
+            // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed
+            uint32_t pk[16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 pk;
-              pk.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]);
-              pk.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
-              pk.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
-              pk.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-              *reinterpret_cast<uint4*>(wbuf + kb2 * 16384 + swz128(trow, c0 + c)) = pk;
-            }
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            tmem_st16(s_addr + ch * 16, pk);
           }
         }
-        // S stage drained (all tcgen05.ld of this thread completed above)
-        tc_fence_before();
-        mbar_arrive(&bars->s_empty[ss]);
         if (kBwd) {
-          fence_proxy_async_smem();
-          mbar_arrive(&bars->w_full[wsg]);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bars->w_full[ss]);
+        } else {
+          tc_fence_before();
+          mbar_arrive(&bars->s_empty[ss]);             // S stage drained (all tcgen05.ld of this thread completed)
         }
         if (kColVec) {
           __syncwarp();
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
           rowacc += bars->part_acc[trow];
           if (MODE == NCE_FWD) {
             float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) +
-                           ((((uint64_t)x.c * p.nProb + x.q) * p.S + x.s) * 2 + x.side) * p.bpad;
+                           ((((uint64_t)x.c * p.nProb + x.q) * p.S + x.s) * 2 + side) * p.bpad;
             rpart[row] = row_ok ? rowacc : 0.f;
           } else {
             hinge_acc += bars->part_hinge[trow];
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
         float* out;
         if (kIsNce) {
           out = reinterpret_cast<float*>(ws + p.probs[x.q].dz_off) +
-                ((uint64_t)x.side * p.S * p.bpad + (uint64_t)x.s * p.bpad + row) * kON;
+                ((uint64_t)side * p.S * p.bpad + (uint64_t)x.s * p.bpad + row) * kON;
         } else {
           out = reinterpret_cast<float*>(ws + p.dx_off) + ((uint64_t)x.c * p.Bpad + row) * kON;
         }
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
         if (!kIsNce && wg == 0 && trow == 0) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
-          const int slot = x.c * nrt + (x.row0 / kTileM - t0);
+          const int slot = x.c * nrt + (row0 / kTileM - t0);
           reinterpret_cast<float*>(ws + p.part3_off)[slot] =
               ((bars->red[0] + bars->red[1]) + (bars->red[2] + bars->red[3])) / ((float)p.b * (float)(p.b - 1));
         }

@@ -29,6 +29,16 @@ struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
   int32_t tu, cu, tv, cv, width;
 };
 
+// Column-tile width of the Gram kernels as a function of the operand width in 64-element K blocks.  TMEM holds
+// O (kb*64 columns) + two S stages (2*BN): kb = 4 leaves room for BN = 96 only (see gram_kernel.cuh).
+constexpr int tile_bn(int kb) { return kb >= 4 ? 96 : 128; }
+
+// Problems handled by one InfoNCE launch (all with the same operand width / K-block count).
+struct ProbSel {
+  int32_t n;
+  int32_t idx[kMaxProb];
+};
+
 struct Plan {
   // dims
   int32_t B, S, M, D, d, b, bpad, Bpad, nT, nOps, nProb, nOrth, kbFull, seq0, seq1, need_grad, terms, num_sms;
@@ -73,10 +83,19 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   if (c.precision != FOCAL_PREC_BF16) return FOCAL_EINVAL;
   p.B = c.B; p.S = c.S; p.M = c.M; p.D = c.D; p.d = c.D / 2;
   p.b = c.B / c.S;
-  p.bpad = (int32_t)align_up(p.b, kTileM);
-  p.Bpad = (int32_t)align_up(p.B, kTileM);
   p.nT = 2 * c.M;
   p.kbFull = (c.D + kKBlk - 1) / kKBlk;
+  {
+    // rows are padded so that every 128-row A tile and every BN-row B tile stays inside the operand arrays
+    auto pad_rows = [](int rows, int bn) {
+      const int by_tile = (rows + bn - 1) / bn * bn;
+      return (int32_t)align_up((uint64_t)(by_tile > rows ? by_tile : rows), kTileM);
+    };
+    const int kbHalf = (p.d + kKBlk - 1) / kKBlk;
+    p.bpad = pad_rows(p.b, tile_bn(kbHalf));
+    if (c.no_private) { const int32_t alt = pad_rows(p.b, tile_bn(p.kbFull)); if (alt > p.bpad) p.bpad = alt; }
+    p.Bpad = pad_rows(p.B, tile_bn(p.kbFull));
+  }
   p.seq0 = c.seq_begin; p.seq1 = c.seq_end;
   if (p.seq0 < 0 || p.seq1 > p.b || p.seq0 >= p.seq1) return FOCAL_EINVAL;
   p.need_grad = c.need_grad; p.terms = c.terms ? c.terms : FOCAL_TERM_ALL;
@@ -124,11 +143,10 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
 
   // ---- column split of the row-sum pass: pick the split with the best wave quantisation
   {
-    const int nt = p.bpad / kTileM;
+    const int nt = (p.b + kTileM - 1) / kTileM;
     const long items = (long)p.nProb * p.S * 2 * nt;   // upper bound (all row tiles)
     int best = 1; double best_eff = 0;
     for (int sp = 1; sp <= 4; ++sp) {
-      if (2 * nt % sp) continue;
       long it = items * sp;
       long waves = (it + num_sms - 1) / num_sms;
       double eff = (double)it / (double)(waves * num_sms);

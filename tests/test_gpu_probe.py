@@ -67,3 +67,23 @@ def test_mnmajor_second_gemm(Nd):
                     Kj // 16, Nd, 1)
     ref = W.float() @ Z.float()
     assert torch.allclose(out, ref, rtol=1e-5, atol=1e-4), float((out - ref).abs().max())
+
+
+@pytest.mark.parametrize("N,b_mn", [(64, 0), (128, 0), (128, 1), (256, 1)])
+def test_a_operand_from_tensor_memory(N, b_mn):
+    """TS mode: A lives in TMEM (lane = row, 32-bit column j = bf16 elements 2j, 2j+1), written with tcgen05.st;
+    B is the usual swizzled smem tile, K-major (UMMA #1) or MN-major (UMMA #2)."""
+    _require_cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    K = 64
+    A = torch.randn(128, K, device="cuda", generator=g).to(torch.bfloat16)
+    a_img = A.contiguous().view(torch.uint8).reshape(-1)
+    if b_mn:
+        Z = torch.randn(K, N, device="cuda", generator=g).to(torch.bfloat16)
+        out = run_probe(a_img, swizzled_image(Z), idesc(128, N, 0, 1), 0, 0, 0, K * 128, 1024, 2048, K // 16, N, 2)
+        ref = A.float() @ Z.float()
+    else:
+        Bm = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+        out = run_probe(a_img, swizzled_image(Bm), idesc(128, N), 0, 0, 0, 16, 1024, 32, K // 16, N, 2)
+        ref = A.float() @ Bm.float().T
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-4), float((out - ref).abs().max())
