@@ -6,6 +6,7 @@
 #include "gram_kernel.cuh"
 #include "plan.h"
 #include "row_kernels.cuh"
+#include "row_kernels_fast.cuh"
 
 using namespace fb;
 
@@ -105,6 +106,56 @@ int tmp_items(const Plan& p) {
   return p.nT * (t1 - t0);
 }
 
+// lanes own VW = d/32 consecutive columns per half on the vectorised row-kernel path (0 = use the generic kernels)
+int fast_row_vw(const Plan& p, int no_private) {
+  if (no_private || (p.D & 1) || p.d % 32 || p.d > 128 || p.d < 32) return 0;
+  return p.d / 32;
+}
+
+template <int VW>
+int launch_prologue_fast_vw(const Plan& p, const FeatPtrs& f, uint8_t* w, size_t smem, int grid, int fuse, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(prologue_fast_kernel<VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return cuda_ok("cudaFuncSetAttribute(prologue_fast_kernel)");
+    configured = smem;
+  }
+  prologue_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, w, fuse);
+  return cuda_ok("prologue_fast_kernel");
+}
+int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, uint8_t* w, size_t smem, int grid, int fuse,
+                         cudaStream_t st) {
+  switch (vw) {
+    case 1: return launch_prologue_fast_vw<1>(p, f, w, smem, grid, fuse, st);
+    case 2: return launch_prologue_fast_vw<2>(p, f, w, smem, grid, fuse, st);
+    case 3: return launch_prologue_fast_vw<3>(p, f, w, smem, grid, fuse, st);
+    case 4: return launch_prologue_fast_vw<4>(p, f, w, smem, grid, fuse, st);
+  }
+  return FOCAL_ESHAPE;
+}
+template <int VW>
+int launch_finalize_fast_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, size_t smem, int grid,
+                            cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(finalize_fast_kernel<VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return cuda_ok("cudaFuncSetAttribute(finalize_fast_kernel)");
+    configured = smem;
+  }
+  finalize_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, g, w);
+  return cuda_ok("finalize_fast_kernel");
+}
+int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, size_t smem,
+                         int grid, cudaStream_t st) {
+  switch (vw) {
+    case 1: return launch_finalize_fast_vw<1>(p, f, g, w, smem, grid, st);
+    case 2: return launch_finalize_fast_vw<2>(p, f, g, w, smem, grid, st);
+    case 3: return launch_finalize_fast_vw<3>(p, f, g, w, smem, grid, st);
+    case 4: return launch_finalize_fast_vw<4>(p, f, g, w, smem, grid, st);
+  }
+  return FOCAL_ESHAPE;
+}
+
 int fill_feats(const Plan& p, const float* const* feats, FeatPtrs& f) {
   if (!feats) return FOCAL_EINVAL;
   for (int t = 0; t < p.nT; ++t) {
@@ -166,16 +217,24 @@ int focal_b200_prologue(const FocalCfg* cfg, const float* const* feats, void* ws
     zero_pad_kernel<<<64, 256, 0, st>>>(p, w);
     if ((rc = cuda_ok("zero_pad_kernel"))) return rc;
   }
-  const size_t smem = (size_t)kRowsPerBlock * p.nT * p.D * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return cuda_ok("cudaFuncSetAttribute(prologue_kernel)");
-    configured = smem;
+  const int vw = fast_row_vw(p, cfg->no_private);
+  bool fused_intra = false;
+  if (vw) {
+    fused_intra = (p.S == 2 || p.S == 4);
+    const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT + 4 * kMaxT) * sizeof(float);
+    if ((rc = launch_prologue_fast(vw, p, f, w, smem, p.nblk1, fused_intra ? 1 : 0, st))) return rc;
+  } else {
+    const size_t smem = (size_t)kRowsPerBlock * p.nT * p.D * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      if (cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return cuda_ok("cudaFuncSetAttribute(prologue_kernel)");
+      configured = smem;
+    }
+    prologue_kernel<<<p.nblk1, 32 * kRowsPerBlock, smem, st>>>(p, f, w);
+    if ((rc = cuda_ok("prologue_kernel"))) return rc;
   }
-  prologue_kernel<<<p.nblk1, 32 * kRowsPerBlock, smem, st>>>(p, f, w);
-  if ((rc = cuda_ok("prologue_kernel"))) return rc;
-  if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p)) {
+  if (!fused_intra && (p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p)) {
     const long warps = (long)p.nT * p.b;
     intra_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(p, f, w);
     if ((rc = cuda_ok("intra_kernel"))) return rc;
@@ -241,16 +300,22 @@ int focal_b200_finalize(const FocalCfg* cfg, const float* const* feats, void* ws
       if (!grads[t] || (reinterpret_cast<uintptr_t>(grads[t]) & 15)) return FOCAL_EINVAL;
       g.g[t] = grads[t];
     }
-    const size_t smem = (size_t)kRowsPerBlock * (2 * p.nT + 1) * p.D * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      if (cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return cuda_ok("cudaFuncSetAttribute(finalize_kernel)");
-      configured = smem;
-    }
     const int rows = (p.seq1 - p.seq0) * p.S;
-    finalize_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, smem, st>>>(p, f, g, w);
-    if ((rc = cuda_ok("finalize_kernel"))) return rc;
+    const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, cfg->no_private) : 0;
+    if (vw) {
+      const size_t smem = ((size_t)8 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);
+      if ((rc = launch_finalize_fast(vw, p, f, g, w, smem, (rows + 3) / 4, st))) return rc;
+    } else {
+      const size_t smem = (size_t)kRowsPerBlock * (2 * p.nT + 1) * p.D * sizeof(float);
+      static size_t configured = 0;
+      if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+          return cuda_ok("cudaFuncSetAttribute(finalize_kernel)");
+        configured = smem;
+      }
+      finalize_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, smem, st>>>(p, f, g, w);
+      if ((rc = cuda_ok("finalize_kernel"))) return rc;
+    }
   }
   loss_reduce_kernel<<<1, 256, 0, st>>>(p, w, loss5, p.nblk2, temporal_degenerate(p) ? 1 : 0);
   return cuda_ok("loss_reduce_kernel");

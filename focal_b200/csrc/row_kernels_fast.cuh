@@ -1,0 +1,381 @@
+// Vectorised variants of the prologue / finalize row kernels for the common shapes:
+//   D even, D/2 a multiple of 32 (D = 64, 128, 192, 256), standard topology (no "noPrivate"), S in {2, 4}.
+// One warp per row, 4 consecutive rows (= whole sequences) per block.  Each lane owns VW = D/64 consecutive columns
+// of the shared half and the matching VW columns of the private half of every tensor, so all per-row dot products are
+// lane-local multiplies + one shuffle reduction, every global access is a coalesced 8/16-byte vector, and the
+// neighbouring windows of a sequence are read from shared memory instead of HBM.  The generic kernels in
+// row_kernels.cuh remain the path for every other shape; both produce identical operand bytes.
+#pragma once
+#include "plan.h"
+#include "ptx.cuh"
+#include "row_kernels.cuh"
+
+namespace fb {
+
+template <int VW>
+__device__ __forceinline__ void ld_frag(const float* p, float (&v)[VW]) {
+  if (VW == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2 % VW] = t.z; v[3 % VW] = t.w;
+  } else if (VW == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1 % VW] = t.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < VW; ++e) v[e] = p[e];
+  }
+}
+template <int VW>
+__device__ __forceinline__ void st_frag(float* p, const float (&v)[VW]) {
+  if (VW == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2 % VW], v[3 % VW]);
+  } else if (VW == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1 % VW]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VW; ++e) p[e] = v[e];
+  }
+}
+
+// Store VW consecutive bf16 operand elements starting at element e0 (multiple of VW) of a swizzled 128-byte-row
+// operand array: K block e0/64, 16-byte chunk ((e0 % 64) / 8) ^ (row & 7).
+template <int VW>
+__device__ __forceinline__ void st_operand(uint8_t* op_base, uint64_t kstride_rows, uint64_t row, int e0,
+                                           const float (&v)[VW]) {
+  uint8_t* dst = op_base + ((uint64_t)(e0 >> 6) * kstride_rows + row) * 128 +
+                 ((((uint32_t)(e0 & 63) >> 3) ^ (uint32_t)(row & 7)) << 4) + (e0 & 7) * 2;
+  if (VW == 4) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2 % VW], v[3 % VW]));
+  } else if (VW == 2) {
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v[0], v[1 % VW]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      const int el = e0 + e;
+      uint8_t* d1 = op_base + ((uint64_t)(el >> 6) * kstride_rows + row) * 128 +
+                    ((((uint32_t)(el & 63) >> 3) ^ (uint32_t)(row & 7)) << 4) + (el & 7) * 2;
+      *reinterpret_cast<uint16_t*>(d1) = (uint16_t)(pack_bf16x2(v[e], 0.f) & 0xffffu);
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_rows(const Plan& p, const FeatPtrs& f, int i, float* xs, int lane) {
+  const int nv = p.D >> 2;                       // D % 4 == 0 on this path
+  for (int t = 0; t < p.nT; ++t) {
+    const float4* src = reinterpret_cast<const float4*>(f.x[t] + (size_t)i * p.D);
+    float4* dst = reinterpret_cast<float4*>(xs + t * p.D);
+    for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fast prologue (+ fused intra-sequence means when S divides 4)
+// ---------------------------------------------------------------------------------------------------------
+template <int VW>
+__global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constant__ Plan p,
+                                                            const __grid_constant__ FeatPtrs f,
+                                                            uint8_t* __restrict__ ws, int fuse_intra) {
+  extern __shared__ float smem_f[];
+  __shared__ float red[4][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp;
+  const int D = p.D, d = p.d;
+  float* xs = smem_f + (size_t)warp * p.nT * D;
+  float acc_orth = 0.f, acc_ps = 0.f, acc_pp = 0.f;
+  const bool live = i < p.B;
+  if (live) stage_rows(p, f, i, xs, lane);
+  __syncthreads();
+  if (live) {
+    const int I = i / p.S, s = i % p.S;
+    const uint64_t rowN = (uint64_t)s * p.bpad + I;
+    const uint64_t rowsNce = (uint64_t)p.S * p.bpad;
+    const int c0 = VW * lane;
+    float* nrm = smem_f + (size_t)4 * p.nT * D + warp * 2 * kMaxT;     // [t][2] scale factors alpha / max(|.|, eps)
+
+    for (int t = 0; t < p.nT; ++t) {
+      float sh[VW], pr[VW];
+      ld_frag<VW>(xs + t * D + c0, sh);
+      ld_frag<VW>(xs + t * D + d + c0, pr);
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int e = 0; e < VW; ++e) { a = fmaf(sh[e], sh[e], a); b = fmaf(pr[e], pr[e], b); }
+      a = warp_sum(a); b = warp_sum(b);
+      if (lane == 0) { nrm[2 * t] = a; nrm[2 * t + 1] = b; }
+      if (p.terms & FOCAL_TERM_NCE) {
+        const float fa = p.alpha / fmaxf(sqrtf(a), kNceEps), fb2 = p.alpha / fmaxf(sqrtf(b), kNceEps);
+        float zs[VW], zp[VW];
+#pragma unroll
+        for (int e = 0; e < VW; ++e) { zs[e] = sh[e] * fa; zp[e] = pr[e] * fb2; }
+        st_operand<VW>(ws + p.ops[2 * t].off, rowsNce, rowN, c0, zs);
+        st_operand<VW>(ws + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp);
+      }
+      if (p.terms & FOCAL_TERM_TEMPORAL) {
+        uint8_t* xt = ws + p.xt_off + (uint64_t)t * p.kbFull * p.Bpad * 128;
+        st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, c0, sh);
+        st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, d + c0, pr);
+        float sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          const float r0 = bf16_round(sh[e]), r1 = bf16_round(pr[e]);
+          sq = fmaf(r0, r0, fmaf(r1, r1, sq));
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
+      }
+    }
+    __syncwarp();
+    if (I >= p.seq0 && I < p.seq1) {
+      if (p.terms & FOCAL_TERM_NCE) {
+        const float sc = -2.f * 0.6931471805599453f / ((float)p.S * (float)(2 * p.b));   // -2 ln2 G~ / (S N)
+        for (int q = 0; q < p.nProb; ++q) {
+          const OpDesc& a = p.ops[p.probs[q].opA];
+          const OpDesc& b = p.ops[p.probs[q].opB];
+          const int ha = a.col0 ? 1 : 0, hb = b.col0 ? 1 : 0;
+          const float fa = p.alpha / fmaxf(sqrtf(nrm[2 * a.tensor + ha]), kNceEps);
+          const float fb2 = p.alpha / fmaxf(sqrtf(nrm[2 * b.tensor + hb]), kNceEps);
+          float xa[VW], xb[VW];
+          ld_frag<VW>(xs + a.tensor * D + a.col0 + c0, xa);
+          ld_frag<VW>(xs + b.tensor * D + b.col0 + c0, xb);
+          float dot = 0.f;
+#pragma unroll
+          for (int e = 0; e < VW; ++e) dot = fmaf(bf16_round(xa[e] * fa), bf16_round(xb[e] * fb2), dot);
+          dot = warp_sum(dot);
+          if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
+        }
+      }
+      if (p.terms & FOCAL_TERM_ORTH) {
+        for (int k = 0; k < p.nOrth; ++k) {
+          const OrthDesc& od = p.orth[k];
+          float u[VW], v[VW];
+          ld_frag<VW>(xs + od.tu * D + od.cu + c0, u);
+          ld_frag<VW>(xs + od.tv * D + od.cv + c0, v);
+          float dot = 0.f;
+#pragma unroll
+          for (int e = 0; e < VW; ++e) dot = fmaf(u[e], v[e], dot);
+          dot = warp_sum(dot);
+          const float nu = nrm[2 * od.tu + (od.cu ? 1 : 0)] + kOrthEps;
+          const float nv = nrm[2 * od.tv + (od.cv ? 1 : 0)] + kOrthEps;
+          acc_orth += fmaxf(dot / sqrtf(nu * nv), 0.f);
+        }
+      }
+    }
+    // ---- intra-sequence mean distance of the rounded rows (the other rows of the sequence sit in this block)
+    if (fuse_intra && (p.terms & FOCAL_TERM_TEMPORAL) && p.S > 1 && p.b > 1) {
+      const int S = p.S;
+      const int w0 = warp - s;                        // warp holding position 0 of this sequence
+      // per-row sums sum_j delta(i, j); the S rows of the sequence are added up through shared memory below
+      float* rowsum = smem_f + (size_t)4 * p.nT * D + 4 * 2 * kMaxT + warp * kMaxT;
+      for (int t = 0; t < p.nT; ++t) {
+        float sh[VW], pr[VW];
+        ld_frag<VW>(xs + t * D + c0, sh);
+        ld_frag<VW>(xs + t * D + d + c0, pr);
+        float sum = 0.f;
+        for (int j = 0; j < S; ++j) {
+          if (j == s) continue;
+          const float* xo = smem_f + (size_t)(w0 + j) * p.nT * D + t * D;
+          float osh[VW], opr[VW];
+          ld_frag<VW>(xo + c0, osh);
+          ld_frag<VW>(xo + d + c0, opr);
+          float d2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < VW; ++e) {
+            const float a = bf16_round(sh[e]) - bf16_round(osh[e]), b = bf16_round(pr[e]) - bf16_round(opr[e]);
+            d2 = fmaf(a, a, fmaf(b, b, d2));
+          }
+          sum += sqrtf(warp_sum(d2));
+        }
+        if (lane == 0) rowsum[t] = sum;
+      }
+    }
+  }
+  if (lane == 0) { red[warp][0] = acc_orth; red[warp][1] = acc_ps; red[warp][2] = acc_pp; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s2 = 0.f;
+    for (int w = 0; w < 4; ++w) s2 += red[w][threadIdx.x];
+    if (threadIdx.x == 0) s2 /= (float)p.B;
+    reinterpret_cast<float*>(ws + p.part1_off)[(size_t)blockIdx.x * 4 + threadIdx.x] = s2;
+  }
+  if (fuse_intra && live && (p.terms & FOCAL_TERM_TEMPORAL) && p.S > 1 && p.b > 1 && lane < p.nT) {
+    const int S = p.S, s = i % S, w0 = warp - s;
+    const float* rs = smem_f + (size_t)4 * p.nT * D + 4 * 2 * kMaxT;
+    float m = 0.f;
+    for (int j = 0; j < S; ++j) m += rs[(w0 + j) * kMaxT + lane];
+    reinterpret_cast<float*>(ws + p.mintra_off)[(uint64_t)lane * p.Bpad + i] = m / (float)(S * S - S);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fast finalize
+// ---------------------------------------------------------------------------------------------------------
+template <int VW>
+__global__ void __launch_bounds__(128) finalize_fast_kernel(const __grid_constant__ Plan p,
+                                                            const __grid_constant__ FeatPtrs f,
+                                                            const __grid_constant__ GradPtrs g,
+                                                            const uint8_t* __restrict__ ws) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = p.seq0 * p.S + blockIdx.x * 4 + warp;
+  const int D = p.D, d = p.d, S = p.S;
+  const bool live = i < p.seq1 * S;
+  float* xs = smem_f + (size_t)warp * p.nT * D;
+  float* gs = smem_f + (size_t)4 * p.nT * D + (size_t)warp * p.nT * D;
+  float* nrm = smem_f + (size_t)8 * p.nT * D + warp * 2 * kMaxT;
+  if (live) stage_rows(p, f, i, xs, lane);
+  __syncthreads();
+  if (!live) return;
+  const int I = i / S, s = i % S;
+  const uint64_t rowN = (uint64_t)s * p.bpad + I;
+  const int c0 = VW * lane;
+  const bool do_tmp = (p.terms & FOCAL_TERM_TEMPORAL) && p.b > 1 && S > 1;
+  const float bb = (float)p.b * (float)(p.b - 1);
+  const int Dp = p.kbFull * 64;
+
+  // ---- norms + temporal part (initialises the gradient rows in shared memory)
+  for (int t = 0; t < p.nT; ++t) {
+    float sh[VW], pr[VW];
+    ld_frag<VW>(xs + t * D + c0, sh);
+    ld_frag<VW>(xs + t * D + d + c0, pr);
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int e = 0; e < VW; ++e) { a = fmaf(sh[e], sh[e], a); b = fmaf(pr[e], pr[e], b); }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { nrm[2 * t] = a; nrm[2 * t + 1] = b; }
+    float gsh[VW], gpr[VW];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) { gsh[e] = 0.f; gpr[e] = 0.f; }
+    if (do_tmp) {
+      const float rho = __ldg(reinterpret_cast<const float*>(ws + p.rho_off) + (uint64_t)t * p.Bpad + i);
+      const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
+      const int cnt = __ldg(reinterpret_cast<const int32_t*>(ws + p.cnt_off) + (uint64_t)t * p.bpad + I);
+      float ysh[VW], ypr[VW];
+      ld_frag<VW>(y + c0, ysh);
+      ld_frag<VW>(y + d + c0, ypr);
+      float rsh[VW], rpr[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        rsh[e] = bf16_round(sh[e]); rpr[e] = bf16_round(pr[e]);
+        gsh[e] = p.w_rank * (rsh[e] * rho - ysh[e]);
+        gpr[e] = p.w_rank * (rpr[e] * rho - ypr[e]);
+      }
+      // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
+      const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
+      if (cnt > 0) {
+        const int w0 = warp - s;
+        for (int j = 0; j < S; ++j) {
+          if (j == s) continue;
+          const float* xo = smem_f + (size_t)(w0 + j) * p.nT * D + t * D;
+          float osh[VW], opr[VW];
+          ld_frag<VW>(xo + c0, osh);
+          ld_frag<VW>(xo + d + c0, opr);
+          float d2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < VW; ++e) {
+            osh[e] = rsh[e] - bf16_round(osh[e]); opr[e] = rpr[e] - bf16_round(opr[e]);
+            d2 = fmaf(osh[e], osh[e], fmaf(opr[e], opr[e], d2));
+          }
+          d2 = warp_sum(d2);
+          if (d2 > 0.f) {
+            const float r = coef * rsqrtf(d2);
+#pragma unroll
+            for (int e = 0; e < VW; ++e) { gsh[e] = fmaf(r, osh[e], gsh[e]); gpr[e] = fmaf(r, opr[e], gpr[e]); }
+          }
+        }
+      }
+    }
+    st_frag<VW>(gs + t * D + c0, gsh);
+    st_frag<VW>(gs + t * D + d + c0, gpr);
+  }
+  __syncwarp();
+
+  // ---- InfoNCE (standard topology: operand o = 2 t + half, width d)
+  if (p.terms & FOCAL_TERM_NCE) {
+    const float inv_tsn = 1.f / (p.T * (float)S * (float)(2 * p.b));
+    const float inv_alpha = 1.f / p.alpha;
+    for (int o = 0; o < p.nOps; ++o) {
+      const OpDesc& op = p.ops[o];
+      const int wp = op.kb * 64;
+      const int hk = op.col0 ? 1 : 0;
+      const float nk = fmaxf(sqrtf(nrm[2 * op.tensor + hk]), kNceEps);
+      const float fk = p.alpha / nk;
+      float x[VW], tmp[VW];
+      ld_frag<VW>(xs + op.tensor * D + op.col0 + c0, x);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) tmp[e] = 0.f;
+      bool used = false;
+      for (int q = 0; q < p.nProb; ++q) {
+        const ProbDesc& pr = p.probs[q];
+        int side = -1;
+        if (pr.opA == o) side = 0; else if (pr.opB == o) side = 1;
+        if (side < 0) continue;
+        used = true;
+        const OpDesc& po = p.ops[side == 0 ? pr.opB : pr.opA];            // partner operand: positive row p(k)
+        const float fp = p.alpha / fmaxf(sqrtf(nrm[2 * po.tensor + (po.col0 ? 1 : 0)]), kNceEps);
+        float px[VW], acc[VW];
+        ld_frag<VW>(xs + po.tensor * D + po.col0 + c0, px);
+        ld_frag<VW>(reinterpret_cast<const float*>(ws + pr.dz_off) + ((uint64_t)side * S * p.bpad + rowN) * wp + c0, acc);
+        // positive column in fp32 (masked out of the tiles): W_kp - 2 is a tiny difference when the positive dominates
+        float gpos = 0.f;
+#pragma unroll
+        for (int e = 0; e < VW; ++e) { px[e] = bf16_round(px[e] * fp); gpos = fmaf(bf16_round(x[e] * fk), px[e], gpos); }
+        gpos = warp_sum(gpos);
+        const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
+        const float wkp = exp2f(gpos) * (1.f / __ldg(rs + (uint64_t)side * p.bpad + I) +
+                                         1.f / __ldg(rs + (uint64_t)(1 - side) * p.bpad + I));
+        const float wq = pr.weight * inv_tsn * inv_alpha;
+#pragma unroll
+        for (int e = 0; e < VW; ++e) tmp[e] = fmaf(wq, acc[e] + (wkp - 2.f) * px[e], tmp[e]);
+      }
+      if (!used) continue;
+      float dot = 0.f;                                // d zh / d z = (I - zh zh^T) / n
+#pragma unroll
+      for (int e = 0; e < VW; ++e) dot = fmaf(tmp[e], x[e], dot);
+      dot = warp_sum(dot) / (nk * nk);
+      float go[VW];
+      ld_frag<VW>(gs + op.tensor * D + op.col0 + c0, go);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) go[e] += (tmp[e] - dot * x[e]) / nk;
+      st_frag<VW>(gs + op.tensor * D + op.col0 + c0, go);
+    }
+  }
+
+  // ---- orthogonality
+  if (p.terms & FOCAL_TERM_ORTH) {
+    for (int k = 0; k < p.nOrth; ++k) {
+      const OrthDesc& od = p.orth[k];
+      float u[VW], v[VW];
+      ld_frag<VW>(xs + od.tu * D + od.cu + c0, u);
+      ld_frag<VW>(xs + od.tv * D + od.cv + c0, v);
+      float dot = 0.f;
+#pragma unroll
+      for (int e = 0; e < VW; ++e) dot = fmaf(u[e], v[e], dot);
+      dot = warp_sum(dot);
+      const float nu = nrm[2 * od.tu + (od.cu ? 1 : 0)] + kOrthEps;
+      const float nv = nrm[2 * od.tv + (od.cv ? 1 : 0)] + kOrthEps;
+      const float den = sqrtf(nu * nv);
+      const float cs = dot / den;
+      if (cs >= 0.f) {                                    // clamp_min passes gradient at equality
+        const float a = p.w_orth / (float)p.B;
+        float gu[VW], gv[VW];
+        ld_frag<VW>(gs + od.tu * D + od.cu + c0, gu);
+        ld_frag<VW>(gs + od.tv * D + od.cv + c0, gv);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          gu[e] += a * (v[e] / den - cs * u[e] / nu);
+          gv[e] += a * (u[e] / den - cs * v[e] / nv);
+        }
+        st_frag<VW>(gs + od.tu * D + od.cu + c0, gu);
+        st_frag<VW>(gs + od.tv * D + od.cv + c0, gv);
+      }
+    }
+  }
+  __syncwarp();
+  const int nv4 = D >> 2;
+  for (int t = 0; t < p.nT; ++t) {
+    float4* out = reinterpret_cast<float4*>(g.g[t] + (size_t)i * D);
+    const float4* src = reinterpret_cast<const float4*>(gs + t * D);
+    for (int c = lane; c < nv4; c += 32) out[c] = src[c];
+  }
+}
+
+}  // namespace fb

@@ -140,6 +140,28 @@ def test_against_fp64_oracle(gen, B, D, mods, T, seed):
         assert_grads_close(g2[m].grad, ref.grads2[m], ref, len(mods) + i, 4, GRAD_RTOL_BF16, (m, 2))
 
 
+@pytest.mark.parametrize("S,B,D,tag", [
+    (2, 256, 128, None),          # two rows per sequence (SEQ = 2 epilogue, fused intra means)
+    (8, 512, 128, None),          # S = 8: generic finalize + separate intra-sequence kernel
+    (16, 512, 64, None),
+    (32, 1024, 96, None),         # a sequence spans a whole warp; D/2 = 48 takes the generic row kernels
+    (4, 512, 256, "noPrivate"),   # shared InfoNCE on full-width rows (4 K blocks) + private on halves (2 K blocks)
+    (4, 384, 128, "noPrivate"),
+])
+def test_sequence_lengths_and_noprivate(S, B, D, tag):
+    _require_cuda()
+    mods = ["seismic", "audio"]
+    cfg = fo.FocalConfig(modalities=mods, seq_len=S, temperature=0.5, no_private=(tag == "noPrivate"))
+    f1, f2 = fo.make_structured(11 + S, mods, B, D, S)
+    mod, loss, g1, g2 = run_module(f1, f2, cfg)
+    ref = fo.focal_closed_form({m: v.cuda() for m, v in f1.items()}, {m: v.cuda() for m, v in f2.items()}, cfg,
+                               dtype=torch.float64)
+    assert abs(float(loss) - float(ref.loss)) / abs(float(ref.loss)) < LOSS_RTOL, (float(loss), float(ref.loss))
+    for i, m in enumerate(mods):
+        assert_grads_close(g1[m].grad, ref.grads1[m], ref, i, S, GRAD_RTOL_BF16, (m, 1))
+        assert_grads_close(g2[m].grad, ref.grads2[m], ref, len(mods) + i, S, GRAD_RTOL_BF16, (m, 2))
+
+
 def test_headline_size_against_fp64_oracle():
     """BASELINE.json's metric configuration: B = 8192, M = 2, S = 4, D = 256, T = 0.5."""
     _require_cuda()
