@@ -54,27 +54,69 @@ def measured_peaks():
 # clocks sampler (nvidia-smi during the timed region)
 # -------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU during the timed region (NVML; nvidia-smi fallback)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, power_w, reasons bitmask)
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        except Exception:
+            pw = float("nan")
+        try:
+            rs = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        self.samples.append((float(sm), float(self._max), pw, int(rs)))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 7:
+            bits = 0
+            for k, bit in enumerate((0x8, 0x40, 0x20, 0x4)):
+                if parts[3 + k].lower().startswith("active"):
+                    bits |= bit
+            self.samples.append((float(parts[0]), float(parts[1]), float(parts[2]), bits))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t.start()
@@ -87,12 +129,17 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        # NVML clocks-event-reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal, 0x40 hw_thermal
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        allbits = 0
+        for s_ in self.samples:
+            allbits |= s_[3]
+        return {"sm_mhz": statistics.median(s_[0] for s_ in self.samples),
+                "sm_min_mhz": min(s_[0] for s_ in self.samples),
+                "sm_max_mhz": max(s_[1] for s_ in self.samples),
+                "power_w_max": max(s_[2] for s_ in self.samples),
+                "reasons": [n for b, n in names.items() if allbits & b], "samples": len(self.samples),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -234,8 +281,10 @@ def run_ours(args):
         sampler.__enter__()
     sync_all()
     ev0.record()
+    h0 = time.perf_counter()
     for k in range(args.steps):
         loss5, grads = step(k)
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps     # time the host needs to enqueue one step
     ev1.record()
     sync_all()
     if sampler:
@@ -314,7 +363,7 @@ def run_ours(args):
             "alg_tflops": F / (ms_step * 1e-3) / 1e12,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": args.steps * launches_per_step(B, S, world),
-            "stages_ms": stages,
+            "stages_ms": stages, "host_enqueue_ms_per_step": host_ms,
             "clocks": sampler.summary() if sampler else None,
             "loss": float(loss5[0].item()),
         }

@@ -13,10 +13,15 @@ using namespace fb;
 namespace {
 
 int device_sms() {
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
-  return sms;
+  static int cached[64] = {0};          // SM count per device ordinal (never changes; avoid a driver query per call)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] <= 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+    cached[dev] = sms;
+  }
+  return cached[dev];
 }
 
 int make_plan(const FocalCfg* cfg, Plan& p) {

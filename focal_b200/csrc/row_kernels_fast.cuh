@@ -108,6 +108,12 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
         for (int e = 0; e < VW; ++e) { zs[e] = sh[e] * fa; zp[e] = pr[e] * fb2; }
         st_operand<VW>(ws + p.ops[2 * t].off, rowsNce, rowN, c0, zs);
         st_operand<VW>(ws + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp);
+        if (VW & 1) {
+          // d = 32 or 96: the last K block is half full -- its 32 padding columns must read as zeros
+          const float z1[1] = {0.f};
+          st_operand<1>(ws + p.ops[2 * t].off, rowsNce, rowN, d + lane, z1);
+          st_operand<1>(ws + p.ops[2 * t + 1].off, rowsNce, rowN, d + lane, z1);
+        }
       }
       if (p.terms & FOCAL_TERM_TEMPORAL) {
         uint8_t* xt = ws + p.xt_off + (uint64_t)t * p.kbFull * p.Bpad * 128;

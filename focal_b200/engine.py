@@ -53,6 +53,7 @@ class CudaBackend:
     def __init__(self):
         self.lib = _cabi.load()          # raises ImportError when the extension is missing -- no fallback
         self._ws: Dict[tuple, Tuple[torch.Tensor, torch.Tensor, _cabi.FocalWsInfo]] = {}
+        self._plans: Dict[tuple, tuple] = {}
 
     # -- helpers ------------------------------------------------------------------------------------
     def _cfg(self, hp: FocalHyper, B: int, D: int, need_grad: bool, seq: Tuple[int, int]) -> _cabi.FocalCfg:
@@ -91,10 +92,15 @@ class CudaBackend:
         x0 = feats[0]
         B, D = x0.shape
         dev = x0.device
-        cfg = self._cfg(hp, B, D, need_grad, seq)
-        ws, info = self.workspace(cfg, dev)
+        key = (hp, B, D, need_grad, seq, dev.index)
+        hit = self._plans.get(key)
+        if hit is None:
+            cfg = self._cfg(hp, B, D, need_grad, seq)
+            ws, info = self.workspace(cfg, dev)
+            hit = (cfg, ws, info, C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()))
+            self._plans[key] = hit
+        cfg, ws, info, wsp, wsn = hit
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        wsp, wsn = C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel())
         fptr = _cabi.ptr_array([t.data_ptr() for t in feats])
         loss5 = torch.empty(5, dtype=torch.float32, device=dev)
         grads = [torch.empty_like(t) for t in feats] if need_grad else None
