@@ -179,8 +179,9 @@ class FocalEngine:
         nT = len(local)
         # (1) all-gather the raw features: [R, 2M, Bl, D] -> per tensor [R*Bl, D] rank-major
         mine = torch.stack(local, dim=0)
-        gathered = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        gathered = torch.empty((world * mine.shape[0],) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)       # concatenated along dim 0, rank-major
+        gathered = gathered.view((world,) + tuple(mine.shape))
         full = [gathered[:, t].reshape(world * Bl, D) for t in range(nT)]
         b = world * Bl // hp.seq_len
         seq = shard_sequences(b, world, rank)
@@ -189,8 +190,9 @@ class FocalEngine:
             # rs: [P, S, 2, bpad]; every rank computed the k-range [seq0, seq1) -- all-gather the slices
             k0, k1 = seq
             part = rs[..., k0:k1].contiguous()
-            allp = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
+            allp = torch.empty((world * part.shape[0],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
             dist.all_gather_into_tensor(allp, part, group=self.group)
+            allp = allp.view((world,) + tuple(part.shape))
             per = k1 - k0
             for r in range(world):
                 if r != rank:
