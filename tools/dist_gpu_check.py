@@ -35,7 +35,10 @@ def main():
         l2 = {m: v[rank * Bl:(rank + 1) * Bl].to(dev) for m, v in f2.items()}
         loss5, grads = sharded.loss_and_grads(l1, l2, True)
         torch.cuda.synchronize()
-        lerr = float(((loss5 - full5).abs() / full5.abs().clamp_min(1e-12)).max())
+        # total loss relative; the sub-loss sums are compared with an absolute floor (at T = 0.07 the InfoNCE parts are
+        # ~1e-3 differences of ~13-sized fp32 sums, so their last bits depend on the per-rank summation split)
+        lerr = max(float((loss5[0] - full5[0]).abs() / full5[0].abs()),
+                   float(((loss5[1:] - full5[1:]).abs() / full5[1:].abs().clamp_min(1.0)).max()))
         gerr = max(float((g - fg[rank * Bl:(rank + 1) * Bl]).norm() / fg[rank * Bl:(rank + 1) * Bl].norm())
                    for g, fg in zip(grads, fullg))
         good = lerr < 2e-6 and gerr < 1e-5
