@@ -35,6 +35,7 @@ constexpr int kGramThreads = 64 + 256;
 constexpr int kEpiThreads = 256;
 constexpr int kNumBStages = 3;
 constexpr int kTmemCols = 512;
+constexpr int kPolyPer8 = 3;            // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe
 
 template <int BN, int KB>
 struct GramSmem {
@@ -324,16 +325,14 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         const bool overlap = col0 < row0 + kTileM && col0 + BN > row0;
         const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == side)) : overlap;
         const uint32_t s_addr = tmem + tlane + kSCol + ss * BN;
-#pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          float v[32];
-          tmem_ld32(s_addr + ch * 32, v);
-          tmem_ld_wait();
+        auto process = [&](float (&v)[32], const int ch) {
           const int cbase = col0 + ch * 32;           // column (within side) of v[0]
           if (kIsNce) {
             // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
+            // exponentials: kPolyPer8 of every 8 columns on the FMA pipe, the rest on the MUFU pipe (same columns in
+            // the forward and the backward pass, so P_kj is formed from the same E_kj in both)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = ((j & 7) >= 8 - kPolyPer8) ? ex2_poly(v[j]) : ex2_approx(v[j]);
             if (MODE == NCE_BWD) {
               // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
 #pragma unroll
@@ -398,6 +397,19 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             tmem_st16(s_addr + ch * 16, pk);
+          }
+        };
+        // chunks of 32 columns, software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+        {
+          float va[32], vb[32];
+          tmem_ld32(s_addr, va);
+#pragma unroll
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            tmem_ld_wait();
+            if (ch + 1 < BN / 32) {
+              if (ch & 1) tmem_ld32(s_addr + (ch + 1) * 32, va); else tmem_ld32(s_addr + (ch + 1) * 32, vb);
+            }
+            if (ch & 1) process(vb, ch); else process(va, ch);
           }
         }
         if (kBwd) {

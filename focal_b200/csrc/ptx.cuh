@@ -228,6 +228,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f via the 1.5*2^23 trick, degree-4 minimax
+// polynomial for 2^f on [-0.5, 0.5] (max relative error 2.7e-6), exponent patched in with an integer add.
+// Valid for |x| < 126.  Used for a fixed subset of the columns of every logit tile so that the MUFU pipe
+// (16 ex2/clk/SM) is not the only unit producing exponentials.
+__device__ __forceinline__ float ex2_poly(float x) {
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.009570101276040077f, 0.05591785907745361f);
+  p = fmaf(p, f, 0.240247443318367f);
+  p = fmaf(p, f, 0.6931217908859253f);
+  p = fmaf(p, f, 0.9999992847442627f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
