@@ -38,6 +38,17 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS)
 
 
+def build_variant(tag: str, defines: dict) -> str:
+    """Experiment builds (tools/variant_bench.py): libfocal_b200_<tag>.so with extra -D knobs."""
+    out = os.path.join(PKG_DIR, f"libfocal_b200_{tag}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{k}={v}" for k, v in defines.items()] + ["-o", out] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed building variant {tag}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH

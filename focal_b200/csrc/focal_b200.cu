@@ -50,9 +50,10 @@ bool temporal_degenerate(const Plan& p) { return p.b <= 1 || p.S <= 1; }
 
 template <int MODE, int KB, int SEQ>
 int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int n_items) {
-  constexpr int BN = tile_bn(KB);
-  using L = GramSmem<BN, KB>;
-  auto kfn = gram_kernel<MODE, BN, KB, SEQ>;
+  using G = GramCfg<MODE, KB, SEQ>;
+  static_assert(G::BN == tile_bn(KB), "plan.h and gram_kernel.cuh must agree on the column tile");
+  using L = GramSmem<G::BN, KB, G::NB>;
+  auto kfn = gram_kernel<MODE, KB, SEQ>;
   static bool configured = false;     // per instantiation; the attribute is sticky per context
   if (!configured) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic) != cudaSuccess)
@@ -61,16 +62,18 @@ int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st,
   }
   if (n_items <= 0) return FOCAL_OK;
   const int grid = n_items < p.num_sms ? n_items : p.num_sms;     // persistent: one CTA per SM
-  kfn<<<grid, kGramThreads, L::kDynamic, st>>>(p, sel, ws);
+  kfn<<<grid, G::kThreads, L::kDynamic, st>>>(p, sel, ws);
   return cuda_ok("gram_kernel launch");
 }
 
 template <int MODE, int SEQ>
 int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int n_items) {
   switch (kb) {
+#ifndef FB_FAST_BUILD
     case 1: return launch_gram<MODE, 1, SEQ>(p, sel, ws, st, n_items);
-    case 2: return launch_gram<MODE, 2, SEQ>(p, sel, ws, st, n_items);
     case 3: return launch_gram<MODE, 3, SEQ>(p, sel, ws, st, n_items);
+#endif
+    case 2: return launch_gram<MODE, 2, SEQ>(p, sel, ws, st, n_items);
     case 4: return launch_gram<MODE, 4, SEQ>(p, sel, ws, st, n_items);
   }
   return FOCAL_ESHAPE;
@@ -80,11 +83,13 @@ template <int MODE>
 int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int n_items) {
   ProbSel sel{};
   switch (p.S) {
-    case 2: return launch_gram_kb<MODE, 2>(p, sel, ws, st, p.kbFull, n_items);
     case 4: return launch_gram_kb<MODE, 4>(p, sel, ws, st, p.kbFull, n_items);
+#ifndef FB_FAST_BUILD                 // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
+    case 2: return launch_gram_kb<MODE, 2>(p, sel, ws, st, p.kbFull, n_items);
     case 8: return launch_gram_kb<MODE, 8>(p, sel, ws, st, p.kbFull, n_items);
     case 16: return launch_gram_kb<MODE, 16>(p, sel, ws, st, p.kbFull, n_items);
     case 32: return launch_gram_kb<MODE, 32>(p, sel, ws, st, p.kbFull, n_items);
+#endif
   }
   return FOCAL_ESHAPE;
 }

@@ -11,14 +11,15 @@
 // laid out in HBM exactly as the UMMA wants them in shared memory (K-block-major, 128-byte rows, SWIZZLE_128B),
 // so each tile is a single linear TMA bulk copy per K block.
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM owner), warps 2..9 = two epilogue
-// warpgroups that alternate column tiles (each owns one S stage in TMEM; within a warpgroup each warp owns one
-// TMEM lane quarter).  Two warpgroups put two epilogue warps on every SM sub-partition so the MUFU / FMA chains of
-// one hide behind the other.
+// Roles (64 + 128*NS threads): warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM owner), then NS epilogue
+// warpgroups; warpgroup w owns S stage w in TMEM and handles the column tiles n with n % NS == w (within a warpgroup
+// each warp owns one TMEM lane quarter).  NS = 3 or 4 puts 3-4 epilogue warps on every SM sub-partition (their
+// MUFU / FMA dependency chains hide behind each other) and lets UMMA #1 run NS-1 tiles ahead of the epilogue, so
+// the issuer <-> epilogue round trip is off the critical path (with NS = 2 it was the bound: profiles/r1_ncu_summary.md).
 //
-// Tensor memory (512 columns): O accumulator [0, KB*64), S stages at KB*64 + {0, BN}.  In the backward modes the
-// epilogue overwrites the S stage it just consumed with W as packed bf16 (tcgen05.st) and UMMA #2 reads its A
-// operand straight from TMEM -- W never touches shared memory.
+// Tensor memory (512 columns): backward modes: O accumulator [0, KB*64), S stages at KB*64 + w*BN; forward modes:
+// S stages at w*BN.  In the backward modes the epilogue overwrites the S stage it just consumed with W as packed
+// bf16 (tcgen05.st) and UMMA #2 reads its A operand straight from TMEM -- W never touches shared memory.
 //
 // Measured on B200 (tools/umma_rate.py): one thread can issue a tcgen05.mma about every 45 clk and an M=128, K=16
 // instruction occupies the tensor pipe N/2 clk, so N >= 96 is needed to stay tensor-bound; the issue loop below is
@@ -31,13 +32,26 @@ namespace fb {
 
 enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 
-constexpr int kGramThreads = 64 + 256;
-constexpr int kEpiThreads = 256;
-constexpr int kNumBStages = 3;
+// ---- tuning knobs (overridable with -D for tools/variant_bench.py experiments) ----
+#ifndef FB_POLY_PER8
+#define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
+#endif
 constexpr int kTmemCols = 512;
-constexpr int kPolyPer8 = 3;            // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe
 
-template <int BN, int KB>
+// Tile configuration as a function of the mode and the operand width in 64-element K blocks (see header comment).
+template <int MODE, int KB, int SEQ>
+struct GramCfg {
+  static constexpr bool kBwd = (MODE == 1 || MODE == 3);
+  static constexpr bool kTmp = (MODE >= 2);
+  static constexpr int BN = KB <= 2 ? 128 : 64;                       // column tile
+  static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : 4;             // S stages == epilogue warpgroups
+  static constexpr int NB = KB <= 3 ? 5 : 4;                          // B-tile ring stages (shared memory budget)
+  static constexpr int CW = (NS == 4 && kTmp && SEQ <= 16) ? 16 : 32; // columns per tcgen05.ld (register budget)
+  static constexpr int kThreads = 64 + 128 * NS;
+  static_assert((kBwd ? KB * 64 : 0) + NS * BN <= kTmemCols, "TMEM budget");
+};
+
+template <int BN, int KB, int kNumBStages>
 struct GramSmem {
   static constexpr uint32_t kABytes = KB * 128 * 128;           // [KB][128 rows][128 B]
   static constexpr uint32_t kBTile = KB * BN * 128;             // [KB][BN rows][128 B]
@@ -45,7 +59,7 @@ struct GramSmem {
   static constexpr uint32_t kAOff = 0;
   static constexpr uint32_t kBOff = kAOff + kABytes;
   static constexpr uint32_t kBarOff = kBOff + kNumBStages * kBStage;
-  static constexpr uint32_t kTotal = kBarOff + 2048;
+  static constexpr uint32_t kTotal = kBarOff + 8192;
   static constexpr uint32_t kDynamic = kTotal + 1024;           // slack for manual 1024-B alignment
   static_assert(2 * BN * 4 <= 1024, "column vectors fit the stage tail");
   static_assert((BN * 128) % 1024 == 0, "K blocks of a B tile stay 1024-B aligned");
@@ -53,17 +67,17 @@ struct GramSmem {
 
 struct GramBars {
   uint64_t a_full, a_empty;
-  uint64_t b_full[kNumBStages], b_empty[kNumBStages];
-  uint64_t s_full[2], s_empty[2];
-  uint64_t w_full[2];
+  uint64_t b_full[8], b_empty[8];
+  uint64_t s_full[4], s_empty[4];
+  uint64_t w_full[4];
   uint64_t o_full, o_empty;
   uint32_t tmem_base;
   float red[4];
-  float part_acc[128];     // per-row partials of epilogue warpgroup 1, folded into warpgroup 0 at the end of an item
-  float part_hinge[128];
-  int32_t part_cnt[128];
+  float part_acc[3][128];     // per-row partials of epilogue warpgroups 1.., folded into warpgroup 0 at the end of an item
+  float part_hinge[3][128];
+  int32_t part_cnt[3][128];
 };
-static_assert(sizeof(GramBars) <= 2048, "barrier block");
+static_assert(sizeof(GramBars) <= 8192, "barrier block");
 
 // ---------------------------------------------------------------------------------------------------------
 // work-item decoding (everything a role needs about one 128-row block; no arrays, lives in registers)
@@ -153,19 +167,21 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE, int BN, int KB, int SEQ>
-__global__ void __launch_bounds__(kGramThreads, 1)
+template <int MODE, int KB, int SEQ>
+__global__ void __launch_bounds__((GramCfg<MODE, KB, SEQ>::kThreads), 1)
 gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel, uint8_t* __restrict__ ws) {
-  using L = GramSmem<BN, KB>;
+  using G = GramCfg<MODE, KB, SEQ>;
+  constexpr int BN = G::BN, NS = G::NS, NB = G::NB, CW = G::CW;
+  using L = GramSmem<BN, KB, NB>;
   constexpr bool kIsNce = (MODE == NCE_FWD || MODE == NCE_BWD);
   constexpr bool kBwd = (MODE == NCE_BWD || MODE == TMP_BWD);
   constexpr bool kColVec = (MODE != NCE_FWD);
+  constexpr int kEpiThreads = 128 * NS;
   constexpr int kON = KB * 64;                       // UMMA #2 N = padded operand width
   constexpr int kKSteps = KB * 4;                    // UMMA #1 K steps (K padded to 64 with zeros)
-  constexpr uint32_t kOCol = 0;                      // TMEM: O accumulator at [0, kON)
-  constexpr uint32_t kSCol = kON;                    // TMEM: S stages at kON + {0, BN}
-  static_assert(kON + 2 * BN <= kTmemCols, "TMEM budget");
-  static_assert(BN % 32 == 0 && BN % 16 == 0, "column tile");
+  constexpr uint32_t kOCol = 0;                      // TMEM: O accumulator at [0, kON) (backward modes only)
+  constexpr uint32_t kSCol = kBwd ? kON : 0;         // TMEM: S stage w at kSCol + w * BN
+  static_assert(BN % CW == 0 && (SEQ == 0 || CW % (SEQ > 0 ? SEQ : 1) == 0), "column tile / chunk / sequence");
   static_assert(L::kDynamic <= 232448, "shared memory budget");
 
   extern __shared__ uint8_t smem_raw[];
@@ -176,11 +192,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   if (threadIdx.x == 0) {
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
-    for (int i = 0; i < kNumBStages; ++i) {
+    for (int i = 0; i < NB; ++i) {
       mbar_init(&bars->b_full[i], 1);
       mbar_init(&bars->b_empty[i], kColVec ? 1 + 4 : 1);    // UMMA commit (+ one elected lane per epilogue warp)
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->s_empty[i], 128);
       mbar_init(&bars->w_full[i], 128);
@@ -212,10 +228,10 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         for (int kb = 0; kb < KB; ++kb)
           tma_load_1d(smem + L::kAOff + kb * 16384, x.a_src + kb * x.kstride, 16384, &bars->a_full);
         for (int ct = x.ct_begin; ct < x.ct_end; ++ct, ++nb) {
-          const uint32_t st = nb % kNumBStages;
+          const uint32_t st = nb % NB;
           const int cs = ct >= x.ntc ? 1 : 0, tc = ct - cs * x.ntc;
           const uint8_t* src = (cs ? x.b_src1 : x.b_src0) + (uint64_t)tc * BN * 128;
-          mbar_wait(&bars->b_empty[st], ((nb / kNumBStages) & 1) ^ 1);
+          mbar_wait(&bars->b_empty[st], ((nb / NB) & 1) ^ 1);
           uint8_t* dst = smem + L::kBOff + st * L::kBStage;
           constexpr uint32_t bytes = L::kBTile + (kColVec ? (kIsNce ? 1 : 2) * BN * 4 : 0);
           mbar_arrive_expect_tx(&bars->b_full[st], bytes);
@@ -237,20 +253,21 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const uint64_t da0 = umma_smem_desc(smem_u32(smem + L::kAOff), 16, 1024);
       const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
       const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
+      constexpr int kLag = kBwd ? NS - 1 : 0;         // UMMA #2 of tile t is issued after UMMA #1 of tile t + kLag
       uint32_t nb = 0, ni = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
         mbar_wait(&bars->a_full, ni & 1);
         const int ntiles = x.ct_end - x.ct_begin;
-        for (int t = 0; t <= ntiles; ++t) {
+        for (int t = 0; t < ntiles + kLag; ++t) {
           if (t < ntiles) {
-            // ---- UMMA #1 of tile t
-            const uint32_t n = nb + t, st = n % kNumBStages, ss = n & 1;
-            mbar_wait(&bars->b_full[st], (n / kNumBStages) & 1);
-            // backward modes: the S stage is free once UMMA #2 of tile t-2 has been issued (program order);
+            // ---- UMMA #1 of tile t into S stage n % NS
+            const uint32_t n = nb + t, st = n % NB, ss = n % NS;
+            mbar_wait(&bars->b_full[st], (n / NB) & 1);
+            // backward modes: the stage is free once UMMA #2 of tile n - NS has been issued (program order below);
             // forward modes: once the epilogue has drained it
-            if (!kBwd) mbar_wait(&bars->s_empty[ss], ((n >> 1) & 1) ^ 1);
+            if (!kBwd) mbar_wait(&bars->s_empty[ss], ((n / NS) & 1) ^ 1);
             tc_fence_after();
             const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
             const uint32_t d = tmem + kSCol + ss * BN;
@@ -261,15 +278,16 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             umma_commit(&bars->s_full[ss]);
             if (!kBwd) umma_commit(&bars->b_empty[st]);
           }
-          if (kBwd && t > 0) {
-            // ---- UMMA #2 of tile t-1 (issued after UMMA #1 of tile t so the tensor pipe never waits on the epilogue)
-            const uint32_t n = nb + t - 1, st = n % kNumBStages, ss = n & 1;
-            if (t == 1) mbar_wait(&bars->o_empty, (ni & 1) ^ 1);
-            mbar_wait(&bars->w_full[ss], (n >> 1) & 1);
+          if (kBwd && t >= kLag) {
+            // ---- UMMA #2 of tile t - kLag: O += W * B, W = packed bf16 the epilogue left in the consumed S stage
+            const int t2 = t - kLag;
+            const uint32_t n = nb + t2, st = n % NB, ss = n % NS;
+            if (t2 == 0) mbar_wait(&bars->o_empty, (ni & 1) ^ 1);
+            mbar_wait(&bars->w_full[ss], (n / NS) & 1);
             tc_fence_after();
             const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4));
-            const uint32_t a = tmem + kSCol + ss * BN;        // W: packed bf16 over the consumed S stage
-            const uint32_t acc = (t > 1) ? 1u : 0u;
+            const uint32_t a = tmem + kSCol + ss * BN;
+            const uint32_t acc = (t2 > 0) ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < BN / 16; ++k)
               umma_bf16_ts(tmem + kOCol, a + k * 8, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
@@ -285,7 +303,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     }
   } else {
     // =============================== epilogue warps ===============================
-    const int wg = (warp - 2) >> 2;                   // epilogue warpgroup: handles tiles with (tile counter & 1) == wg
+    const int wg = (warp - 2) >> 2;                   // epilogue warpgroup == S stage it owns
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;             // row within the tile == TMEM lane
     const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
@@ -295,6 +313,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     const float coef2 = 2.f * coef1;
     const float margin = p.margin;
     const uint32_t cv_base = smem_u32(smem + L::kBOff + L::kBTile);
+    const uint32_t s_addr = tmem + tlane + kSCol + wg * BN;
     uint32_t nb = 0, ni = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
       Item x;
@@ -309,41 +328,43 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       if (!kIsNce && row_ok) { n_i = x.cv0_0[row]; mim = x.cv1[row] + margin; }   // m_II + margin
       const int seq_i = row / SQ;
       const int ntiles = x.ct_end - ct_begin;
-      for (int t = (wg - (int)nb) & 1; t < ntiles; t += 2) {
-        const uint32_t n = nb + t, st = n % kNumBStages;
-        const uint32_t ss = wg;                       // (n & 1) == wg
+      // first tile of this item that belongs to this warpgroup: (nb + t) % NS == wg
+      for (int t = (int)((wg + NS - nb % NS) % NS); t < ntiles; t += NS) {
+        const uint32_t n = nb + t, st = n % NB;
+        const uint32_t sphase = (n / NS) & 1;
         const int ct = ct_begin + t;
         const int cs = ct >= ntc ? 1 : 0, tc = ct - cs * ntc;
         const int col0 = tc * BN;                     // first column (within side) of this tile
         const uint32_t cv = cv_base + st * L::kBStage;
-        if (kColVec) mbar_wait(&bars->b_full[st], (n / kNumBStages) & 1);
-        mbar_wait(&bars->s_full[ss], (n >> 1) & 1);
+        if (kColVec) mbar_wait(&bars->b_full[st], (n / NB) & 1);
+        mbar_wait(&bars->s_full[wg], sphase);
         tc_fence_after();
         const bool tail = col0 + BN > ncol_valid;
         // columns to drop: j == k (same side) always; in the backward pass also the positive p(k) (other side,
         // same sequence index), whose contribution the finalize kernel adds in fp32
         const bool overlap = col0 < row0 + kTileM && col0 + BN > row0;
         const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == side)) : overlap;
-        const uint32_t s_addr = tmem + tlane + kSCol + ss * BN;
-        auto process = [&](float (&v)[32], const int ch) {
-          const int cbase = col0 + ch * 32;           // column (within side) of v[0]
+#pragma unroll 1
+        for (int ch = 0; ch < BN / CW; ++ch) {
+          float v[CW];
+          tmem_ld_chunk<CW>(s_addr + ch * CW, v);
+          tmem_ld_wait();
+          const int cbase = col0 + ch * CW;           // column (within side) of v[0]
           if (kIsNce) {
             // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
-            // exponentials: kPolyPer8 of every 8 columns on the FMA pipe, the rest on the MUFU pipe (same columns in
-            // the forward and the backward pass, so P_kj is formed from the same E_kj in both)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((j & 7) >= 8 - kPolyPer8) ? ex2_poly(v[j]) : ex2_approx(v[j]);
+            for (int j = 0; j < CW; ++j) v[j] = ((j & 7) >= 8 - FB_POLY_PER8) ? ex2_poly(v[j]) : ex2_approx(v[j]);
             if (MODE == NCE_BWD) {
               // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 cj = lds128(cv + (ch * 32 + j) * 4);
+              for (int j = 0; j < CW; j += 4) {
+                const float4 cj = lds128(cv + (ch * CW + j) * 4);
                 v[j] *= ck + cj.x; v[j + 1] *= ck + cj.y; v[j + 2] *= ck + cj.z; v[j + 3] *= ck + cj.w;
               }
             }
             if (diag || tail) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
+              for (int j = 0; j < CW; ++j) {
                 const int col = cbase + j;
                 if ((diag && col == row) || col >= ncol_valid) v[j] = 0.f;
               }
@@ -351,19 +372,19 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             if (MODE == NCE_FWD) {
               float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
+              for (int j = 0; j < CW; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
               rowacc += (s0 + s1) + (s2 + s3);
             }
           } else {
             // ---------------- temporal: delta_ij, S x S block means, hinge, r_ij
-            float nj[32];
+            float nj[CW];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t4 = lds128(cv + (ch * 32 + j) * 4);
+            for (int j = 0; j < CW; j += 4) {
+              const float4 t4 = lds128(cv + (ch * CW + j) * 4);
               nj[j] = n_i + t4.x; nj[j + 1] = n_i + t4.y; nj[j + 2] = n_i + t4.z; nj[j + 3] = n_i + t4.w;
             }
 #pragma unroll
-            for (int g0 = 0; g0 < 32; g0 += SQ) {
+            for (int g0 = 0; g0 < CW; g0 += SQ) {
               float gsum = 0.f;
 #pragma unroll
               for (int j = 0; j < SQ; ++j) {
@@ -377,7 +398,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               for (int o = 1; o < SQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
               const int colg = cbase + g0;
               const float m_ij = gsum * inv_cnt;
-              const float mjm = lds32(cv + (BN + ch * 32 + g0) * 4) + margin;   // m_JJ + margin
+              const float mjm = lds32(cv + (BN + ch * CW + g0) * 4) + margin;   // m_JJ + margin
               bool pair_ok = row_ok;
               if (tail) pair_ok = pair_ok && colg < ncol_valid;
               if (diag) pair_ok = pair_ok && (colg / SQ) != seq_i;    // the block diagonal is done exactly elsewhere
@@ -393,32 +414,19 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           }
           if (kBwd) {
             // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed
-            uint32_t pk[16];
+            uint32_t pk[CW / 2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            tmem_st16(s_addr + ch * 16, pk);
-          }
-        };
-        // chunks of 32 columns, software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
-        {
-          float va[32], vb[32];
-          tmem_ld32(s_addr, va);
-#pragma unroll
-          for (int ch = 0; ch < BN / 32; ++ch) {
-            tmem_ld_wait();
-            if (ch + 1 < BN / 32) {
-              if (ch & 1) tmem_ld32(s_addr + (ch + 1) * 32, va); else tmem_ld32(s_addr + (ch + 1) * 32, vb);
-            }
-            if (ch & 1) process(vb, ch); else process(va, ch);
+            for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            tmem_st_packed<CW>(s_addr + ch * (CW / 2), pk);
           }
         }
         if (kBwd) {
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(&bars->w_full[ss]);
+          mbar_arrive(&bars->w_full[wg]);
         } else {
           tc_fence_before();
-          mbar_arrive(&bars->s_empty[ss]);             // S stage drained (all tcgen05.ld of this thread completed)
+          mbar_arrive(&bars->s_empty[wg]);             // S stage drained (all tcgen05.ld of this thread completed)
         }
         if (kColVec) {
           __syncwarp();
@@ -427,22 +435,23 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       }
       nb += ntiles;
 
-      // ---------------- item epilogue: fold warpgroup 1's per-row partials into warpgroup 0
+      // ---------------- item epilogue: fold the per-row partials of warpgroups 1.. into warpgroup 0
       if (MODE != NCE_BWD) {
-        if (wg == 1) {
-          bars->part_acc[trow] = rowacc;
-          if (!kIsNce) { bars->part_hinge[trow] = hinge_acc; bars->part_cnt[trow] = cnt_i; }
+        if (wg > 0) {
+          bars->part_acc[wg - 1][trow] = rowacc;
+          if (!kIsNce) { bars->part_hinge[wg - 1][trow] = hinge_acc; bars->part_cnt[wg - 1][trow] = cnt_i; }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (wg == 0) {
-          rowacc += bars->part_acc[trow];
+#pragma unroll
+          for (int w = 0; w < NS - 1; ++w) rowacc += bars->part_acc[w][trow];
           if (MODE == NCE_FWD) {
             float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) +
                            ((((uint64_t)x.c * p.nProb + x.q) * p.S + x.s) * 2 + side) * p.bpad;
             rpart[row] = row_ok ? rowacc : 0.f;
           } else {
-            hinge_acc += bars->part_hinge[trow];
-            cnt_i += bars->part_cnt[trow];
+#pragma unroll
+            for (int w = 0; w < NS - 1; ++w) { hinge_acc += bars->part_hinge[w][trow]; cnt_i += bars->part_cnt[w][trow]; }
             if (kBwd && row_ok) reinterpret_cast<float*>(ws + p.rho_off)[(uint64_t)x.c * p.Bpad + row] = rowacc;
             if (row_ok && (lane & (SQ - 1)) == 0)
               reinterpret_cast<int32_t*>(ws + p.cnt_off)[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
@@ -463,7 +472,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           out = reinterpret_cast<float*>(ws + p.dx_off) + ((uint64_t)x.c * p.Bpad + row) * kON;
         }
 #pragma unroll 1
-        for (int ch = wg; ch < kON / 32; ch += 2) {     // the two warpgroups split the columns of O
+        for (int ch = wg; ch < kON / 32; ch += NS) {     // the warpgroups split the columns of O
           float v[32];
           tmem_ld32(tmem + tlane + kOCol + ch * 32, v);
           tmem_ld_wait();
@@ -477,7 +486,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         mbar_arrive(&bars->o_empty);
       }
       if (MODE != NCE_BWD) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // partial arrays / red[] may be reused after this point
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // partial arrays / red[] may be reused now
         if (!kIsNce && wg == 0 && trow == 0) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;

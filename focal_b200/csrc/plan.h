@@ -30,8 +30,8 @@ struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
 };
 
 // Column-tile width of the Gram kernels as a function of the operand width in 64-element K blocks.  TMEM holds
-// O (kb*64 columns) + two S stages (2*BN): kb = 4 leaves room for BN = 96 only (see gram_kernel.cuh).
-constexpr int tile_bn(int kb) { return kb >= 4 ? 96 : 128; }
+// O (kb*64 columns) + NS S stages (NS*BN): see GramCfg in gram_kernel.cuh.
+constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : 64; }
 
 // Problems handled by one InfoNCE launch (all with the same operand width / K-block count).
 struct ProbSel {

@@ -148,6 +148,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -155,6 +160,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, float (&v)[CW]) {
+  static_assert(CW == 16 || CW == 32, "chunk width");
+  if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+}
+template <int CW>
+__device__ __forceinline__ void tmem_st_packed(uint32_t taddr, const uint32_t (&r)[CW / 2]) {
+  if constexpr (CW == 32) tmem_st16(taddr, r); else tmem_st8(taddr, r);
 }
 
 // ------------------------------------------------------------------ UMMA descriptors
