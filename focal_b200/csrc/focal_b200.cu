@@ -441,7 +441,7 @@ extern "C" int focal_b200_debug_umma(const void* a_img, uint32_t a_bytes, const 
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 template <int N, int B_MN, int A_TMEM>
-__global__ void __launch_bounds__(128, 1) umma_rate_kernel(uint32_t iters, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(uint32_t iters, long long* cycles, uint32_t sync_mode = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -450,61 +450,135 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(uint32_t iters, long 
   for (uint32_t o = threadIdx.x * 16; o < 64 * 1024 + 128 * 1024; o += blockDim.x * 16)
     *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __shared__ uint64_t bar_done[2], bar_ready;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1); mbar_init(&bar_ready, 1);
+    fence_mbar_init();
+  }
   if (warp == 0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (threadIdx.x == 0) {
+  // CUTLASS-style issue: the whole warp runs the (warp-uniform) loop and one elected lane issues.  Every operand of
+  // tcgen05.mma is derived from values the compiler can prove warp-uniform (shfl broadcast, kernel parameters,
+  // shared-memory base), otherwise ptxas wraps each instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall.
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  if (__shfl_sync(0xffffffffu, warp, 0) == 0) {
     const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 64 * 1024);
     constexpr uint32_t idesc = umma_idesc(UMMA_BF16, 128, N, 0, B_MN);
     const uint64_t da0 = umma_smem_desc(a_addr, 16, 1024);
     const uint64_t db0 = B_MN ? umma_smem_desc(b_addr, 128 * 128, 1024) : umma_smem_desc(b_addr, 16, 1024);
     const long long t0 = clock64();
     for (uint32_t it = 0; it < iters; ++it) {
-      const uint32_t d = tmem + (it & 1) * (A_TMEM ? 128 : 256) * (N > 128 && A_TMEM ? 0 : 1);
+      if (sync_mode >= 1 && it >= 2) mbar_wait(&bar_done[it & 1], ((it >> 1) - 1) & 1);   // like s_empty / w_full
+      if (sync_mode >= 2) tc_fence_after();
+      const uint32_t d = tmem_u + (it & 1) * (A_TMEM ? 128 : 256) * (N > 128 && A_TMEM ? 0 : 1);
+      if (elect_one()) {
 #pragma unroll
-      for (uint32_t k = 0; k < 8; ++k) {
-        const uint64_t da = da0 + (((k >> 2) * 16384 + (k & 3) * 32) >> 4);
-        const uint64_t db = db0 + ((B_MN ? k * 2048 : (k >> 2) * (N * 128) + (k & 3) * 32) >> 4);
-        if (A_TMEM) umma_bf16_ts(d, tmem + 384 + k * 8, db, idesc, k > 0);
-        else umma_bf16(d, da, db, idesc, k > 0);
+        for (uint32_t k = 0; k < 8; ++k) {
+          const uint64_t da = da0 + (((k >> 2) * 16384 + (k & 3) * 32) >> 4);
+          const uint64_t db = db0 + ((B_MN ? k * 2048 : (k >> 2) * (N * 128) + (k & 3) * 32) >> 4);
+          if (A_TMEM) umma_bf16_ts(d, tmem_u + 384 + k * 8, db, idesc, k > 0);
+          else umma_bf16(d, da, db, idesc, k > 0);
+        }
+        if (sync_mode >= 1) umma_commit(&bar_done[it & 1]);                                // like s_full
+        if (sync_mode >= 3) umma_commit(&bar_ready);                                       // like b_empty (never waited)
       }
+      __syncwarp();
     }
-    umma_commit(&bar);
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
     mbar_wait(&bar, 0);
     const long long t1 = clock64();
-    cycles[blockIdx.x] = t1 - t0;
+    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 template <int N, int B_MN, int A_TMEM>
-int launch_rate(uint32_t iters, uint32_t grid, long long* cycles, cudaStream_t st) {
+int launch_rate(uint32_t iters, uint32_t grid, long long* cycles, cudaStream_t st, uint32_t sync_mode) {
   const uint32_t smem = 64 * 1024 + 128 * 1024 + 1024;
   auto k = umma_rate_kernel<N, B_MN, A_TMEM>;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return cuda_ok("cudaFuncSetAttribute(umma_rate_kernel)");
-  k<<<grid, 128, smem, st>>>(iters, cycles);
+  k<<<grid, 128, smem, st>>>(iters, cycles, sync_mode);
   return cuda_ok("umma_rate_kernel");
 }
 }  // namespace
 
 // 8 MMAs (K = 16 each) per iteration; returns per-CTA cycles for `iters` iterations.
-extern "C" int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t iters, uint32_t /*unused*/, uint32_t grid,
+extern "C" int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t iters, uint32_t sync_mode, uint32_t grid,
                                           long long* cycles, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint32_t b_mn = flags & 1, a_tmem = (flags >> 1) & 1;
 #define FB_RATE(NN)                                                                      \
   if (N == NN) {                                                                         \
-    if (!b_mn && !a_tmem) return launch_rate<NN, 0, 0>(iters, grid, cycles, st);         \
-    if (b_mn && !a_tmem) return launch_rate<NN, 1, 0>(iters, grid, cycles, st);          \
-    if (!b_mn && a_tmem) return launch_rate<NN, 0, 1>(iters, grid, cycles, st);          \
-    return launch_rate<NN, 1, 1>(iters, grid, cycles, st);                               \
+    if (!b_mn && !a_tmem) return launch_rate<NN, 0, 0>(iters, grid, cycles, st, sync_mode);         \
+    if (b_mn && !a_tmem) return launch_rate<NN, 1, 0>(iters, grid, cycles, st, sync_mode);          \
+    if (!b_mn && a_tmem) return launch_rate<NN, 0, 1>(iters, grid, cycles, st, sync_mode);          \
+    return launch_rate<NN, 1, 1>(iters, grid, cycles, st, sync_mode);                               \
   }
   FB_RATE(32) FB_RATE(64) FB_RATE(96) FB_RATE(128) FB_RATE(192) FB_RATE(256)
 #undef FB_RATE
   return FOCAL_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bring-up micro-benchmark: L2 -> shared-memory throughput of linear bulk copies (cp.async.bulk) per SM
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(64, 1) tma_rate_kernel(const uint8_t* src, uint32_t span_bytes, uint32_t copy_bytes,
+                                                         uint32_t copies_per_stage, uint32_t stages, uint32_t iters,
+                                                         long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[8], empty[8];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t stage_bytes = copy_bytes * copies_per_stage;
+  const int warp_u = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  if (warp_u == 0) {                              // producer: warp-uniform loop, one elected lane issues
+    const long long t0 = clock64();
+    uint32_t off = blockIdx.x * 65536u;
+    for (uint32_t n = 0; n < iters; ++n) {
+      const uint32_t st = n % stages;
+      mbar_wait(&empty[st], ((n / stages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[st], stage_bytes);
+        for (uint32_t c = 0; c < copies_per_stage; ++c) {
+          tma_load_1d(smem + st * stage_bytes + c * copy_bytes, src + (off & (span_bytes - 1)), copy_bytes, &full[st]);
+          off += copy_bytes;
+        }
+      }
+      off = __shfl_sync(0xffffffffu, off, 0);
+    }
+    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x * 2] = clock64() - t0;
+  } else if (threadIdx.x == 32) {                 // consumer: frees the stage as soon as the bytes have landed
+    const long long t0 = clock64();
+    for (uint32_t n = 0; n < iters; ++n) {
+      const uint32_t st = n % stages;
+      mbar_wait(&full[st], (n / stages) & 1);
+      mbar_arrive(&empty[st]);
+    }
+    cycles[blockIdx.x * 2 + 1] = clock64() - t0;
+  }
+}
+}  // namespace
+
+extern "C" int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, uint32_t copy_bytes,
+                                         uint32_t copies_per_stage, uint32_t stages, uint32_t iters, uint32_t grid,
+                                         long long* cycles, void* stream) {
+  const uint32_t smem = copy_bytes * copies_per_stage * stages + 1024;
+  if (smem > 220 * 1024 || stages > 8) return FOCAL_EINVAL;
+  if (cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return cuda_ok("cudaFuncSetAttribute(tma_rate_kernel)");
+  tma_rate_kernel<<<grid, 64, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(src), span_bytes,
+                                                                        copy_bytes, copies_per_stage, stages, iters,
+                                                                        cycles);
+  return cuda_ok("tma_rate_kernel");
 }

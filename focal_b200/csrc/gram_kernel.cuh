@@ -33,6 +33,15 @@ namespace fb {
 enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 
 // ---- tuning knobs (overridable with -D for tools/variant_bench.py experiments) ----
+#ifndef FB_KB4_BN
+#define FB_KB4_BN 64            // column tile for 256-wide operands (TMEM: 256 O columns + NS * BN <= 512)
+#endif
+#ifndef FB_KB4_NS
+#define FB_KB4_NS 4
+#endif
+#ifndef FB_KB4_NB
+#define FB_KB4_NB 4
+#endif
 #ifndef FB_POLY_PER8
 #define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
 #endif
@@ -43,9 +52,9 @@ template <int MODE, int KB, int SEQ>
 struct GramCfg {
   static constexpr bool kBwd = (MODE == 1 || MODE == 3);
   static constexpr bool kTmp = (MODE >= 2);
-  static constexpr int BN = KB <= 2 ? 128 : 64;                       // column tile
-  static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : 4;             // S stages == epilogue warpgroups
-  static constexpr int NB = KB <= 3 ? 5 : 4;                          // B-tile ring stages (shared memory budget)
+  static constexpr int BN = KB <= 2 ? 128 : (KB == 4 ? FB_KB4_BN : 64);          // column tile
+  static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : 4);  // S stages == epilogue warpgroups
+  static constexpr int NB = KB <= 3 ? 5 : FB_KB4_NB;                             // B-tile ring stages (smem budget)
   static constexpr int CW = (NS == 4 && kTmp && SEQ <= 16) ? 16 : 32; // columns per tcgen05.ld (register budget)
   static constexpr int kThreads = 64 + 128 * NS;
   static_assert((kBwd ? KB * 64 : 0) + NS * BN <= kTmemCols, "TMEM budget");
@@ -187,7 +196,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GramBars* bars = reinterpret_cast<GramBars*>(smem + L::kBarOff);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform role index (the compiler must be able to prove uniformity, see the issue-loop note below)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     mbar_init(&bars->a_full, 1);
@@ -212,91 +222,140 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
   const int n_items = gram_num_items<MODE>(p, sel);
+
+  // Issue-loop note (measured, tools/umma_rate.py / tools/tma_rate.py): tcgen05.mma, tcgen05.commit and cp.async.bulk
+  // take their operands from uniform registers.  If ptxas cannot prove an operand warp-uniform it wraps EVERY such
+  // instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~80-270 clk per instruction instead of ~10), which
+  // made the single issuing lane -- not the tensor pipe -- the bound of earlier versions.  Therefore the producer
+  // and issuer warps run their loops with all 32 lanes on warp-uniform values and only the asm itself sits under
+  // elect_one().
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    {
       uint32_t nb = 0, ni = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
         mbar_wait(&bars->a_empty, (ni & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->a_full, L::kABytes);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->a_full, L::kABytes);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_1d(smem + L::kAOff + kb * 16384, x.a_src + kb * x.kstride, 16384, &bars->a_full);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_1d(smem + L::kAOff + kb * 16384, x.a_src + kb * x.kstride, 16384, &bars->a_full);
+        }
+        __syncwarp();
         for (int ct = x.ct_begin; ct < x.ct_end; ++ct, ++nb) {
           const uint32_t st = nb % NB;
           const int cs = ct >= x.ntc ? 1 : 0, tc = ct - cs * x.ntc;
           const uint8_t* src = (cs ? x.b_src1 : x.b_src0) + (uint64_t)tc * BN * 128;
           mbar_wait(&bars->b_empty[st], ((nb / NB) & 1) ^ 1);
-          uint8_t* dst = smem + L::kBOff + st * L::kBStage;
-          constexpr uint32_t bytes = L::kBTile + (kColVec ? (kIsNce ? 1 : 2) * BN * 4 : 0);
-          mbar_arrive_expect_tx(&bars->b_full[st], bytes);
+          if (elect_one()) {
+            uint8_t* dst = smem + L::kBOff + st * L::kBStage;
+            constexpr uint32_t bytes = L::kBTile + (kColVec ? (kIsNce ? 1 : 2) * BN * 4 : 0);
+            mbar_arrive_expect_tx(&bars->b_full[st], bytes);
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_1d(dst + kb * (BN * 128), src + kb * x.kstride, BN * 128, &bars->b_full[st]);
-          if (kColVec) {
-            tma_load_1d(dst + L::kBTile, (cs ? x.cv0_1 : x.cv0_0) + tc * BN, BN * 4, &bars->b_full[st]);
-            if (!kIsNce) tma_load_1d(dst + L::kBTile + BN * 4, x.cv1 + tc * BN, BN * 4, &bars->b_full[st]);
+            for (int kb = 0; kb < KB; ++kb)
+              tma_load_1d(dst + kb * (BN * 128), src + kb * x.kstride, BN * 128, &bars->b_full[st]);
+            if (kColVec) {
+              tma_load_1d(dst + L::kBTile, (cs ? x.cv0_1 : x.cv0_0) + tc * BN, BN * 4, &bars->b_full[st]);
+              if (!kIsNce) tma_load_1d(dst + L::kBTile + BN * 4, x.cv1 + tc * BN, BN * 4, &bars->b_full[st]);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // =============================== UMMA issuer ===============================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc1 = umma_idesc(UMMA_BF16, 128, BN, 0, 0);     // S = A(K-major) * B(K-major)^T
       constexpr uint32_t idesc2 = umma_idesc(UMMA_BF16, 128, kON, 0, 1);    // O += W(TMEM) * B(MN-major)
       const uint64_t da0 = umma_smem_desc(smem_u32(smem + L::kAOff), 16, 1024);
       const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
       const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
-      constexpr int kLag = kBwd ? NS - 1 : 0;         // UMMA #2 of tile t is issued after UMMA #1 of tile t + kLag
       uint32_t nb = 0, ni = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
         mbar_wait(&bars->a_full, ni & 1);
         const int ntiles = x.ct_end - x.ct_begin;
-        for (int t = 0; t < ntiles + kLag; ++t) {
-          if (t < ntiles) {
-            // ---- UMMA #1 of tile t into S stage n % NS
+        if (!kBwd) {
+          for (int t = 0; t < ntiles; ++t) {
+            // ---- UMMA #1 of tile t into S stage n % NS (free once the epilogue has drained it)
             const uint32_t n = nb + t, st = n % NB, ss = n % NS;
             mbar_wait(&bars->b_full[st], (n / NB) & 1);
-            // backward modes: the stage is free once UMMA #2 of tile n - NS has been issued (program order below);
-            // forward modes: once the epilogue has drained it
-            if (!kBwd) mbar_wait(&bars->s_empty[ss], ((n / NS) & 1) ^ 1);
+            mbar_wait(&bars->s_empty[ss], ((n / NS) & 1) ^ 1);
             tc_fence_after();
-            const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
-            const uint32_t d = tmem + kSCol + ss * BN;
+            if (elect_one()) {
+              const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
+              const uint32_t d = tmem + kSCol + ss * BN;
 #pragma unroll
-            for (int k = 0; k < kKSteps; ++k)
-              umma_bf16(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
-                        db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
-            umma_commit(&bars->s_full[ss]);
-            if (!kBwd) umma_commit(&bars->b_empty[st]);
+              for (int k = 0; k < kKSteps; ++k)
+                umma_bf16(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                          db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
+              umma_commit(&bars->s_full[ss]);
+              umma_commit(&bars->b_empty[st]);
+            }
+            __syncwarp();
           }
-          if (kBwd && t >= kLag) {
-            // ---- UMMA #2 of tile t - kLag: O += W * B, W = packed bf16 the epilogue left in the consumed S stage
-            const int t2 = t - kLag;
-            const uint32_t n = nb + t2, st = n % NB, ss = n % NS;
-            if (t2 == 0) mbar_wait(&bars->o_empty, (ni & 1) ^ 1);
-            mbar_wait(&bars->w_full[ss], (n / NS) & 1);
-            tc_fence_after();
-            const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4));
-            const uint32_t a = tmem + kSCol + ss * BN;
-            const uint32_t acc = (t2 > 0) ? 1u : 0u;
+        } else {
+          // Out-of-order issue: UMMA #2 of the oldest tile whose W is ready, else UMMA #1 of the next tile whose B
+          // tile has landed and whose S stage is free (UMMA #2 of tile t1 - NS already issued).  Neither wait may
+          // block the other: the B ring is too short (shared memory) to hide a blocked issuer behind prefetch.
+          int t1 = 0, t2 = 0;
+          while (t2 < ntiles) {
+            bool did = false;
+            if (t2 < t1) {
+              const uint32_t n = nb + t2, st = n % NB, ss = n % NS;
+              if (t2 == 0) mbar_wait(&bars->o_empty, (ni & 1) ^ 1);
+              const bool ready = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&bars->w_full[ss], (n / NS) & 1), 0) != 0;
+              if (ready) {
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4));
+                  const uint32_t a = tmem + kSCol + ss * BN;    // W: packed bf16 over the consumed S stage
+                  const uint32_t acc = (t2 > 0) ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < BN / 16; ++k)
-              umma_bf16_ts(tmem + kOCol, a + k * 8, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
-            umma_commit(&bars->b_empty[st]);
+                  for (int k = 0; k < BN / 16; ++k)
+                    umma_bf16_ts(tmem + kOCol, a + k * 8, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
+                  umma_commit(&bars->b_empty[st]);
+                }
+                __syncwarp();
+                ++t2;
+                did = true;
+              }
+            }
+            if (t1 < ntiles && t1 - t2 < NS) {
+              const uint32_t n = nb + t1, st = n % NB, ss = n % NS;
+              const bool ready = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&bars->b_full[st], (n / NB) & 1), 0) != 0;
+              if (ready) {
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
+                  const uint32_t d = tmem + kSCol + ss * BN;
+#pragma unroll
+                  for (int k = 0; k < kKSteps; ++k)
+                    umma_bf16(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                              db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
+                  umma_commit(&bars->s_full[ss]);
+                }
+                __syncwarp();
+                ++t1;
+                did = true;
+              }
+            }
+            if (!did) __nanosleep(20);
           }
         }
         nb += ntiles;
-        umma_commit(&bars->a_empty);
-        if (kBwd) umma_commit(&bars->o_full);
+        if (elect_one()) {
+          umma_commit(&bars->a_empty);
+          if (kBwd) umma_commit(&bars->o_full);
+        }
+        __syncwarp();
       }
       // commits complete in issue order: once the last one has landed no arrival is still in flight
       if (ni > 0) mbar_wait(&bars->a_empty, (ni - 1) & 1);
@@ -344,16 +403,23 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         // same sequence index), whose contribution the finalize kernel adds in fp32
         const bool overlap = col0 < row0 + kTileM && col0 + BN > row0;
         const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == side)) : overlap;
+#ifdef FB_EXP_LDTM_SKIP
+#define FB_CH_STEP FB_EXP_LDTM_SKIP      /* experiment only: touch every n-th chunk (wrong results) */
+#else
+#define FB_CH_STEP 1
+#endif
 #pragma unroll 1
-        for (int ch = 0; ch < BN / CW; ++ch) {
+        for (int ch = 0; ch < BN / CW; ch += FB_CH_STEP) {
           float v[CW];
           tmem_ld_chunk<CW>(s_addr + ch * CW, v);
           tmem_ld_wait();
           const int cbase = col0 + ch * CW;           // column (within side) of v[0]
           if (kIsNce) {
             // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
+#ifndef FB_EXP_TRIVIAL_EPI
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = ((j & 7) >= 8 - FB_POLY_PER8) ? ex2_poly(v[j]) : ex2_approx(v[j]);
+#endif
             if (MODE == NCE_BWD) {
               // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
 #pragma unroll
@@ -376,6 +442,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               rowacc += (s0 + s1) + (s2 + s3);
             }
           } else {
+#ifdef FB_EXP_TRIVIAL_EPI
+            // experiment only: no epilogue math (wrong results) -- how fast is the skeleton without it?
+#pragma unroll
+            for (int j = 0; j < CW; ++j) { v[j] *= coef1; rowacc += v[j]; }
+#else
             // ---------------- temporal: delta_ij, S x S block means, hinge, r_ij
             float nj[CW];
 #pragma unroll
@@ -411,6 +482,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
               for (int j = 0; j < SQ; ++j) { v[g0 + j] *= coef; rowacc += v[g0 + j]; }
             }
+#endif
           }
           if (kBwd) {
             // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed

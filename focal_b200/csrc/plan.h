@@ -31,7 +31,10 @@ struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
 
 // Column-tile width of the Gram kernels as a function of the operand width in 64-element K blocks.  TMEM holds
 // O (kb*64 columns) + NS S stages (NS*BN): see GramCfg in gram_kernel.cuh.
-constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : 64; }
+#ifndef FB_KB4_BN
+#define FB_KB4_BN 64
+#endif
+constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : (kb == 4 ? FB_KB4_BN : 64); }
 
 // Problems handled by one InfoNCE launch (all with the same operand width / K-block count).
 struct ProbSel {
@@ -153,6 +156,9 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
       if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
     }
     p.nsplit_fwd = best;
+#ifdef FB_NSPLIT_FWD
+    p.nsplit_fwd = FB_NSPLIT_FWD;
+#endif
   }
 
   // ---- workspace

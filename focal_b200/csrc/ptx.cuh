@@ -67,11 +67,20 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 #ifndef FB_WAIT_TIMEOUT_NS
 #define FB_WAIT_TIMEOUT_NS 2000000000ull
 #endif
+#ifndef FB_WAIT_HINT_NS
+#define FB_WAIT_HINT_NS 0       // 0: plain try_wait spin (lowest wake-up latency); > 0: suspend-time hint in ns
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
-  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
-    if (global_timer_ns() - t0 > FB_WAIT_TIMEOUT_NS) {
+  uint32_t spins = 0;
+  while (true) {
+#if FB_WAIT_HINT_NS > 0
+    if (mbar_try_wait_hint(bar, parity, FB_WAIT_HINT_NS)) return;
+#else
+    if (mbar_try_wait(bar, parity)) return;
+#endif
+    if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > FB_WAIT_TIMEOUT_NS) {
       printf("focal_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
       __trap();

@@ -43,7 +43,7 @@ def run(B=8192, D=256, M=2, S=4, steps=30):
         tag = os.path.basename(path)[len("libfocal_b200_"):-3]
         lib = _cabi.load(path)
         cfg = _cabi.FocalCfg(B=B, S=S, M=M, D=D, temperature=0.5, margin=1.0, w_shared=1, w_private=1, w_orth=3,
-                             w_rank=5, need_grad=1, terms=7, seq_begin=0, seq_end=B // S)
+                             w_rank=5, need_grad=int(os.environ.get('FB_NEED_GRAD', '1')), terms=7, seq_begin=0, seq_end=B // S)
         info = _cabi.FocalWsInfo()
         assert lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info)) == 0
         raw = torch.empty(info.total_bytes + 1024, dtype=torch.uint8, device="cuda")
