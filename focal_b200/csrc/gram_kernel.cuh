@@ -34,13 +34,13 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 
 // ---- tuning knobs (overridable with -D for tools/variant_bench.py experiments) ----
 #ifndef FB_KB4_BN
-#define FB_KB4_BN 64            // column tile for 256-wide operands (TMEM: 256 O columns + NS * BN <= 512)
+#define FB_KB4_BN 96            // column tile for 256-wide operands (TMEM: 256 O columns + NS * BN <= 512)
 #endif
 #ifndef FB_KB4_NS
-#define FB_KB4_NS 4
+#define FB_KB4_NS 2
 #endif
 #ifndef FB_KB4_NB
-#define FB_KB4_NB 4
+#define FB_KB4_NB 3
 #endif
 #ifndef FB_POLY_PER8
 #define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
@@ -239,7 +239,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
-        mbar_wait(&bars->a_empty, (ni & 1) ^ 1);
+        mbar_wait_warp(&bars->a_empty, (ni & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bars->a_full, L::kABytes);
 #pragma unroll
@@ -251,7 +251,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           const uint32_t st = nb % NB;
           const int cs = ct >= x.ntc ? 1 : 0, tc = ct - cs * x.ntc;
           const uint8_t* src = (cs ? x.b_src1 : x.b_src0) + (uint64_t)tc * BN * 128;
-          mbar_wait(&bars->b_empty[st], ((nb / NB) & 1) ^ 1);
+          mbar_wait_warp(&bars->b_empty[st], ((nb / NB) & 1) ^ 1);
           if (elect_one()) {
             uint8_t* dst = smem + L::kBOff + st * L::kBStage;
             constexpr uint32_t bytes = L::kBTile + (kColVec ? (kIsNce ? 1 : 2) * BN * 4 : 0);
@@ -280,14 +280,14 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
-        mbar_wait(&bars->a_full, ni & 1);
+        mbar_wait_warp(&bars->a_full, ni & 1);
         const int ntiles = x.ct_end - x.ct_begin;
         if (!kBwd) {
           for (int t = 0; t < ntiles; ++t) {
             // ---- UMMA #1 of tile t into S stage n % NS (free once the epilogue has drained it)
             const uint32_t n = nb + t, st = n % NB, ss = n % NS;
-            mbar_wait(&bars->b_full[st], (n / NB) & 1);
-            mbar_wait(&bars->s_empty[ss], ((n / NS) & 1) ^ 1);
+            mbar_wait_warp(&bars->b_full[st], (n / NB) & 1);
+            mbar_wait_warp(&bars->s_empty[ss], ((n / NS) & 1) ^ 1);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
@@ -310,8 +310,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             bool did = false;
             if (t2 < t1) {
               const uint32_t n = nb + t2, st = n % NB, ss = n % NS;
-              if (t2 == 0) mbar_wait(&bars->o_empty, (ni & 1) ^ 1);
-              const bool ready = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&bars->w_full[ss], (n / NS) & 1), 0) != 0;
+              if (t2 == 0) mbar_wait_warp(&bars->o_empty, (ni & 1) ^ 1);
+              const bool ready = mbar_try_wait_warp(&bars->w_full[ss], (n / NS) & 1);
               if (ready) {
                 tc_fence_after();
                 if (elect_one()) {
@@ -330,7 +330,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             }
             if (t1 < ntiles && t1 - t2 < NS) {
               const uint32_t n = nb + t1, st = n % NB, ss = n % NS;
-              const bool ready = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&bars->b_full[st], (n / NB) & 1), 0) != 0;
+              const bool ready = mbar_try_wait_warp(&bars->b_full[st], (n / NB) & 1);
               if (ready) {
                 tc_fence_after();
                 if (elect_one()) {
@@ -358,7 +358,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         __syncwarp();
       }
       // commits complete in issue order: once the last one has landed no arrival is still in flight
-      if (ni > 0) mbar_wait(&bars->a_empty, (ni - 1) & 1);
+      if (ni > 0) mbar_wait_warp(&bars->a_empty, (ni - 1) & 1);
     }
   } else {
     // =============================== epilogue warps ===============================

@@ -32,7 +32,7 @@ struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
 // Column-tile width of the Gram kernels as a function of the operand width in 64-element K blocks.  TMEM holds
 // O (kb*64 columns) + NS S stages (NS*BN): see GramCfg in gram_kernel.cuh.
 #ifndef FB_KB4_BN
-#define FB_KB4_BN 64
+#define FB_KB4_BN 96
 #endif
 constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : (kb == 4 ? FB_KB4_BN : 64); }
 

@@ -88,6 +88,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Warp-level variants for the single-issuer roles: one elected lane touches the mbarrier (32 lanes polling the same
+// barrier serialise in the SYNCS unit), the result is broadcast so that control flow stays provably warp-uniform.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if (elect_one()) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ bool mbar_try_wait_warp(uint64_t* bar, uint32_t parity) {
+  int ok = 0;
+  if (elect_one()) ok = mbar_try_wait(bar, parity) ? 1 : 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
 // ------------------------------------------------------------------ TMA (bulk, linear)
 // global -> shared, completion reported as transaction bytes on an mbarrier.  SASS: UBLKCP.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
