@@ -19,6 +19,10 @@ constexpr int kKBlk = 64;                                // bf16 elements per 12
 struct OpDesc {          // one normalised InfoNCE operand = a column slice of one feature tensor
   int32_t tensor, col0, width, kb;   // kb = ceil(width / 64) K blocks
   uint64_t off;                      // bytes from ws base: bf16 [kb][S*bpad][64], position-major rows, swizzled
+  int32_t nuse;                      // problems this operand takes part in (<= M - 1 for shared, 1 for private)
+  int32_t use_prob[kMaxM];           // ... their indices,
+  int32_t use_side[kMaxM];           // ... which side of z the operand is on,
+  int32_t use_partner[kMaxM];        // ... and the operand on the other side (row p(k) lives there)
 };
 struct ProbDesc {        // one InfoNCE problem: z = [opA ; opB] per position (loss.py:66-73)
   int32_t opA, opB, kind;            // kind 0 = shared (modal matching), 1 = private (transformation invariant)
@@ -115,12 +119,12 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   auto op_private = [&](int t) { return 2 * t + 1; };
   auto op_full = [&](int t) { return 2 * p.nT + t; };
   for (int t = 0; t < p.nT; ++t) {
-    p.ops[op_shared(t)] = OpDesc{t, 0, d, (d + kKBlk - 1) / kKBlk, 0};
-    p.ops[op_private(t)] = OpDesc{t, d, d, (d + kKBlk - 1) / kKBlk, 0};
+    p.ops[op_shared(t)] = OpDesc{t, 0, d, (d + kKBlk - 1) / kKBlk, 0, 0, {0}, {0}, {0}};
+    p.ops[op_private(t)] = OpDesc{t, d, d, (d + kKBlk - 1) / kKBlk, 0, 0, {0}, {0}, {0}};
   }
   p.nOps = 2 * p.nT;
   if (c.no_private) {
-    for (int t = 0; t < p.nT; ++t) p.ops[op_full(t)] = OpDesc{t, 0, c.D, p.kbFull, 0};
+    for (int t = 0; t < p.nT; ++t) p.ops[op_full(t)] = OpDesc{t, 0, c.D, p.kbFull, 0, 0, {0}, {0}, {0}};
     p.nOps = 3 * p.nT;
   }
   // ---- problems in reference order (loss.py:162-186)
@@ -143,6 +147,15 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
       for (int j = i + 1; j < M; ++j) p.orth[no++] = OrthDesc{t, d, v * M + j, d, d};
     }
   p.nOrth = no;
+  // per-operand use lists (what finalize needs: which dz accumulators belong to an operand)
+  for (int o = 0; o < p.nOps; ++o) p.ops[o].nuse = 0;
+  for (int q = 0; q < p.nProb; ++q) {
+    const int oa = p.probs[q].opA, ob = p.probs[q].opB;
+    OpDesc& A = p.ops[oa];
+    OpDesc& Bo = p.ops[ob];
+    A.use_prob[A.nuse] = q; A.use_side[A.nuse] = 0; A.use_partner[A.nuse] = ob; ++A.nuse;
+    Bo.use_prob[Bo.nuse] = q; Bo.use_side[Bo.nuse] = 1; Bo.use_partner[Bo.nuse] = oa; ++Bo.nuse;
+  }
 
   // ---- column split of the row-sum pass: pick the split with the best wave quantisation
   {

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
       a = warp_sum(a); b = warp_sum(b);
       if (lane == 0) { nrm[2 * t] = a; nrm[2 * t + 1] = b; }
       if (p.terms & FOCAL_TERM_NCE) {
-        const float fa = p.alpha / fmaxf(sqrtf(a), kNceEps), fb2 = p.alpha / fmaxf(sqrtf(b), kNceEps);
+        const float fa = p.alpha * fminf(rsqrtf(a), 1.f / kNceEps), fb2 = p.alpha * fminf(rsqrtf(b), 1.f / kNceEps);
         float zs[VW], zp[VW];
 #pragma unroll
         for (int e = 0; e < VW; ++e) { zs[e] = sh[e] * fa; zp[e] = pr[e] * fb2; }
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
           const OpDesc& a = p.ops[p.probs[q].opA];
           const OpDesc& b = p.ops[p.probs[q].opB];
           const int ha = a.col0 ? 1 : 0, hb = b.col0 ? 1 : 0;
-          const float fa = p.alpha / fmaxf(sqrtf(nrm[2 * a.tensor + ha]), kNceEps);
-          const float fb2 = p.alpha / fmaxf(sqrtf(nrm[2 * b.tensor + hb]), kNceEps);
+          const float fa = p.alpha * fminf(rsqrtf(nrm[2 * a.tensor + ha]), 1.f / kNceEps);
+          const float fb2 = p.alpha * fminf(rsqrtf(nrm[2 * b.tensor + hb]), 1.f / kNceEps);
           float xa[VW], xb[VW];
           ld_frag<VW>(xs + a.tensor * D + a.col0 + c0, xa);
           ld_frag<VW>(xs + b.tensor * D + b.col0 + c0, xb);
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
           dot = warp_sum(dot);
           const float nu = nrm[2 * od.tu + (od.cu ? 1 : 0)] + kOrthEps;
           const float nv = nrm[2 * od.tv + (od.cv ? 1 : 0)] + kOrthEps;
-          acc_orth += fmaxf(dot / sqrtf(nu * nv), 0.f);
+          acc_orth += fmaxf(dot * rsqrtf(nu * nv), 0.f);
         }
       }
     }
@@ -300,47 +300,43 @@ __global__ void __launch_bounds__(128) finalize_fast_kernel(const __grid_constan
     const float inv_alpha = 1.f / p.alpha;
     for (int o = 0; o < p.nOps; ++o) {
       const OpDesc& op = p.ops[o];
+      if (op.nuse == 0) continue;
       const int wp = op.kb * 64;
-      const int hk = op.col0 ? 1 : 0;
-      const float nk = fmaxf(sqrtf(nrm[2 * op.tensor + hk]), kNceEps);
-      const float fk = p.alpha / nk;
+      const float ssk = nrm[2 * op.tensor + (op.col0 ? 1 : 0)];
+      const float inv_nk = fminf(rsqrtf(ssk), 1.f / kNceEps);        // 1 / max(|z|, eps)
+      const float fk = p.alpha * inv_nk;
       float x[VW], tmp[VW];
       ld_frag<VW>(xs + op.tensor * D + op.col0 + c0, x);
 #pragma unroll
       for (int e = 0; e < VW; ++e) tmp[e] = 0.f;
-      bool used = false;
-      for (int q = 0; q < p.nProb; ++q) {
+      for (int u = 0; u < op.nuse; ++u) {
+        const int q = op.use_prob[u], side = op.use_side[u];
         const ProbDesc& pr = p.probs[q];
-        int side = -1;
-        if (pr.opA == o) side = 0; else if (pr.opB == o) side = 1;
-        if (side < 0) continue;
-        used = true;
-        const OpDesc& po = p.ops[side == 0 ? pr.opB : pr.opA];            // partner operand: positive row p(k)
-        const float fp = p.alpha / fmaxf(sqrtf(nrm[2 * po.tensor + (po.col0 ? 1 : 0)]), kNceEps);
+        const OpDesc& po = p.ops[op.use_partner[u]];                  // partner operand: positive row p(k)
+        const float fp = p.alpha * fminf(rsqrtf(nrm[2 * po.tensor + (po.col0 ? 1 : 0)]), 1.f / kNceEps);
         float px[VW], acc[VW];
         ld_frag<VW>(xs + po.tensor * D + po.col0 + c0, px);
         ld_frag<VW>(reinterpret_cast<const float*>(ws + pr.dz_off) + ((uint64_t)side * S * p.bpad + rowN) * wp + c0, acc);
+        const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
+        const float r_k = __ldg(rs + (uint64_t)side * p.bpad + I), r_p = __ldg(rs + (uint64_t)(1 - side) * p.bpad + I);
         // positive column in fp32 (masked out of the tiles): W_kp - 2 is a tiny difference when the positive dominates
         float gpos = 0.f;
 #pragma unroll
         for (int e = 0; e < VW; ++e) { px[e] = bf16_round(px[e] * fp); gpos = fmaf(bf16_round(x[e] * fk), px[e], gpos); }
         gpos = warp_sum(gpos);
-        const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
-        const float wkp = exp2f(gpos) * (1.f / __ldg(rs + (uint64_t)side * p.bpad + I) +
-                                         1.f / __ldg(rs + (uint64_t)(1 - side) * p.bpad + I));
+        const float wkp = ex2_approx(gpos) * (__frcp_rn(r_k) + __frcp_rn(r_p));
         const float wq = pr.weight * inv_tsn * inv_alpha;
 #pragma unroll
-        for (int e = 0; e < VW; ++e) tmp[e] = fmaf(wq, acc[e] + (wkp - 2.f) * px[e], tmp[e]);
+        for (int e = 0; e < VW; ++e) tmp[e] = fmaf(wq, fmaf(wkp - 2.f, px[e], acc[e]), tmp[e]);
       }
-      if (!used) continue;
       float dot = 0.f;                                // d zh / d z = (I - zh zh^T) / n
 #pragma unroll
       for (int e = 0; e < VW; ++e) dot = fmaf(tmp[e], x[e], dot);
-      dot = warp_sum(dot) / (nk * nk);
+      dot = warp_sum(dot) * inv_nk * inv_nk;
       float go[VW];
       ld_frag<VW>(gs + op.tensor * D + op.col0 + c0, go);
 #pragma unroll
-      for (int e = 0; e < VW; ++e) go[e] += (tmp[e] - dot * x[e]) / nk;
+      for (int e = 0; e < VW; ++e) go[e] = fmaf(fmaf(-dot, x[e], tmp[e]), inv_nk, go[e]);
       st_frag<VW>(gs + op.tensor * D + op.col0 + c0, go);
     }
   }
@@ -358,17 +354,18 @@ __global__ void __launch_bounds__(128) finalize_fast_kernel(const __grid_constan
       dot = warp_sum(dot);
       const float nu = nrm[2 * od.tu + (od.cu ? 1 : 0)] + kOrthEps;
       const float nv = nrm[2 * od.tv + (od.cv ? 1 : 0)] + kOrthEps;
-      const float den = sqrtf(nu * nv);
-      const float cs = dot / den;
+      const float inv_den = rsqrtf(nu * nv);
+      const float cs = dot * inv_den;
       if (cs >= 0.f) {                                    // clamp_min passes gradient at equality
         const float a = p.w_orth / (float)p.B;
+        const float ad = a * inv_den, au = -a * cs * __frcp_rn(nu), av = -a * cs * __frcp_rn(nv);
         float gu[VW], gv[VW];
         ld_frag<VW>(gs + od.tu * D + od.cu + c0, gu);
         ld_frag<VW>(gs + od.tv * D + od.cv + c0, gv);
 #pragma unroll
         for (int e = 0; e < VW; ++e) {
-          gu[e] += a * (v[e] / den - cs * u[e] / nu);
-          gv[e] += a * (u[e] / den - cs * v[e] / nv);
+          gu[e] = fmaf(ad, v[e], fmaf(au, u[e], gu[e]));
+          gv[e] = fmaf(ad, u[e], fmaf(av, v[e], gv[e]));
         }
         st_frag<VW>(gs + od.tu * D + od.cu + c0, gu);
         st_frag<VW>(gs + od.tv * D + od.cv + c0, gv);
