@@ -370,9 +370,22 @@ def run_ours(args):
             "loss": float(loss5[0].item()),
         }
         print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
+        # Tear down in a fixed order (graphs hold captured NCCL work) and never let a teardown problem turn into a hung
+        # job: a watchdog hard-exits the rank if the orderly shutdown has not finished after 30 s.
+        def _bail():
+            os._exit(0)
+        wd = threading.Timer(30.0, _bail)
+        wd.daemon = True
+        wd.start()
+        engine._graphs.clear()
+        if module._engine is not None:
+            module._engine._graphs.clear()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+        wd.cancel()
     return 0
 
 
