@@ -30,7 +30,8 @@ class FocalCfg(C.Structure):
         ("w_shared", C.c_float), ("w_private", C.c_float), ("w_orth", C.c_float), ("w_rank", C.c_float),
         ("no_private", C.c_int32), ("need_grad", C.c_int32), ("terms", C.c_int32), ("precision", C.c_int32),
         ("seq_begin", C.c_int32), ("seq_end", C.c_int32), ("num_sms", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("in_block_rows", C.c_int32), ("in_block_stride", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 

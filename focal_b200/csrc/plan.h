@@ -50,6 +50,7 @@ struct Plan {
   // dims
   int32_t B, S, M, D, d, b, bpad, Bpad, nT, nOps, nProb, nOrth, kbFull, seq0, seq1, need_grad, terms, num_sms;
   int32_t nsplit_fwd;                                   // column splits of the row-sum pass
+  int32_t in_rb, in_bs;                                 // row-blocked inputs: rows per block, block stride (floats)
   float T, margin, w_shared, w_private, w_orth, w_rank;
   float alpha;                                          // sqrt(log2(e)/T): operand pre-scale, Gram = log2-domain logit
   OpDesc ops[kMaxOps];
@@ -75,6 +76,11 @@ struct Plan {
 };
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+// element offset of row i inside a (possibly row-blocked) feature tensor
+__host__ __device__ inline size_t feat_row_off(const Plan& p, int i) {
+  return (size_t)(i / p.in_rb) * (size_t)p.in_bs + (size_t)(i % p.in_rb) * (size_t)p.D;
+}
 
 // rows of the prologue / finalize kernels handled per 128-thread block (one warp per row)
 constexpr int kRowsPerBlock = 4;
@@ -106,6 +112,9 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.seq0 = c.seq_begin; p.seq1 = c.seq_end;
   if (p.seq0 < 0 || p.seq1 > p.b || p.seq0 >= p.seq1) return FOCAL_EINVAL;
   p.need_grad = c.need_grad; p.terms = c.terms ? c.terms : FOCAL_TERM_ALL;
+  p.in_rb = c.in_block_rows > 0 ? c.in_block_rows : c.B;
+  p.in_bs = c.in_block_rows > 0 ? c.in_block_stride : 0;
+  if (p.in_rb % c.S || c.B % p.in_rb) return FOCAL_EINVAL;
   p.num_sms = num_sms;
   p.T = c.temperature; p.margin = c.margin;
   p.w_shared = c.w_shared; p.w_private = c.w_private; p.w_orth = c.w_orth; p.w_rank = c.w_rank;

@@ -22,13 +22,13 @@ __device__ __forceinline__ void load_rows(const Plan& p, const FeatPtrs& f, int 
   if ((D & 3) == 0) {
     const int nv = D >> 2;
     for (int t = 0; t < p.nT; ++t) {
-      const float4* src = reinterpret_cast<const float4*>(f.x[t] + (size_t)i * D);
+      const float4* src = reinterpret_cast<const float4*>(f.x[t] + feat_row_off(p, i));
       float4* dst = reinterpret_cast<float4*>(xs + t * D);
       for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
     }
   } else {
     for (int t = 0; t < p.nT; ++t)
-      for (int c = lane; c < D; c += 32) xs[t * D + c] = __ldg(f.x[t] + (size_t)i * D + c);
+      for (int c = lane; c < D; c += 32) xs[t * D + c] = __ldg(f.x[t] + feat_row_off(p, i) + c);
   }
   __syncwarp();
 }
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan
   if (w >= (long)p.nT * p.b) return;
   const int t = (int)(w / p.b), I = (int)(w % p.b);
   const int S = p.S, D = p.D;
-  const float* x = f.x[t] + (size_t)I * S * D;
+  const float* x = f.x[t] + feat_row_off(p, I * S);
   float tot = 0.f;
   for (int a = 0; a < S; ++a)
     for (int b2 = a + 1; b2 < S; ++b2) {
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
       // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
       const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
       if (cnt > 0) {
-        const float* base = f.x[t] + (size_t)I * S * D;
+        const float* base = f.x[t] + feat_row_off(p, I * S);
         for (int j = 0; j < S; ++j) {
           if (j == s) continue;
           float d2 = 0.f;

@@ -62,7 +62,7 @@ __device__ __forceinline__ void st_operand(uint8_t* op_base, uint64_t kstride_ro
 __device__ __forceinline__ void stage_rows(const Plan& p, const FeatPtrs& f, int i, float* xs, int lane) {
   const int nv = p.D >> 2;                       // D % 4 == 0 on this path
   for (int t = 0; t < p.nT; ++t) {
-    const float4* src = reinterpret_cast<const float4*>(f.x[t] + (size_t)i * p.D);
+    const float4* src = reinterpret_cast<const float4*>(f.x[t] + feat_row_off(p, i));
     float4* dst = reinterpret_cast<float4*>(xs + t * p.D);
     for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
   }

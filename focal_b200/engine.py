@@ -85,17 +85,25 @@ class CudaBackend:
         return ws[off: off + nbytes].view(dtype).view(*shape)
 
     # -- the whole path -----------------------------------------------------------------------------
+    supports_blocked = True
+
     def run(self, hp: FocalHyper, feats: Sequence[torch.Tensor], seq: Tuple[int, int], need_grad: bool,
-            exchange_rowsum=None):
-        """feats: 2M full [B, D] fp32 CUDA tensors (view-major).  Returns (loss5 [5] fp32 device tensor with the
-        partial sums of the owned rows, grads: list of 2M [B, D] tensors with the owned rows filled, or None)."""
+            exchange_rowsum=None, blocked: Optional[Tuple[int, int, int]] = None):
+        """feats: 2M fp32 CUDA tensors (view-major).  Plain mode: each is the full [B, D] tensor.  Blocked mode
+        (``blocked = (B, rows_per_block, block_stride_in_floats)``): each is the first row block of a row-blocked
+        tensor (the layout an all-gather of per-rank [2M, B/R, D] buffers produces).
+        Returns (loss5 [5] fp32 device tensor with the partial sums of the owned rows, grads: list of 2M tensors
+        holding d loss / d (owned rows) -- [rows_owned, D] -- or None)."""
         x0 = feats[0]
-        B, D = x0.shape
+        D = x0.shape[1]
+        B = blocked[0] if blocked is not None else x0.shape[0]
         dev = x0.device
-        key = (hp, B, D, need_grad, seq, dev.index)
+        key = (hp, B, D, need_grad, seq, dev.index, blocked)
         hit = self._plans.get(key)
         if hit is None:
             cfg = self._cfg(hp, B, D, need_grad, seq)
+            if blocked is not None:
+                cfg.in_block_rows, cfg.in_block_stride = blocked[1], blocked[2]
             ws, info = self.workspace(cfg, dev)
             hit = (cfg, ws, info, C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()))
             self._plans[key] = hit
@@ -103,8 +111,13 @@ class CudaBackend:
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         fptr = _cabi.ptr_array([t.data_ptr() for t in feats])
         loss5 = torch.empty(5, dtype=torch.float32, device=dev)
-        grads = [torch.empty_like(t) for t in feats] if need_grad else None
-        gptr = _cabi.ptr_array([g.data_ptr() for g in grads]) if need_grad else None
+        rows0, rows1 = seq[0] * hp.seq_len, seq[1] * hp.seq_len
+        grads = gptr = None
+        if need_grad:
+            # only the owned rows are written: hand the kernels a base pointer such that global row i lands at local
+            # row i - rows0 of a [rows_owned, D] tensor
+            grads = [torch.empty((rows1 - rows0, D), dtype=torch.float32, device=dev) for _ in feats]
+            gptr = _cabi.ptr_array([g.data_ptr() - rows0 * D * 4 for g in grads])
         lib, ref = self.lib, C.byref(cfg)
         if exchange_rowsum is None:
             _cabi.check(lib.focal_b200_loss(ref, fptr, wsp, wsn, C.c_void_p(loss5.data_ptr()), gptr, stream),
@@ -215,32 +228,32 @@ class FocalEngine:
         import torch.distributed as dist
         Bl, D = local[0].shape
         nT = len(local)
-        # (1) all-gather the raw features: [R, 2M, Bl, D] -> per tensor [R*Bl, D] rank-major
+        # (1) all-gather the raw features: per-rank [2M, Bl, D] -> [R, 2M, Bl, D]
         mine = torch.stack(local, dim=0)
-        gathered = torch.empty((world * mine.shape[0],) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        gathered = torch.empty((world * nT, Bl, D), dtype=mine.dtype, device=mine.device)
         dist.all_gather_into_tensor(gathered, mine, group=self.group)       # concatenated along dim 0, rank-major
-        gathered = gathered.view((world,) + tuple(mine.shape))
-        full = [gathered[:, t].reshape(world * Bl, D) for t in range(nT)]
         b = world * Bl // hp.seq_len
         seq = shard_sequences(b, world, rank)
+        per = seq[1] - seq[0]
 
         def exchange_rowsum(rs: torch.Tensor):
-            # rs: [P, S, 2, bpad]; every rank computed the k-range [seq0, seq1) -- all-gather the slices
-            k0, k1 = seq
-            part = rs[..., k0:k1].contiguous()
+            # rs: [P, S, 2, bpad]; every rank computed the k-range [seq0, seq1): all-gather the slices, one permuted copy back
+            part = rs[..., seq[0]:seq[1]].contiguous()
             allp = torch.empty((world * part.shape[0],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
             dist.all_gather_into_tensor(allp, part, group=self.group)
-            allp = allp.view((world,) + tuple(part.shape))
-            per = k1 - k0
-            for r in range(world):
-                if r != rank:
-                    rs[..., r * per:(r + 1) * per] = allp[r]
+            P_, S_ = part.shape[0], part.shape[1]
+            rs[..., :b].view(P_, S_, 2, world, per).copy_(allp.view(world, P_, S_, 2, per).permute(1, 2, 3, 0, 4))
 
-        loss5, gfull = self.backend.run(hp, full, seq, need_grad, exchange_rowsum)
+        if getattr(self.backend, "supports_blocked", False):
+            # kernels read the gathered buffer in place: row i of tensor t sits in block i // Bl
+            heads = [gathered[t] for t in range(nT)]
+            loss5, grads = self.backend.run(hp, heads, seq, need_grad, exchange_rowsum,
+                                            blocked=(world * Bl, Bl, nT * Bl * D))
+        else:
+            full = [gathered.view(world, nT, Bl, D)[:, t].reshape(world * Bl, D) for t in range(nT)]
+            loss5, gfull = self.backend.run(hp, full, seq, need_grad, exchange_rowsum)
+            r0 = seq[0] * hp.seq_len
+            grads = [g[r0: r0 + Bl] if g.shape[0] != Bl else g for g in gfull] if need_grad else None
         # (3) loss partials of the owned rows -> global loss on every rank
         dist.all_reduce(loss5, op=dist.ReduceOp.SUM, group=self.group)
-        grads = None
-        if need_grad:
-            r0 = seq[0] * hp.seq_len
-            grads = [g[r0: r0 + Bl] for g in gfull]
         return loss5, grads

@@ -55,7 +55,12 @@ typedef struct FocalCfg {
   int32_t precision;     /* FOCAL_PREC_* */
   int32_t seq_begin, seq_end;
   int32_t num_sms;       /* 0 = query the current device */
-  int32_t reserved[3];
+  /* Row-blocked inputs (what an all-gather of per-rank [2M][B/R][D] buffers produces): row i of feature tensor t
+   * lives at feats[t] + (i / in_block_rows) * in_block_stride + (i % in_block_rows) * D (in floats).
+   * in_block_rows == 0 means plain contiguous [B, D] tensors.  Sequences never straddle blocks. */
+  int32_t in_block_rows;
+  int32_t in_block_stride;
+  int32_t reserved[1];
 } FocalCfg;
 
 /* Byte offsets (from the workspace base) and extents of the buffers a host may need to look at:
@@ -118,6 +123,13 @@ int focal_b200_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img
                           uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep_bytes, uint32_t b_lbo, uint32_t b_sbo,
                           uint32_t b_kstep_bytes, uint32_t ksteps, uint32_t ncols, uint32_t a_via_st, float* d_out,
                           void* stream);
+
+/* Bring-up micro-benchmarks (tools/umma_rate.py, tools/tma_rate.py): cycles per tcgen05.mma for a given N / operand
+ * placement / per-tile barrier traffic, and per-SM throughput of linear TMA bulk copies. */
+int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t iters, uint32_t sync_mode, uint32_t grid,
+                               long long* cycles, void* stream);
+int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, uint32_t copy_bytes, uint32_t copies_per_stage,
+                              uint32_t stages, uint32_t iters, uint32_t grid, long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }

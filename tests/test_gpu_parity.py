@@ -294,7 +294,8 @@ def test_row_shards_on_one_gpu_sum_to_global():
         acc5 += l5
         for t in range(len(feats)):
             rows = slice(lo * S, hi * S)
-            assert rel_err(g[t][rows], fullg[t][rows]) < 1e-5
+            assert g[t].shape == ((hi - lo) * S, D)            # only the owned rows are returned
+            assert rel_err(g[t], fullg[t][rows]) < 1e-5
     assert torch.allclose(acc5, full5, rtol=1e-5)
 
 
@@ -326,3 +327,25 @@ def test_cuda_graph_replay_matches_eager():
     l_e, g_e = eager.loss_and_grads(x1, x2, True)
     torch.cuda.synchronize()
     assert torch.equal(l5, l_e) and all(torch.equal(a, b2) for a, b2 in zip(g, g_e))
+
+
+def test_row_blocked_inputs_match_contiguous():
+    """The layout an all-gather of per-rank [2M, B/R, D] buffers produces is read in place (no re-pack copy)."""
+    _require_cuda()
+    from focal_b200.engine import CudaBackend, FocalHyper
+    mods = ["seismic", "audio"]
+    B, D, S, R = 1024, 128, 4, 4
+    f1, f2 = fo.make_structured(6, mods, B, D, S)
+    hp = FocalHyper(tuple(mods), S, 0.5, 1.0, 1.0, 1.0, 3.0, 5.0)
+    be = CudaBackend()
+    feats = [f1[m].cuda() for m in mods] + [f2[m].cuda() for m in mods]
+    nT, Bl = len(feats), B // R
+    l_ref, g_ref = be.run(hp, feats, (0, B // S), True, None)
+    l_ref, g_ref = l_ref.clone(), [g.clone() for g in g_ref]
+    blocked = torch.stack([torch.stack([f[r * Bl:(r + 1) * Bl] for f in feats]) for r in range(R)])   # [R, 2M, Bl, D]
+    heads = [blocked[0, t] for t in range(nT)]
+    l5, g = be.run(hp, heads, (0, B // S), True, None, blocked=(B, Bl, nT * Bl * D))
+    torch.cuda.synchronize()
+    assert torch.equal(l5, l_ref)
+    for a, b2 in zip(g, g_ref):
+        assert torch.equal(a, b2)
