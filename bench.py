@@ -29,14 +29,26 @@ sys.path.insert(0, ROOT)
 
 METRIC = "FOCAL loss fwd+bwd samples/s @B=8192"
 UNIT = "samples/s"
-WORKLOAD = dict(B=8192, S=4, M=2, D=256, T=0.5, margin=1.0, weights=(1.0, 1.0, 3.0, 5.0),
-                mods=("seismic", "audio"))
+WORKLOADS = {
+    # BASELINE.json metric configuration (configs[1] dims at the headline batch): the default and the only bench line
+    "headline": dict(B=8192, S=4, M=2, D=256, T=0.5, mods=("seismic", "audio"), terms=7),
+    # the other BASELINE.json configs, for profiles/ (python bench.py --workload cfg3 ...)
+    "cfg2": dict(B=1024, S=4, M=2, D=256, T=0.5, mods=("seismic", "audio"), terms=7),
+    "cfg3": dict(B=4096, S=4, M=3, D=256, T=0.07, mods=("acc", "gyr", "mag"), terms=7),
+    "cfg4": dict(B=65536, S=1, M=2, D=128, T=0.5, mods=("seismic", "audio"), terms=1),      # global InfoNCE only
+    "cfg5": dict(B=16384, S=4, M=4, D=256, T=0.5, mods=("m0", "m1", "m2", "m3"), terms=7),
+}
+for _w in WORKLOADS.values():
+    _w.update(margin=1.0, weights=(1.0, 1.0, 3.0, 5.0))
+WORKLOAD = WORKLOADS["headline"]
 L2_BYTES = 126 * 2 ** 20
 
 
-def f_alg(B, M, D, S):
-    """Algorithmic FLOPs of one step, SURVEY.md §8d: 12 B^2 D (M^2/S + M)."""
-    return 12.0 * B * B * D * (M * M / S + M)
+def f_alg(B, M, D, S, terms=7):
+    """Algorithmic FLOPs of one step, SURVEY.md §8d: 12 B^2 D (M^2/S + M)  (InfoNCE part + temporal part)."""
+    nce = 12.0 * M * M * B * B * D / S if terms & 1 else 0.0
+    tmp = 12.0 * M * B * B * D if terms & 4 else 0.0
+    return nce + tmp
 
 
 def measured_peaks():
@@ -244,7 +256,7 @@ def run_ours(args):
     if B % (S * world):
         raise SystemExit("global batch does not shard over the ranks")
     Bl = B // world
-    hp = FocalHyper(tuple(mods), S, w["T"], w["margin"], *w["weights"])
+    hp = FocalHyper(tuple(mods), S, w["T"], w["margin"], *w["weights"], False, w["terms"])
     engine = FocalEngine(hp, process_group=group)
 
     # synthetic inputs: NSETS different batches so that consecutive steps read their inputs from HBM, not L2
@@ -300,6 +312,8 @@ def run_ours(args):
     # ---- end-to-end: pinned host inputs -> H2D -> loss + grads -> D2H of the loss, through the module API
     args_ns = make_args(mods, S, w, group)
     module = focal_b200.FOCALLoss(args_ns).to(dev)
+    if w["terms"] != 7:
+        module._engine = FocalEngine(hp, process_group=group)      # sub-set of the terms (cfg4: InfoNCE only)
     stage = [torch.empty(Bl, D, device=dev) for _ in range(2 * M)]
 
     def e2e_step(k):
@@ -333,16 +347,25 @@ def run_ours(args):
     out = None
     if rank == 0:
         peaks = measured_peaks()
-        F = f_alg(B, M, D, S)
+        F = f_alg(B, M, D, S, w["terms"])
         roof = None
         if stages is not None:
-            # dominant kernel: the fused temporal distance/ranking pass (2M calls, fwd+bwd in one launch)
-            F_tmp = 12.0 * M * B * B * D
-            t_tmp = stages["temporal"] * 1e-3
-            roof = {"bound": "tensor", "kernel": "gram_kernel<TMP_BWD> (temporal ranking fwd+bwd, fused)",
-                    "achieved": F_tmp / t_tmp / 1e12, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": F_tmp / t_tmp / 1e12 / peaks["tflops"], "peak_source": peaks["source"] + " (sustained bf16)",
-                    "traffic": None, "alg_flops_per_launch": F_tmp, "launch_ms": stages["temporal"]}
+            # dominant launch: the fused temporal distance/ranking pass (2M calls, fwd+bwd in one launch); for the
+            # InfoNCE-only workload the backward Gram pass (2 of the 3 GEMM-equivalents of the InfoNCE term)
+            if w["terms"] & 4:
+                kname, F_k, t_k = "gram_kernel<TMP_BWD> (temporal ranking fwd+bwd, fused)", 12.0 * M * B * B * D, stages["temporal"]
+            else:
+                kname, F_k, t_k = "gram_kernel<NCE_BWD> (InfoNCE backward)", 8.0 * M * M * B * B * D / S, stages["nce_grad"]
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if args.workload == "headline" and os.path.exists(tpath):
+                with open(tpath) as fh:
+                    traffic = json.load(fh).get("gram_kernel_tmp_bwd_dram_bytes_per_launch")
+            t_s = max(t_k, 1e-6) * 1e-3
+            roof = {"bound": "tensor", "kernel": kname, "achieved": F_k / t_s / 1e12, "peak": peaks["tflops"],
+                    "unit": "TFLOP/s", "frac": F_k / t_s / 1e12 / peaks["tflops"],
+                    "peak_source": peaks["source"] + " (sustained bf16)", "traffic": traffic,
+                    "alg_flops_per_launch": F_k, "launch_ms": t_k}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -453,7 +476,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="headline",
+                    help="other BASELINE.json configurations (for profiles/); the bench line is the default")
     args = ap.parse_args()
+    global WORKLOAD, METRIC
+    WORKLOAD = WORKLOADS[args.workload]
+    if args.workload != "headline":
+        METRIC = f"FOCAL loss fwd+bwd samples/s @B={WORKLOAD['B']} ({args.workload})"
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
