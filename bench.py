@@ -314,23 +314,41 @@ def run_ours(args):
     module = focal_b200.FOCALLoss(args_ns).to(dev)
     if w["terms"] != 7:
         module._engine = FocalEngine(hp, process_group=group)      # sub-set of the terms (cfg4: InfoNCE only)
-    stage = [torch.empty(Bl, D, device=dev) for _ in range(2 * M)]
+    # Two device staging sets (ping-pong) fed from pinned host memory on a copy stream: the H2D copy of step k+1 overlaps the
+    # kernels of step k, like a pinned-memory data loader with non_blocking copies.  Every step still copies its own
+    # inputs host->device and reads its loss back to the host (a host sync per step, like pretrain.py:74).
+    stages_dev = [[torch.empty(Bl, D, device=dev) for _ in range(2 * M)] for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(k):
+        slot = k % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])            # the step that last used this slot has finished with it
+            for dst, src in zip(stages_dev[slot], host_sets[k % nsets]):
+                dst.copy_(src, non_blocking=True)
+            copied[slot].record(copy_stream)
 
     def e2e_step(k):
-        hs = host_sets[k % nsets]
-        for dst, src in zip(stage, hs):
-            dst.copy_(src, non_blocking=True)
-        xs = [t.requires_grad_(True) for t in (s_.detach() for s_ in stage)]
+        slot = k % 2
+        prefetch(k + 1)                                       # next step's inputs travel while this step computes
+        torch.cuda.current_stream().wait_event(copied[slot])
+        xs = [s_.detach().requires_grad_(True) for s_ in stages_dev[slot]]
         f1, f2 = as_dicts(xs)
         loss = module(f1, f2)
         loss.backward()
+        consumed[slot].record()
         return float(loss.detach().cpu())          # D2H read of the step's result (host sync, like pretrain.py:74)
 
+    for ev in consumed:
+        ev.record()
+    prefetch(0)
     for k in range(3 * nsets):
         e2e_step(k)
     sync_all()
     ev0.record()
-    for k in range(args.steps):
+    for k in range(3 * nsets, 3 * nsets + args.steps):
         e2e_step(k)
     ev1.record()
     sync_all()
