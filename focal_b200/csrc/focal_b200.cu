@@ -104,7 +104,7 @@ int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st) {
     for (int q = 0; q < p.nProb; ++q)
       if (p.ops[p.probs[q].opA].kb == kb) sel.idx[sel.n++] = q;
     if (!sel.n) continue;
-    const int items = sel.n * p.S * 2 * (t1 - t0) * (MODE == NCE_FWD ? p.nsplit_fwd : 1);
+    const int items = sel.n * p.S * 2 * (t1 - t0);
     const int rc = launch_gram_kb<MODE, 0>(p, sel, ws, st, kb, items);
     if (rc) return rc;
   }

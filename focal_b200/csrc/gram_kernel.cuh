@@ -112,8 +112,7 @@ template <int MODE>
 __device__ __forceinline__ int gram_num_items(const Plan& p, const ProbSel& sel) {
   if (MODE == NCE_FWD || MODE == NCE_BWD) {
     const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM;
-    const int nsp = (MODE == NCE_FWD) ? p.nsplit_fwd : 1;
-    return sel.n * p.S * 2 * (t1 - t0) * nsp;
+    return sel.n * p.S * 2 * (t1 - t0);
   } else {
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
     return p.nT * (t1 - t0);
@@ -124,9 +123,7 @@ template <int MODE, int BN>
 __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, const uint8_t* ws, int it, Item& x) {
   if (MODE == NCE_FWD || MODE == NCE_BWD) {
     const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM, nrt = t1 - t0;
-    const int nsp = (MODE == NCE_FWD) ? p.nsplit_fwd : 1;
     int r = it;
-    const int sp = r % nsp; r /= nsp;
     const int rt = t0 + r % nrt; r /= nrt;
     const int side = r % 2; r /= 2;
     const int s = r % p.S; r /= p.S;
@@ -139,12 +136,11 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
     const float* rinv = reinterpret_cast<const float*>(ws + p.rinv_off) + ((uint64_t)(q * p.S + s) * 2) * p.bpad;
     x.cv0_0 = rinv; x.cv0_1 = rinv + p.bpad; x.cv1 = rinv;
     x.ntc = (p.b + BN - 1) / BN;
-    const int nct = 2 * x.ntc;
-    x.ct_begin = (int)((long)nct * sp / nsp);
-    x.ct_end = (int)((long)nct * (sp + 1) / nsp);
+    x.ct_begin = 0;
+    x.ct_end = 2 * x.ntc;
     x.row0 = rt * kTileM; x.side = side; x.ncol_valid = p.b;
     x.row_lo = p.seq0; x.row_hi = p.seq1;
-    x.q = q; x.s = s; x.c = sp;
+    x.q = q; x.s = s; x.c = 0;
   } else {
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM, nrt = t1 - t0;
     const int rt = t0 + it % nrt;
@@ -160,6 +156,36 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
     x.row_lo = p.seq0 * p.S; x.row_hi = p.seq1 * p.S;
     x.q = 0; x.s = 0; x.c = c;
   }
+}
+
+// Stream-K work split: the (row block, column tile) pairs of a launch are numbered consecutively and every CTA takes an
+// equal contiguous share, so a row block may be cut into a primary piece (starts at tile 0) and a secondary piece
+// (the rest, handled by the next CTA) -- never more, because a share is at least one whole row block long.  All SMs
+// stay busy until the end of the launch (with whole row blocks 256 equal items on 148 SMs ran 2 rounds for 1.73
+// rounds of work).  Secondary pieces write to their own accumulators (dz2 / dx2 / ...), so the result is deterministic.
+struct PieceIter {
+  long u, u1;
+  int T;
+  __device__ __forceinline__ PieceIter(int n_items, int tiles_per_item) {
+    T = tiles_per_item;
+    const long total = (long)n_items * T;
+    const long share = (total + gridDim.x - 1) / gridDim.x;
+    u = (long)blockIdx.x * share;
+    u1 = u + share < total ? u + share : total;
+  }
+  __device__ __forceinline__ bool next(int& item, int& t0, int& t1) {
+    if (u >= u1) return false;
+    item = (int)(u / T);
+    t0 = (int)(u - (long)item * T);
+    const long rest = u1 - u;
+    t1 = (long)(T - t0) <= rest ? T : (int)(t0 + rest);
+    u += t1 - t0;
+    return true;
+  }
+};
+template <int MODE, int BN>
+__device__ __forceinline__ int gram_tiles_per_item(const Plan& p) {
+  return (MODE == NCE_FWD || MODE == NCE_BWD) ? 2 * ((p.b + BN - 1) / BN) : (p.B + BN - 1) / BN;
 }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -236,9 +262,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     // =============================== TMA producer ===============================
     {
       uint32_t nb = 0, ni = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p));
+      for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
+        x.ct_begin = pt0; x.ct_end = pt1;
         mbar_wait_warp(&bars->a_empty, (ni & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bars->a_full, L::kABytes);
@@ -277,9 +305,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
       const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
       uint32_t nb = 0, ni = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p));
+      for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
+        x.ct_begin = pt0; x.ct_end = pt1;
         mbar_wait_warp(&bars->a_full, ni & 1);
         const int ntiles = x.ct_end - x.ct_begin;
         if (!kBwd) {
@@ -374,9 +404,13 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     const uint32_t cv_base = smem_u32(smem + L::kBOff + L::kBTile);
     const uint32_t s_addr = tmem + tlane + kSCol + wg * BN;
     uint32_t nb = 0, ni = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++ni) {
+    PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p));
+    for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
       Item x;
       gram_decode<MODE, BN>(p, sel, ws, it, x);
+      x.ct_begin = pt0; x.ct_end = pt1;
+      const bool second = pt0 > 0;                    // secondary piece of a split row block
+      const bool split = !second && pt1 < pieces.T;   // primary piece of a split row block
       const int row0 = x.row0, ncol_valid = x.ncol_valid, side = x.side, ntc = x.ntc, ct_begin = x.ct_begin;
       const int row = row0 + trow;                    // row within side (NCE: sequence index k) / tensor (TMP: i)
       const bool row_ok = row < ncol_valid && row >= x.row_lo && row < x.row_hi;
@@ -518,15 +552,17 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
           for (int w = 0; w < NS - 1; ++w) rowacc += bars->part_acc[w][trow];
           if (MODE == NCE_FWD) {
-            float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) +
-                           ((((uint64_t)x.c * p.nProb + x.q) * p.S + x.s) * 2 + side) * p.bpad;
-            rpart[row] = row_ok ? rowacc : 0.f;
+            const uint64_t slot_stride = (uint64_t)p.nProb * p.S * 2 * p.bpad;
+            float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) + (((uint64_t)x.q * p.S + x.s) * 2 + side) * p.bpad;
+            rpart[(second ? slot_stride : 0) + row] = row_ok ? rowacc : 0.f;
+            if (!second && !split) rpart[slot_stride + row] = 0.f;           // no secondary piece: its slot reads as 0
           } else {
 #pragma unroll
             for (int w = 0; w < NS - 1; ++w) { hinge_acc += bars->part_hinge[w][trow]; cnt_i += bars->part_cnt[w][trow]; }
-            if (kBwd && row_ok) reinterpret_cast<float*>(ws + p.rho_off)[(uint64_t)x.c * p.Bpad + row] = rowacc;
+            if (kBwd && row_ok)
+              reinterpret_cast<float*>(ws + p.rho_off + (second ? p.rho2_delta : 0))[(uint64_t)x.c * p.Bpad + row] = rowacc;
             if (row_ok && (lane & (SQ - 1)) == 0)
-              reinterpret_cast<int32_t*>(ws + p.cnt_off)[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
+              reinterpret_cast<int32_t*>(ws + p.cnt_off + (second ? p.cnt2_delta : 0))[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
             // every lane of a sequence accumulated the same hinge values: count each (I, J) once
             const float hs = warp_sum(((lane & (SQ - 1)) == 0) ? hinge_acc : 0.f);
             if (lane == 0) bars->red[quarter] = hs;
@@ -538,10 +574,15 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         tc_fence_after();
         float* out;
         if (kIsNce) {
-          out = reinterpret_cast<float*>(ws + p.probs[x.q].dz_off) +
+          out = reinterpret_cast<float*>(ws + p.probs[x.q].dz_off + (second ? p.dz2_delta : 0)) +
                 ((uint64_t)side * p.S * p.bpad + (uint64_t)x.s * p.bpad + row) * kON;
+          if (!second && trow == 0)
+            reinterpret_cast<int32_t*>(ws + p.flag_nce_off)[(((uint64_t)x.q * p.S + x.s) * 2 + side) * (p.bpad / kTileM) +
+                                                            row0 / kTileM] = split ? 1 : 0;
         } else {
-          out = reinterpret_cast<float*>(ws + p.dx_off) + ((uint64_t)x.c * p.Bpad + row) * kON;
+          out = reinterpret_cast<float*>(ws + p.dx_off + (second ? p.dx2_delta : 0)) + ((uint64_t)x.c * p.Bpad + row) * kON;
+          if (!second && trow == 0)
+            reinterpret_cast<int32_t*>(ws + p.flag_tmp_off)[(uint64_t)x.c * (p.Bpad / kTileM) + row0 / kTileM] = split ? 1 : 0;
         }
 #pragma unroll 1
         for (int ch = wg; ch < kON / 32; ch += NS) {     // the warpgroups split the columns of O
@@ -562,9 +603,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         if (!kIsNce && wg == 0 && trow == 0) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
-          const int slot = x.c * nrt + (row0 / kTileM - t0);
-          reinterpret_cast<float*>(ws + p.part3_off)[slot] =
+          const int slot = 2 * (x.c * nrt + (row0 / kTileM - t0));
+          float* p3 = reinterpret_cast<float*>(ws + p.part3_off);
+          p3[slot + (second ? 1 : 0)] =
               ((bars->red[0] + bars->red[1]) + (bars->red[2] + bars->red[3])) / ((float)p.b * (float)(p.b - 1));
+          if (!second && !split) p3[slot + 1] = 0.f;
         }
       }
     }

@@ -71,6 +71,10 @@ struct Plan {
   uint64_t part3_off;   // fp32 [nitems3]   hinge partials
   uint64_t lossd_off;   // double [8]
   uint64_t dz_off, dz_bytes, dx_bytes;
+  // stream-K: a 128-row block whose column tiles are split over two CTAs has a second set of accumulators
+  uint64_t dz2_delta, dx2_delta, rho2_delta, cnt2_delta;   // byte distance from the primary to the secondary buffer
+  uint64_t flag_tmp_off;   // int32 [2M][Bpad/128]: 1 if the row block has a secondary piece (temporal)
+  uint64_t flag_nce_off;   // int32 [nProb][S][2][bpad/128]: same for the InfoNCE backward pass
   uint64_t total_bytes;
   int32_t nblk1, nblk2, nitems3;
 };
@@ -166,22 +170,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     Bo.use_prob[Bo.nuse] = q; Bo.use_side[Bo.nuse] = 1; Bo.use_partner[Bo.nuse] = oa; ++Bo.nuse;
   }
 
-  // ---- column split of the row-sum pass: pick the split with the best wave quantisation
-  {
-    const int nt = (p.b + kTileM - 1) / kTileM;
-    const long items = (long)p.nProb * p.S * 2 * nt;   // upper bound (all row tiles)
-    int best = 1; double best_eff = 0;
-    for (int sp = 1; sp <= 4; ++sp) {
-      long it = items * sp;
-      long waves = (it + num_sms - 1) / num_sms;
-      double eff = (double)it / (double)(waves * num_sms);
-      if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
-    }
-    p.nsplit_fwd = best;
-#ifdef FB_NSPLIT_FWD
-    p.nsplit_fwd = FB_NSPLIT_FWD;
-#endif
-  }
+  p.nsplit_fwd = 2;      // row-sum slots per row: primary / secondary stream-K piece
 
   // ---- workspace
   uint64_t off = 0;
@@ -199,13 +188,20 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   for (int q = 0; q < p.nProb; ++q)
     p.probs[q].dz_off = take((uint64_t)2 * rowsNce * p.ops[p.probs[q].opA].kb * kKBlk * 4);
   p.dz_bytes = off - p.dz_off;
+  p.dz2_delta = p.dz_bytes;
+  take(p.dz_bytes);                                                  // secondary dz accumulators
   p.dx_bytes = (uint64_t)p.nT * p.Bpad * p.kbFull * kKBlk * 4;
   p.dx_off = take(p.dx_bytes);
+  p.dx2_delta = take(p.dx_bytes) - p.dx_off;
   p.rho_off = take((uint64_t)p.nT * p.Bpad * 4);
+  p.rho2_delta = take((uint64_t)p.nT * p.Bpad * 4) - p.rho_off;
   p.cnt_off = take((uint64_t)p.nT * p.bpad * 4);
+  p.cnt2_delta = take((uint64_t)p.nT * p.bpad * 4) - p.cnt_off;
+  p.flag_tmp_off = take((uint64_t)p.nT * (p.Bpad / kTileM) * 4);
+  p.flag_nce_off = take((uint64_t)p.nProb * p.S * 2 * (p.bpad / kTileM) * 4);
   p.nblk1 = (p.B + kRowsPerBlock - 1) / kRowsPerBlock;
   p.nblk2 = (int32_t)((rowsNce * 2 * p.nProb + 255) / 256);
-  p.nitems3 = p.nT * (p.Bpad / kTileM);
+  p.nitems3 = 2 * p.nT * (p.Bpad / kTileM);          // two hinge-partial slots (primary / secondary piece) per row block
   p.part1_off = take((uint64_t)p.nblk1 * 4 * 4);
   p.part2_off = take((uint64_t)p.nblk2 * 2 * 4);
   p.part3_off = take((uint64_t)p.nitems3 * 4);
