@@ -42,6 +42,9 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_KB4_NB
 #define FB_KB4_NB 3
 #endif
+#ifndef FB_KB4_NW
+#define FB_KB4_NW 2             // epilogue warpgroups sharing one S stage (they split its 16-column chunks)
+#endif
 #ifndef FB_POLY_PER8
 #define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
 #endif
@@ -55,8 +58,11 @@ struct GramCfg {
   static constexpr int BN = KB <= 2 ? 128 : (KB == 4 ? FB_KB4_BN : 64);          // column tile
   static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : 4);  // S stages == epilogue warpgroups
   static constexpr int NB = KB <= 3 ? 5 : FB_KB4_NB;                             // B-tile ring stages (smem budget)
-  static constexpr int CW = (NS == 4 && kTmp && SEQ <= 16) ? 16 : 32; // columns per tcgen05.ld (register budget)
-  static constexpr int kThreads = 64 + 128 * NS;
+  static constexpr int NW = (KB == 4 && SEQ <= 16) ? FB_KB4_NW : 1;              // warpgroups per S stage
+  static constexpr int NG = NS * NW;                                             // epilogue warpgroups in total
+  static constexpr int CW = (NG == 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
+  static constexpr int kThreads = 64 + 128 * NG;
+  static_assert(NG <= 4, "partial-sum arrays and register budget are sized for <= 4 epilogue warpgroups");
   static_assert((kBwd ? KB * 64 : 0) + NS * BN <= kTmemCols, "TMEM budget");
 };
 
@@ -163,17 +169,33 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
 // (the rest, handled by the next CTA) -- never more, because a share is at least one whole row block long.  All SMs
 // stay busy until the end of the launch (with whole row blocks 256 equal items on 148 SMs ran 2 rounds for 1.73
 // rounds of work).  Secondary pieces write to their own accumulators (dz2 / dx2 / ...), so the result is deterministic.
+#ifndef FB_STREAMK_TMP
+#define FB_STREAMK_TMP 0        // temporal kernel: whole row blocks per CTA measured faster than stream-K pieces (B200)
+#endif
+#ifndef FB_STREAMK_NCE
+#define FB_STREAMK_NCE 1
+#endif
 struct PieceIter {
   long u, u1;
-  int T;
-  __device__ __forceinline__ PieceIter(int n_items, int tiles_per_item) {
+  int T, item_, n_items_;
+  bool streamk;
+  __device__ __forceinline__ PieceIter(int n_items, int tiles_per_item, bool use_streamk) {
     T = tiles_per_item;
+    streamk = use_streamk;
+    n_items_ = n_items;
+    item_ = blockIdx.x;
     const long total = (long)n_items * T;
     const long share = (total + gridDim.x - 1) / gridDim.x;
     u = (long)blockIdx.x * share;
     u1 = u + share < total ? u + share : total;
   }
   __device__ __forceinline__ bool next(int& item, int& t0, int& t1) {
+    if (!streamk) {                       // whole row blocks, CTA-strided
+      if (item_ >= n_items_) return false;
+      item = item_; t0 = 0; t1 = T;
+      item_ += gridDim.x;
+      return true;
+    }
     if (u >= u1) return false;
     item = (int)(u / T);
     t0 = (int)(u - (long)item * T);
@@ -206,12 +228,17 @@ template <int MODE, int KB, int SEQ>
 __global__ void __launch_bounds__((GramCfg<MODE, KB, SEQ>::kThreads), 1)
 gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel, uint8_t* __restrict__ ws) {
   using G = GramCfg<MODE, KB, SEQ>;
-  constexpr int BN = G::BN, NS = G::NS, NB = G::NB, CW = G::CW;
+  constexpr int BN = G::BN, NS = G::NS, NB = G::NB, CW = G::CW, NW = G::NW, NG = G::NG;
   using L = GramSmem<BN, KB, NB>;
   constexpr bool kIsNce = (MODE == NCE_FWD || MODE == NCE_BWD);
   constexpr bool kBwd = (MODE == NCE_BWD || MODE == TMP_BWD);
   constexpr bool kColVec = (MODE != NCE_FWD);
-  constexpr int kEpiThreads = 128 * NS;
+  constexpr int kEpiThreads = 128 * NG;
+  // TMEM columns between the W of consecutive UMMA #2 K steps (16 bf16 = 8 packed columns).  When two warpgroups share a
+  // stage each W chunk stays inside the 16 S columns its own warpgroup consumed, so nobody overwrites columns the
+  // other warpgroup may not have read yet.
+  constexpr int kWStep = (NW > 1) ? 16 : 8;
+  static_assert(NW == 1 || CW == 16, "shared stages use 16-column chunks");
   constexpr int kON = KB * 64;                       // UMMA #2 N = padded operand width
   constexpr int kKSteps = KB * 4;                    // UMMA #1 K steps (K padded to 64 with zeros)
   constexpr uint32_t kOCol = 0;                      // TMEM: O accumulator at [0, kON) (backward modes only)
@@ -230,12 +257,12 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     mbar_init(&bars->a_empty, 1);
     for (int i = 0; i < NB; ++i) {
       mbar_init(&bars->b_full[i], 1);
-      mbar_init(&bars->b_empty[i], kColVec ? 1 + 4 : 1);    // UMMA commit (+ one elected lane per epilogue warp)
+      mbar_init(&bars->b_empty[i], kColVec ? 1 + 4 * NW : 1);   // UMMA commit (+ one elected lane per epilogue warp)
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->s_empty[i], 128);
-      mbar_init(&bars->w_full[i], 128);
+      mbar_init(&bars->s_empty[i], 128 * NW);
+      mbar_init(&bars->w_full[i], 128 * NW);
     }
     mbar_init(&bars->o_full, 1);
     mbar_init(&bars->o_empty, kEpiThreads);
@@ -262,7 +289,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     // =============================== TMA producer ===============================
     {
       uint32_t nb = 0, ni = 0;
-      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p));
+      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), kIsNce ? (FB_STREAMK_NCE != 0) : (FB_STREAMK_TMP != 0));
       for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
@@ -305,7 +332,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
       const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
       uint32_t nb = 0, ni = 0;
-      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p));
+      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), kIsNce ? (FB_STREAMK_NCE != 0) : (FB_STREAMK_TMP != 0));
       for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
@@ -350,7 +377,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                   const uint32_t acc = (t2 > 0) ? 1u : 0u;
 #pragma unroll
                   for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem + kOCol, a + k * 8, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
+                    umma_bf16_ts(tmem + kOCol, a + k * kWStep, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
                   umma_commit(&bars->b_empty[st]);
                 }
                 __syncwarp();
@@ -392,7 +419,9 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     }
   } else {
     // =============================== epilogue warps ===============================
-    const int wg = (warp - 2) >> 2;                   // epilogue warpgroup == S stage it owns
+    const int wgi = (warp - 2) >> 2;                  // epilogue warpgroup index
+    const int wg = wgi / NW;                          // S stage this warpgroup works on
+    const int sub = wgi % NW;                         // which of the stage's chunks it takes (chunk % NW == sub)
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;             // row within the tile == TMEM lane
     const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
@@ -404,7 +433,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     const uint32_t cv_base = smem_u32(smem + L::kBOff + L::kBTile);
     const uint32_t s_addr = tmem + tlane + kSCol + wg * BN;
     uint32_t nb = 0, ni = 0;
-    PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p));
+    PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), kIsNce ? (FB_STREAMK_NCE != 0) : (FB_STREAMK_TMP != 0));
     for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
       Item x;
       gram_decode<MODE, BN>(p, sel, ws, it, x);
@@ -443,7 +472,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #define FB_CH_STEP 1
 #endif
 #pragma unroll 1
-        for (int ch = 0; ch < BN / CW; ch += FB_CH_STEP) {
+        for (int ch = sub; ch < BN / CW; ch += NW * FB_CH_STEP) {
           float v[CW];
           tmem_ld_chunk<CW>(s_addr + ch * CW, v);
           tmem_ld_wait();
@@ -523,7 +552,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             uint32_t pk[CW / 2];
 #pragma unroll
             for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            tmem_st_packed<CW>(s_addr + ch * (CW / 2), pk);
+            tmem_st_packed<CW>(s_addr + ch * (NW > 1 ? CW : CW / 2), pk);
           }
         }
         if (kBwd) {
@@ -543,14 +572,14 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 
       // ---------------- item epilogue: fold the per-row partials of warpgroups 1.. into warpgroup 0
       if (MODE != NCE_BWD) {
-        if (wg > 0) {
-          bars->part_acc[wg - 1][trow] = rowacc;
-          if (!kIsNce) { bars->part_hinge[wg - 1][trow] = hinge_acc; bars->part_cnt[wg - 1][trow] = cnt_i; }
+        if (wgi > 0) {
+          bars->part_acc[wgi - 1][trow] = rowacc;
+          if (!kIsNce) { bars->part_hinge[wgi - 1][trow] = hinge_acc; bars->part_cnt[wgi - 1][trow] = cnt_i; }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (wg == 0) {
+        if (wgi == 0) {
 #pragma unroll
-          for (int w = 0; w < NS - 1; ++w) rowacc += bars->part_acc[w][trow];
+          for (int w = 0; w < NG - 1; ++w) rowacc += bars->part_acc[w][trow];
           if (MODE == NCE_FWD) {
             const uint64_t slot_stride = (uint64_t)p.nProb * p.S * 2 * p.bpad;
             float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) + (((uint64_t)x.q * p.S + x.s) * 2 + side) * p.bpad;
@@ -558,7 +587,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             if (!second && !split) rpart[slot_stride + row] = 0.f;           // no secondary piece: its slot reads as 0
           } else {
 #pragma unroll
-            for (int w = 0; w < NS - 1; ++w) { hinge_acc += bars->part_hinge[w][trow]; cnt_i += bars->part_cnt[w][trow]; }
+            for (int w = 0; w < NG - 1; ++w) { hinge_acc += bars->part_hinge[w][trow]; cnt_i += bars->part_cnt[w][trow]; }
             if (kBwd && row_ok)
               reinterpret_cast<float*>(ws + p.rho_off + (second ? p.rho2_delta : 0))[(uint64_t)x.c * p.Bpad + row] = rowacc;
             if (row_ok && (lane & (SQ - 1)) == 0)
@@ -585,7 +614,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             reinterpret_cast<int32_t*>(ws + p.flag_tmp_off)[(uint64_t)x.c * (p.Bpad / kTileM) + row0 / kTileM] = split ? 1 : 0;
         }
 #pragma unroll 1
-        for (int ch = wg; ch < kON / 32; ch += NS) {     // the warpgroups split the columns of O
+        for (int ch = wgi; ch < kON / 32; ch += NG) {    // the warpgroups split the columns of O
           float v[32];
           tmem_ld32(tmem + tlane + kOCol + ch * 32, v);
           tmem_ld_wait();
@@ -600,7 +629,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       }
       if (MODE != NCE_BWD) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // partial arrays / red[] may be reused now
-        if (!kIsNce && wg == 0 && trow == 0) {
+        if (!kIsNce && wgi == 0 && trow == 0) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
           const int slot = 2 * (x.c * nrt + (row0 / kTileM - t0));
