@@ -147,7 +147,9 @@ class FocalEngine:
         self.backend = backend if backend is not None else CudaBackend()
         # CUDA graphs: the whole step (9 kernel launches, plus the collectives when row-sharded) is replayed as one
         # graph when the same input buffers are seen again -- the launch-bound tail of the step disappears.
-        self.use_cuda_graph = use_cuda_graph and getattr(self.backend, "name", "") == "cuda"
+        import os
+        self.use_cuda_graph = (use_cuda_graph and getattr(self.backend, "name", "") == "cuda"
+                               and os.environ.get("FOCAL_B200_CUDA_GRAPH", "1") != "0")
         self._graphs: Dict[tuple, tuple] = {}
         self._seen: Dict[tuple, int] = {}
         self.graph_replays = 0
