@@ -405,7 +405,7 @@ def run_ours(args):
             "tensor_roofline_frac": F / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
             "alg_tflops": F / (ms_step * 1e-3) / 1e12,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": args.steps * launches_per_step(B, S, world),
+            "gpu_launches": args.steps * launches_per_step(engine, B, D, world),
             "stages_ms": stages, "host_enqueue_ms_per_step": host_ms,
             "cuda_graph_replays": engine.graph_replays,
             "clocks": sampler.summary() if sampler else None,
@@ -431,11 +431,27 @@ def run_ours(args):
     return 0
 
 
-def launches_per_step(B, S, world):
-    b = B // S
-    pad = 1 if (b % 128 or B % 128) else 0
-    # prologue, intra, nce_rowsum, nce_lse, nce_grad, temporal, finalize, loss_reduce (+ nce_lse(all) when sharded)
-    return pad + 8 + (1 if world > 1 else 0)
+def launches_per_step(engine, B, D, world):
+    """Kernels of libfocal_b200.so per step: [zero_pad], prologue (fused intra), nce_rowsum, nce_lse, nce_grad, temporal,
+    finalize, loss_reduce (+ nce_lse(all rows) when row-sharded).  Counted from the plan of this workload."""
+    import ctypes as C
+
+    from focal_b200 import _cabi
+    hp = engine.hp
+    be = engine.backend
+    cfg = be._cfg(hp, B, D, True, (0, B // hp.seq_len))
+    info = _cabi.FocalWsInfo()
+    _cabi.check(be.lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info)), "workspace_info")
+    n = 0
+    n += 1 if (info.bpad != info.b or info.Bpad != B) else 0        # zero_pad_kernel
+    n += 1                                                          # prologue (m_II fused for S in {2, 4})
+    n += 0 if hp.seq_len in (2, 4) or not (hp.terms & 4) else 1     # separate intra_kernel otherwise
+    if hp.terms & 1:
+        n += 3 + (1 if world > 1 else 0)                            # nce_rowsum, nce_lse (+ all rows), nce_grad
+    if (hp.terms & 4) and hp.seq_len > 1:
+        n += 1                                                      # temporal
+    n += 2                                                          # finalize, loss_reduce
+    return n
 
 
 def make_args(mods, S, w, group):
