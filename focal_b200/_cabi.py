@@ -45,6 +45,7 @@ class FocalWsInfo(C.Structure):
         ("mintra_off", C.c_size_t), ("lossparts_off", C.c_size_t),
         ("dz_off", C.c_size_t), ("dz_bytes", C.c_size_t),
         ("dx_off", C.c_size_t), ("dx_bytes", C.c_size_t),
+        ("cnt_piece_stride", C.c_size_t), ("n_pieces_nce", C.c_int32), ("n_pieces_tmp", C.c_int32),
     ]
 
 

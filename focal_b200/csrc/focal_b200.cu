@@ -49,7 +49,7 @@ int cuda_ok(const char* what) {
 bool temporal_degenerate(const Plan& p) { return p.b <= 1 || p.S <= 1; }
 
 template <int MODE, int KB, int SEQ>
-int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int n_items) {
+int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int grid) {
   using G = GramCfg<MODE, KB, SEQ>;
   static_assert(G::BN == tile_bn(KB), "plan.h and gram_kernel.cuh must agree on the column tile");
   using L = GramSmem<G::BN, KB, G::NB>;
@@ -60,35 +60,34 @@ int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st,
       return cuda_ok("cudaFuncSetAttribute(gram_kernel)");
     configured = true;
   }
-  if (n_items <= 0) return FOCAL_OK;
-  const int grid = n_items < p.num_sms ? n_items : p.num_sms;     // persistent: one CTA per SM
+  if (grid <= 0) return FOCAL_OK;                                 // persistent: at most one CTA per SM (plan.h)
   kfn<<<grid, G::kThreads, L::kDynamic, st>>>(p, sel, ws);
   return cuda_ok("gram_kernel launch");
 }
 
 template <int MODE, int SEQ>
-int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int n_items) {
+int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int grid) {
   switch (kb) {
 #ifndef FB_FAST_BUILD
-    case 1: return launch_gram<MODE, 1, SEQ>(p, sel, ws, st, n_items);
-    case 3: return launch_gram<MODE, 3, SEQ>(p, sel, ws, st, n_items);
+    case 1: return launch_gram<MODE, 1, SEQ>(p, sel, ws, st, grid);
+    case 3: return launch_gram<MODE, 3, SEQ>(p, sel, ws, st, grid);
 #endif
-    case 2: return launch_gram<MODE, 2, SEQ>(p, sel, ws, st, n_items);
-    case 4: return launch_gram<MODE, 4, SEQ>(p, sel, ws, st, n_items);
+    case 2: return launch_gram<MODE, 2, SEQ>(p, sel, ws, st, grid);
+    case 4: return launch_gram<MODE, 4, SEQ>(p, sel, ws, st, grid);
   }
   return FOCAL_ESHAPE;
 }
 
 template <int MODE>
-int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int n_items) {
+int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid) {
   ProbSel sel{};
   switch (p.S) {
-    case 4: return launch_gram_kb<MODE, 4>(p, sel, ws, st, p.kbFull, n_items);
+    case 4: return launch_gram_kb<MODE, 4>(p, sel, ws, st, p.kbFull, grid);
 #ifndef FB_FAST_BUILD                 // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
-    case 2: return launch_gram_kb<MODE, 2>(p, sel, ws, st, p.kbFull, n_items);
-    case 8: return launch_gram_kb<MODE, 8>(p, sel, ws, st, p.kbFull, n_items);
-    case 16: return launch_gram_kb<MODE, 16>(p, sel, ws, st, p.kbFull, n_items);
-    case 32: return launch_gram_kb<MODE, 32>(p, sel, ws, st, p.kbFull, n_items);
+    case 2: return launch_gram_kb<MODE, 2>(p, sel, ws, st, p.kbFull, grid);
+    case 8: return launch_gram_kb<MODE, 8>(p, sel, ws, st, p.kbFull, grid);
+    case 16: return launch_gram_kb<MODE, 16>(p, sel, ws, st, p.kbFull, grid);
+    case 32: return launch_gram_kb<MODE, 32>(p, sel, ws, st, p.kbFull, grid);
 #endif
   }
   return FOCAL_ESHAPE;
@@ -98,22 +97,15 @@ int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int n_items) {
 // shared problems use the full D columns and the private ones D/2).
 template <int MODE>
 int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st) {
-  const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM;
   for (int kb = 1; kb <= 4; ++kb) {
     ProbSel sel{};
     for (int q = 0; q < p.nProb; ++q)
       if (p.ops[p.probs[q].opA].kb == kb) sel.idx[sel.n++] = q;
     if (!sel.n) continue;
-    const int items = sel.n * p.S * 2 * (t1 - t0);
-    const int rc = launch_gram_kb<MODE, 0>(p, sel, ws, st, kb, items);
+    const int rc = launch_gram_kb<MODE, 0>(p, sel, ws, st, kb, p.grid_nce[kb]);
     if (rc) return rc;
   }
   return FOCAL_OK;
-}
-
-int tmp_items(const Plan& p) {
-  const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
-  return p.nT * (t1 - t0);
 }
 
 // lanes own VW = d/32 consecutive columns per half on the vectorised row-kernel path (0 = use the generic kernels)
@@ -211,6 +203,8 @@ int focal_b200_workspace_info(const FocalCfg* cfg, FocalWsInfo* info) {
   info->lossparts_off = p.lossd_off;
   info->dz_off = p.dz_off; info->dz_bytes = p.dz_bytes;
   info->dx_off = p.dx_off; info->dx_bytes = p.dx_bytes;
+  info->cnt_piece_stride = p.cnt2_delta;
+  info->n_pieces_nce = p.np_nce; info->n_pieces_tmp = p.np_tmp;
   return FOCAL_OK;
 }
 
@@ -288,7 +282,7 @@ int focal_b200_temporal(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* st
   if (!(p.terms & FOCAL_TERM_TEMPORAL) || temporal_degenerate(p)) return FOCAL_OK;
   uint8_t* w = static_cast<uint8_t*>(ws);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, tmp_items(p)) : launch_temporal<TMP_FWD>(p, w, st, tmp_items(p));
+  return p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp);
 }
 
 int focal_b200_finalize(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,

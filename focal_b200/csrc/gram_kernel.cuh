@@ -165,18 +165,13 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
 }
 
 // Stream-K work split: the (row block, column tile) pairs of a launch are numbered consecutively and every CTA takes an
-// equal contiguous share, so a row block may be cut into a primary piece (starts at tile 0) and a secondary piece
-// (the rest, handled by the next CTA) -- never more, because a share is at least one whole row block long.  All SMs
-// stay busy until the end of the launch (with whole row blocks 256 equal items on 148 SMs ran 2 rounds for 1.73
-// rounds of work).  Secondary pieces write to their own accumulators (dz2 / dx2 / ...), so the result is deterministic.
-#ifndef FB_STREAMK_TMP
-#define FB_STREAMK_TMP 0        // temporal kernel: whole row blocks per CTA measured faster than stream-K pieces (B200)
-#endif
-#ifndef FB_STREAMK_NCE
-#define FB_STREAMK_NCE 1
-#endif
+// equal contiguous share, so a row block may be cut into a primary piece (starts at tile 0) and secondary pieces
+// (handled by the following CTAs): one when a share is at least a row block long, up to kMaxPieces - 1 when a row shard
+// leaves fewer row blocks than SMs.  All SMs stay busy until the end of the launch (with whole row blocks 256 equal
+// items on 148 SMs ran 2 rounds for 1.73 rounds of work).  Piece k writes to its own copy of the accumulators
+// (dz / dx / rho / cnt / row sums + k * delta) and finalize adds them in piece order, so the result is deterministic.
 struct PieceIter {
-  long u, u1;
+  long u, u1, share;
   int T, item_, n_items_;
   bool streamk;
   __device__ __forceinline__ PieceIter(int n_items, int tiles_per_item, bool use_streamk) {
@@ -185,22 +180,28 @@ struct PieceIter {
     n_items_ = n_items;
     item_ = blockIdx.x;
     const long total = (long)n_items * T;
-    const long share = (total + gridDim.x - 1) / gridDim.x;
+    share = (total + gridDim.x - 1) / gridDim.x;
     u = (long)blockIdx.x * share;
     u1 = u + share < total ? u + share : total;
   }
-  __device__ __forceinline__ bool next(int& item, int& t0, int& t1) {
+  // next piece of this CTA: row block `item`, column tiles [t0, t1); pk = index of the piece within its row block,
+  // npi = number of pieces the row block is cut into
+  __device__ __forceinline__ bool next(int& item, int& t0, int& t1, int& pk, int& npi) {
     if (!streamk) {                       // whole row blocks, CTA-strided
       if (item_ >= n_items_) return false;
-      item = item_; t0 = 0; t1 = T;
+      item = item_; t0 = 0; t1 = T; pk = 0; npi = 1;
       item_ += gridDim.x;
       return true;
     }
     if (u >= u1) return false;
     item = (int)(u / T);
-    t0 = (int)(u - (long)item * T);
+    const long i0 = (long)item * T;
+    t0 = (int)(u - i0);
     const long rest = u1 - u;
     t1 = (long)(T - t0) <= rest ? T : (int)(t0 + rest);
+    const int cfirst = (int)(i0 / share);
+    pk = (int)blockIdx.x - cfirst;
+    npi = (int)((i0 + T - 1) / share) - cfirst + 1;
     u += t1 - t0;
     return true;
   }
@@ -289,8 +290,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     // =============================== TMA producer ===============================
     {
       uint32_t nb = 0, ni = 0;
-      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), kIsNce ? (FB_STREAMK_NCE != 0) : (FB_STREAMK_TMP != 0));
-      for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
+      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
+      for (int it, pt0, pt1, pk, npi; pieces.next(it, pt0, pt1, pk, npi); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
         x.ct_begin = pt0; x.ct_end = pt1;
@@ -332,8 +333,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
       const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
       uint32_t nb = 0, ni = 0;
-      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), kIsNce ? (FB_STREAMK_NCE != 0) : (FB_STREAMK_TMP != 0));
-      for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
+      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
+      for (int it, pt0, pt1, pk, npi; pieces.next(it, pt0, pt1, pk, npi); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
         x.ct_begin = pt0; x.ct_end = pt1;
@@ -433,13 +434,12 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     const uint32_t cv_base = smem_u32(smem + L::kBOff + L::kBTile);
     const uint32_t s_addr = tmem + tlane + kSCol + wg * BN;
     uint32_t nb = 0, ni = 0;
-    PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), kIsNce ? (FB_STREAMK_NCE != 0) : (FB_STREAMK_TMP != 0));
-    for (int it, pt0, pt1; pieces.next(it, pt0, pt1); ++ni) {
+    PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
+    for (int it, pt0, pt1, pk, npi; pieces.next(it, pt0, pt1, pk, npi); ++ni) {
       Item x;
       gram_decode<MODE, BN>(p, sel, ws, it, x);
       x.ct_begin = pt0; x.ct_end = pt1;
-      const bool second = pt0 > 0;                    // secondary piece of a split row block
-      const bool split = !second && pt1 < pieces.T;   // primary piece of a split row block
+      const bool second = pk > 0;                     // secondary piece of a split row block
       const int row0 = x.row0, ncol_valid = x.ncol_valid, side = x.side, ntc = x.ntc, ct_begin = x.ct_begin;
       const int row = row0 + trow;                    // row within side (NCE: sequence index k) / tensor (TMP: i)
       const bool row_ok = row < ncol_valid && row >= x.row_lo && row < x.row_hi;
@@ -583,15 +583,16 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           if (MODE == NCE_FWD) {
             const uint64_t slot_stride = (uint64_t)p.nProb * p.S * 2 * p.bpad;
             float* rpart = reinterpret_cast<float*>(ws + p.rpart_off) + (((uint64_t)x.q * p.S + x.s) * 2 + side) * p.bpad;
-            rpart[(second ? slot_stride : 0) + row] = row_ok ? rowacc : 0.f;
-            if (!second && !split) rpart[slot_stride + row] = 0.f;           // no secondary piece: its slot reads as 0
+            rpart[(uint64_t)pk * slot_stride + row] = row_ok ? rowacc : 0.f;
+            if (!second)                                                     // slots without a piece read as 0
+              for (int k = npi; k < p.nsplit_fwd; ++k) rpart[(uint64_t)k * slot_stride + row] = 0.f;
           } else {
 #pragma unroll
             for (int w = 0; w < NG - 1; ++w) { hinge_acc += bars->part_hinge[w][trow]; cnt_i += bars->part_cnt[w][trow]; }
             if (kBwd && row_ok)
-              reinterpret_cast<float*>(ws + p.rho_off + (second ? p.rho2_delta : 0))[(uint64_t)x.c * p.Bpad + row] = rowacc;
+              reinterpret_cast<float*>(ws + p.rho_off + (uint64_t)pk * p.rho2_delta)[(uint64_t)x.c * p.Bpad + row] = rowacc;
             if (row_ok && (lane & (SQ - 1)) == 0)
-              reinterpret_cast<int32_t*>(ws + p.cnt_off + (second ? p.cnt2_delta : 0))[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
+              reinterpret_cast<int32_t*>(ws + p.cnt_off + (uint64_t)pk * p.cnt2_delta)[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
             // every lane of a sequence accumulated the same hinge values: count each (I, J) once
             const float hs = warp_sum(((lane & (SQ - 1)) == 0) ? hinge_acc : 0.f);
             if (lane == 0) bars->red[quarter] = hs;
@@ -603,15 +604,15 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         tc_fence_after();
         float* out;
         if (kIsNce) {
-          out = reinterpret_cast<float*>(ws + p.probs[x.q].dz_off + (second ? p.dz2_delta : 0)) +
+          out = reinterpret_cast<float*>(ws + p.probs[x.q].dz_off + (uint64_t)pk * p.dz2_delta) +
                 ((uint64_t)side * p.S * p.bpad + (uint64_t)x.s * p.bpad + row) * kON;
           if (!second && trow == 0)
             reinterpret_cast<int32_t*>(ws + p.flag_nce_off)[(((uint64_t)x.q * p.S + x.s) * 2 + side) * (p.bpad / kTileM) +
-                                                            row0 / kTileM] = split ? 1 : 0;
+                                                            row0 / kTileM] = npi - 1;
         } else {
-          out = reinterpret_cast<float*>(ws + p.dx_off + (second ? p.dx2_delta : 0)) + ((uint64_t)x.c * p.Bpad + row) * kON;
+          out = reinterpret_cast<float*>(ws + p.dx_off + (uint64_t)pk * p.dx2_delta) + ((uint64_t)x.c * p.Bpad + row) * kON;
           if (!second && trow == 0)
-            reinterpret_cast<int32_t*>(ws + p.flag_tmp_off)[(uint64_t)x.c * (p.Bpad / kTileM) + row0 / kTileM] = split ? 1 : 0;
+            reinterpret_cast<int32_t*>(ws + p.flag_tmp_off)[(uint64_t)x.c * (p.Bpad / kTileM) + row0 / kTileM] = npi - 1;
         }
 #pragma unroll 1
         for (int ch = wgi; ch < kON / 32; ch += NG) {    // the warpgroups split the columns of O
@@ -632,11 +633,12 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         if (!kIsNce && wgi == 0 && trow == 0) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
-          const int slot = 2 * (x.c * nrt + (row0 / kTileM - t0));
+          const int slot = p.np_tmp * (x.c * nrt + (row0 / kTileM - t0));
           float* p3 = reinterpret_cast<float*>(ws + p.part3_off);
-          p3[slot + (second ? 1 : 0)] =
+          p3[slot + pk] =
               ((bars->red[0] + bars->red[1]) + (bars->red[2] + bars->red[3])) / ((float)p.b * (float)(p.b - 1));
-          if (!second && !split) p3[slot + 1] = 0.f;
+          if (!second)
+            for (int k = npi; k < p.np_tmp; ++k) p3[slot + k] = 0.f;
         }
       }
     }

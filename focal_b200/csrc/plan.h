@@ -49,7 +49,10 @@ struct ProbSel {
 struct Plan {
   // dims
   int32_t B, S, M, D, d, b, bpad, Bpad, nT, nOps, nProb, nOrth, kbFull, seq0, seq1, need_grad, terms, num_sms;
-  int32_t nsplit_fwd;                                   // column splits of the row-sum pass
+  int32_t nsplit_fwd;                                   // row-sum slots per row (= np_nce)
+  // stream-K split of the Gram launches (see PieceIter): grid sizes and the largest number of pieces one 128-row
+  // block is cut into; piece k of a block accumulates into the k-th copy of the output buffers
+  int32_t sk_nce, sk_tmp, np_nce, np_tmp, grid_tmp, grid_nce[5];
   int32_t in_rb, in_bs;                                 // row-blocked inputs: rows per block, block stride (floats)
   float T, margin, w_shared, w_private, w_orth, w_rank;
   float alpha;                                          // sqrt(log2(e)/T): operand pre-scale, Gram = log2-domain logit
@@ -71,9 +74,9 @@ struct Plan {
   uint64_t part3_off;   // fp32 [nitems3]   hinge partials
   uint64_t lossd_off;   // double [8]
   uint64_t dz_off, dz_bytes, dx_bytes;
-  // stream-K: a 128-row block whose column tiles are split over two CTAs has a second set of accumulators
-  uint64_t dz2_delta, dx2_delta, rho2_delta, cnt2_delta;   // byte distance from the primary to the secondary buffer
-  uint64_t flag_tmp_off;   // int32 [2M][Bpad/128]: 1 if the row block has a secondary piece (temporal)
+  // stream-K: a 128-row block whose column tiles are split over several CTAs has one set of accumulators per piece
+  uint64_t dz2_delta, dx2_delta, rho2_delta, cnt2_delta;   // byte distance between the buffers of consecutive pieces
+  uint64_t flag_tmp_off;   // int32 [2M][Bpad/128]: number of secondary pieces of the row block (temporal)
   uint64_t flag_nce_off;   // int32 [nProb][S][2][bpad/128]: same for the InfoNCE backward pass
   uint64_t total_bytes;
   int32_t nblk1, nblk2, nitems3;
@@ -88,6 +91,40 @@ __host__ __device__ inline size_t feat_row_off(const Plan& p, int i) {
 
 // rows of the prologue / finalize kernels handled per 128-thread block (one warp per row)
 constexpr int kRowsPerBlock = 4;
+
+// Stream-K geometry of one Gram launch: n_items row blocks of T column tiles each are numbered consecutively and cut
+// into one contiguous share per CTA.  Returns the grid size and (np) the largest number of pieces a row block is cut
+// into; the grid shrinks until np <= kMaxPieces and a share is at least kMinShare tiles.
+constexpr int kMaxPieces = 8;
+constexpr int kMinShare = 4;
+inline int piece_grid(int n_items, int T, int num_sms, bool streamk, int* np) {
+  *np = 1;
+  if (n_items <= 0) return 0;
+  if (!streamk) return n_items < num_sms ? n_items : num_sms;
+  const long total = (long)n_items * T;
+  long grid = num_sms;
+  if (total / kMinShare < grid) grid = total / kMinShare > 0 ? total / kMinShare : 1;
+  for (;; --grid) {
+    const long share = (total + grid - 1) / grid;
+    int worst = 1;
+    for (int i = 0; i < n_items; ++i) {
+      const long i0 = (long)i * T;
+      const int n = (int)((i0 + T - 1) / share - i0 / share) + 1;
+      if (n > worst) worst = n;
+    }
+    if (worst <= kMaxPieces || grid == 1) { *np = worst; return (int)grid; }
+  }
+}
+__host__ __device__ inline int nce_row_tiles(const Plan& p) { return (p.seq1 + kTileM - 1) / kTileM - p.seq0 / kTileM; }
+__host__ __device__ inline int tmp_row_tiles(const Plan& p) {
+  return (p.seq1 * p.S + kTileM - 1) / kTileM - (p.seq0 * p.S) / kTileM;
+}
+#ifndef FB_STREAMK_TMP
+#define FB_STREAMK_TMP 1        // 1: always; 0: only when the launch has fewer row blocks than SMs (row shards); -1: never
+#endif
+#ifndef FB_STREAMK_NCE
+#define FB_STREAMK_NCE 1
+#endif
 
 inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   std::memset(&p, 0, sizeof(p));
@@ -170,7 +207,25 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     Bo.use_prob[Bo.nuse] = q; Bo.use_side[Bo.nuse] = 1; Bo.use_partner[Bo.nuse] = oa; ++Bo.nuse;
   }
 
-  p.nsplit_fwd = 2;      // row-sum slots per row: primary / secondary stream-K piece
+  // ---- stream-K geometry of the Gram launches
+  p.sk_nce = FB_STREAMK_NCE;
+  p.np_nce = 2;
+  for (int kb = 1; kb <= 4; ++kb) {
+    int n = 0, np1 = 1;
+    for (int q = 0; q < p.nProb; ++q) n += p.ops[p.probs[q].opA].kb == kb;
+    const int bn = tile_bn(kb);
+    p.grid_nce[kb] = piece_grid(n * p.S * 2 * nce_row_tiles(p), 2 * ((p.b + bn - 1) / bn), num_sms, p.sk_nce != 0, &np1);
+    if (np1 > p.np_nce) p.np_nce = np1;
+  }
+  {
+    const int items = p.nT * tmp_row_tiles(p), bn = tile_bn(p.kbFull);
+    p.sk_tmp = (FB_STREAMK_TMP > 0) || (FB_STREAMK_TMP == 0 && items < num_sms);
+    p.np_tmp = 2;
+    int np1 = 1;
+    p.grid_tmp = piece_grid(items, (p.B + bn - 1) / bn, num_sms, p.sk_tmp != 0, &np1);
+    if (np1 > p.np_tmp) p.np_tmp = np1;
+  }
+  p.nsplit_fwd = p.np_nce;      // row-sum slots per row: one per stream-K piece
 
   // ---- workspace
   uint64_t off = 0;
@@ -189,19 +244,22 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     p.probs[q].dz_off = take((uint64_t)2 * rowsNce * p.ops[p.probs[q].opA].kb * kKBlk * 4);
   p.dz_bytes = off - p.dz_off;
   p.dz2_delta = p.dz_bytes;
-  take(p.dz_bytes);                                                  // secondary dz accumulators
+  for (int k = 1; k < p.np_nce; ++k) take(p.dz_bytes);               // dz accumulators of the secondary pieces
+  auto take_n = [&](uint64_t bytes, int n, uint64_t* delta) {        // n equally spaced copies
+    const uint64_t o = take(bytes);
+    *delta = align_up(bytes, 1024);
+    for (int k = 1; k < n; ++k) take(bytes);
+    return o;
+  };
   p.dx_bytes = (uint64_t)p.nT * p.Bpad * p.kbFull * kKBlk * 4;
-  p.dx_off = take(p.dx_bytes);
-  p.dx2_delta = take(p.dx_bytes) - p.dx_off;
-  p.rho_off = take((uint64_t)p.nT * p.Bpad * 4);
-  p.rho2_delta = take((uint64_t)p.nT * p.Bpad * 4) - p.rho_off;
-  p.cnt_off = take((uint64_t)p.nT * p.bpad * 4);
-  p.cnt2_delta = take((uint64_t)p.nT * p.bpad * 4) - p.cnt_off;
+  p.dx_off = take_n(p.dx_bytes, p.np_tmp, &p.dx2_delta);
+  p.rho_off = take_n((uint64_t)p.nT * p.Bpad * 4, p.np_tmp, &p.rho2_delta);
+  p.cnt_off = take_n((uint64_t)p.nT * p.bpad * 4, p.np_tmp, &p.cnt2_delta);
   p.flag_tmp_off = take((uint64_t)p.nT * (p.Bpad / kTileM) * 4);
   p.flag_nce_off = take((uint64_t)p.nProb * p.S * 2 * (p.bpad / kTileM) * 4);
   p.nblk1 = (p.B + kRowsPerBlock - 1) / kRowsPerBlock;
   p.nblk2 = (int32_t)((rowsNce * 2 * p.nProb + 255) / 256);
-  p.nitems3 = 2 * p.nT * (p.Bpad / kTileM);          // two hinge-partial slots (primary / secondary piece) per row block
+  p.nitems3 = p.np_tmp * p.nT * (p.Bpad / kTileM);   // one hinge-partial slot per piece of a row block
   p.part1_off = take((uint64_t)p.nblk1 * 4 * 4);
   p.part2_off = take((uint64_t)p.nblk2 * 2 * 4);
   p.part3_off = take((uint64_t)p.nitems3 * 4);

@@ -317,17 +317,21 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
     const int Dp = p.kbFull * 64;
     for (int t = 0; t < p.nT; ++t) {
       const float* x = xs + t * D;
-      // a row block whose column tiles were split over two CTAs (stream-K) has a secondary set of accumulators
-      const bool two = reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off)[(uint64_t)t * (p.Bpad / kTileM) + i / kTileM] != 0;
+      // a row block whose column tiles were split over several CTAs (stream-K) has one set of accumulators per piece
+      const int extra = reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off)[(uint64_t)t * (p.Bpad / kTileM) + i / kTileM];
       float rho = reinterpret_cast<const float*>(ws + p.rho_off)[(uint64_t)t * p.Bpad + i];
       const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
-      const float* y2 = reinterpret_cast<const float*>(ws + p.dx_off + p.dx2_delta) + ((uint64_t)t * p.Bpad + i) * Dp;
       int cnt = reinterpret_cast<const int32_t*>(ws + p.cnt_off)[(uint64_t)t * p.bpad + I];
-      if (two) {
-        rho += reinterpret_cast<const float*>(ws + p.rho_off + p.rho2_delta)[(uint64_t)t * p.Bpad + i];
-        cnt += reinterpret_cast<const int32_t*>(ws + p.cnt_off + p.cnt2_delta)[(uint64_t)t * p.bpad + I];
+      for (int k = 1; k <= extra; ++k) {
+        rho += reinterpret_cast<const float*>(ws + p.rho_off + k * p.rho2_delta)[(uint64_t)t * p.Bpad + i];
+        cnt += reinterpret_cast<const int32_t*>(ws + p.cnt_off + k * p.cnt2_delta)[(uint64_t)t * p.bpad + I];
       }
-      for (int c = lane; c < D; c += 32) gs[t * D + c] = p.w_rank * (bf16_round(x[c]) * rho - (y[c] + (two ? y2[c] : 0.f)));
+      for (int c = lane; c < D; c += 32) {
+        float yc = y[c];
+        for (int k = 1; k <= extra; ++k)
+          yc += (reinterpret_cast<const float*>(ws + p.dx_off + k * p.dx2_delta) + ((uint64_t)t * p.Bpad + i) * Dp)[c];
+        gs[t * D + c] = p.w_rank * (bf16_round(x[c]) * rho - yc);
+      }
       // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
       const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
       if (cnt > 0) {
@@ -375,10 +379,8 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
         const float* px = xs + po.tensor * D + po.col0;
         const float* acc = reinterpret_cast<const float*>(ws + pr.dz_off) +
                            ((uint64_t)side * S * p.bpad + rowN) * wp;
-        const float* acc2 = reinterpret_cast<const float*>(ws + pr.dz_off + p.dz2_delta) +
-                            ((uint64_t)side * S * p.bpad + rowN) * wp;
-        const bool two = reinterpret_cast<const int32_t*>(ws + p.flag_nce_off)[(((uint64_t)q * S + s) * 2 + side) *
-                                                                               (p.bpad / kTileM) + I / kTileM] != 0;
+        const int extra = reinterpret_cast<const int32_t*>(ws + p.flag_nce_off)[(((uint64_t)q * S + s) * 2 + side) *
+                                                                                (p.bpad / kTileM) + I / kTileM];
         const float wq = pr.weight * inv_tsn;
         // The positive column p(k) is masked out of the tiles and handled here in fp32: where the positive
         // dominates the row (small T, aligned views) W_kp - 2 is a tiny difference that bf16 W would destroy.
@@ -388,8 +390,12 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
         gpos = warp_sum(gpos);
         const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
         const float wkp = exp2f(gpos) * (1.f / rs[(uint64_t)side * p.bpad + I] + 1.f / rs[(uint64_t)(1 - side) * p.bpad + I]);
-        for (int c = lane; c < w; c += 32)
-          tmp[c] += wq * inv_alpha * (acc[c] + (two ? acc2[c] : 0.f) + (wkp - 2.f) * bf16_round(px[c] * pinv));
+        for (int c = lane; c < w; c += 32) {
+          float ac = acc[c];
+          for (int k = 1; k <= extra; ++k)
+            ac += (reinterpret_cast<const float*>(ws + pr.dz_off + k * p.dz2_delta) + ((uint64_t)side * S * p.bpad + rowN) * wp)[c];
+          tmp[c] += wq * inv_alpha * (ac + (wkp - 2.f) * bf16_round(px[c] * pinv));
+        }
       }
       if (!used) continue;
       // d zh / d z = (I - zh zh^T) / n
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant_
   if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_nan) {
     const int t0 = (p.seq0 * p.S) / kTileM;
     const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
-    for (int k = threadIdx.x; k < 2 * p.nT * nrt; k += 256) acc[3] += p3[k];
+    for (int k = threadIdx.x; k < p.np_tmp * p.nT * nrt; k += 256) acc[3] += p3[k];
   }
   double out[4];
   for (int a = 0; a < 4; ++a) {

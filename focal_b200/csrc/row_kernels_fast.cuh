@@ -251,23 +251,23 @@ __global__ void __launch_bounds__(128) finalize_fast_kernel(const __grid_constan
 #pragma unroll
     for (int e = 0; e < VW; ++e) { gsh[e] = 0.f; gpr[e] = 0.f; }
     if (do_tmp) {
-      // a row block whose column tiles were split over two CTAs (stream-K) has a secondary set of accumulators
-      const bool two = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off) + (uint64_t)t * (p.Bpad / kTileM) + i / kTileM) != 0;
+      // a row block whose column tiles were split over several CTAs (stream-K) has one set of accumulators per piece
+      const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off) + (uint64_t)t * (p.Bpad / kTileM) + i / kTileM);
       float rho = __ldg(reinterpret_cast<const float*>(ws + p.rho_off) + (uint64_t)t * p.Bpad + i);
       const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
       int cnt = __ldg(reinterpret_cast<const int32_t*>(ws + p.cnt_off) + (uint64_t)t * p.bpad + I);
       float ysh[VW], ypr[VW];
       ld_frag<VW>(y + c0, ysh);
       ld_frag<VW>(y + d + c0, ypr);
-      if (two) {
-        const float* y2 = reinterpret_cast<const float*>(ws + p.dx_off + p.dx2_delta) + ((uint64_t)t * p.Bpad + i) * Dp;
+      for (int k = 1; k <= extra; ++k) {
+        const float* y2 = reinterpret_cast<const float*>(ws + p.dx_off + k * p.dx2_delta) + ((uint64_t)t * p.Bpad + i) * Dp;
         float zsh[VW], zpr[VW];
         ld_frag<VW>(y2 + c0, zsh);
         ld_frag<VW>(y2 + d + c0, zpr);
 #pragma unroll
         for (int e = 0; e < VW; ++e) { ysh[e] += zsh[e]; ypr[e] += zpr[e]; }
-        rho += __ldg(reinterpret_cast<const float*>(ws + p.rho_off + p.rho2_delta) + (uint64_t)t * p.Bpad + i);
-        cnt += __ldg(reinterpret_cast<const int32_t*>(ws + p.cnt_off + p.cnt2_delta) + (uint64_t)t * p.bpad + I);
+        rho += __ldg(reinterpret_cast<const float*>(ws + p.rho_off + k * p.rho2_delta) + (uint64_t)t * p.Bpad + i);
+        cnt += __ldg(reinterpret_cast<const int32_t*>(ws + p.cnt_off + k * p.cnt2_delta) + (uint64_t)t * p.bpad + I);
       }
       float rsh[VW], rpr[VW];
 #pragma unroll
@@ -329,10 +329,11 @@ __global__ void __launch_bounds__(128) finalize_fast_kernel(const __grid_constan
         float px[VW], acc[VW];
         ld_frag<VW>(xs + po.tensor * D + po.col0 + c0, px);
         ld_frag<VW>(reinterpret_cast<const float*>(ws + pr.dz_off) + ((uint64_t)side * S * p.bpad + rowN) * wp + c0, acc);
-        if (__ldg(reinterpret_cast<const int32_t*>(ws + p.flag_nce_off) + (((uint64_t)q * S + s) * 2 + side) * (p.bpad / kTileM) +
-                  I / kTileM) != 0) {
+        const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_nce_off) +
+                                (((uint64_t)q * S + s) * 2 + side) * (p.bpad / kTileM) + I / kTileM);
+        for (int k = 1; k <= extra; ++k) {
           float acc2[VW];
-          ld_frag<VW>(reinterpret_cast<const float*>(ws + pr.dz_off + p.dz2_delta) + ((uint64_t)side * S * p.bpad + rowN) * wp + c0, acc2);
+          ld_frag<VW>(reinterpret_cast<const float*>(ws + pr.dz_off + k * p.dz2_delta) + ((uint64_t)side * S * p.bpad + rowN) * wp + c0, acc2);
 #pragma unroll
           for (int e = 0; e < VW; ++e) acc[e] += acc2[e];
         }

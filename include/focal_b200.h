@@ -70,12 +70,14 @@ typedef struct FocalWsInfo {
   int32_t b, bpad, Bpad, n_problems, n_ops, kb_full;
   size_t rowsum_off;     /* fp32 [n_problems][S][2][bpad]  sum_{j != k} exp(s_kj), position-major          */
   size_t rowsum_bytes;
-  size_t cnt_off;        /* int32 [2M][bpad_seq]: active hinge count per sequence (temporal)               */
-  size_t cnt_bytes;
+  size_t cnt_off;        /* int32 [2M][bpad]: active hinge count per sequence (temporal); one copy per      */
+  size_t cnt_bytes;      /* stream-K piece: copy k at cnt_off + k * cnt_piece_stride, k < n_pieces_tmp; sum them */
   size_t mintra_off;     /* fp32 [2M][Bpad]: m_II of the row's sequence                                    */
   size_t lossparts_off;  /* double [8]: total, shared, private, orth, temporal (un-weighted sums) ...      */
   size_t dz_off, dz_bytes;     /* fp32 InfoNCE operand-gradient accumulators                               */
   size_t dx_off, dx_bytes;     /* fp32 [2M][Bpad][kb_full*64] temporal gradient accumulators               */
+  size_t cnt_piece_stride;     /* bytes between the per-piece copies of cnt                                */
+  int32_t n_pieces_nce, n_pieces_tmp; /* most pieces a 128-row block is cut into (stream-K over column tiles) */
 } FocalWsInfo;
 
 int focal_b200_abi_version(void);

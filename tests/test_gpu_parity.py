@@ -200,7 +200,13 @@ def test_intermediates_rowsum_and_hinge_counts():
         want = ref.aux["nce_rowsum"][q] * math.exp(1.0 / 0.5)          # oracle sums exp(s - 1/T)
         got = torch.cat((rs[q, :, 0, :b], rs[q, :, 1, :b]), dim=1).double()
         assert torch.allclose(got, want, rtol=3e-3), (q, float((got / want - 1).abs().max()))
-    cnt = be._view(ws, info.cnt_off, info.cnt_bytes, torch.int32, (2 * len(mods), info.bpad)).cpu()
+    # one copy of the counts per stream-K piece of a row block (unused copies hold stale data -> only sum pieces that
+    # exist: a piece that does not exist for a block was never written, so zero the workspace first and re-run)
+    ws.zero_()
+    be.run(hp, feats, (0, b), True, None)
+    torch.cuda.synchronize()
+    cnt = sum(be._view(ws, info.cnt_off + k * info.cnt_piece_stride, info.cnt_bytes, torch.int32,
+                       (2 * len(mods), info.bpad)).cpu() for k in range(info.n_pieces_tmp))
     for t in range(2 * len(mods)):
         act = ref.aux["temporal"][t]["active"]
         m = ref.aux["temporal"][t]["m"]
