@@ -398,7 +398,11 @@ def run_ours(args):
             "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(), "global_batch": B, "rows_per_gpu": Bl,
-                       "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"row-sharded x{world}, "
+                                       + ("exchange by kernel stores into NVLink peer memory + device barriers"
+                                          if any(v is not None for v in getattr(engine.backend, "_peers", {}).values())
+                                          else "NCCL all-gather(features, row sums) + all-reduce(loss)"))
+                       if world > 1 else "single GPU",
                        "l2": f"inputs rotate over {nsets} batches ({nsets * 2 * M * B * D * 4 / 2 ** 20:.0f} MiB"
                              + (" > 126 MiB L2)" if nsets * 2 * M * B * D * 4 > L2_BYTES else ", fits L2: small side workload)"),
                        "tiles": "bf16 operands, fp32 accumulation (tcgen05 kind::f16)"},
@@ -446,8 +450,11 @@ def launches_per_step(engine, B, D, world):
     n += 1 if (info.bpad != info.b or info.Bpad != B) else 0        # zero_pad_kernel
     n += 1                                                          # prologue (m_II fused for S in {2, 4})
     n += 0 if hp.seq_len in (2, 4) or not (hp.terms & 4) else 1     # separate intra_kernel otherwise
+    peer = world > 1 and any(v is not None for v in getattr(be, "_peers", {}).values())
     if hp.terms & 1:
-        n += 3 + (1 if world > 1 else 0)                            # nce_rowsum, nce_lse (+ all rows), nce_grad
+        n += 3 + (1 if world > 1 else 0)                            # nce_rowsum, nce_lse, nce_grad + (sharded) either
+    if peer:                                                        # nce_lse(all rows) or the 2nd peer barrier
+        n += 1                                                      # peer barrier after the prologue
     if (hp.terms & 4) and hp.seq_len > 1:
         n += 1                                                      # temporal
     n += 2                                                          # finalize, loss_reduce

@@ -20,7 +20,10 @@ EXPORTS = (
     "focal_b200_abi_version", "focal_b200_strerror", "focal_b200_workspace_info", "focal_b200_prologue",
     "focal_b200_nce_rowsum", "focal_b200_nce_lse", "focal_b200_nce_grad", "focal_b200_temporal",
     "focal_b200_finalize", "focal_b200_loss", "focal_b200_debug_umma",
+    "focal_b200_peer_alloc", "focal_b200_peer_open", "focal_b200_peer_close", "focal_b200_peer_free",
+    "focal_b200_loss_sharded",
 )
+FOCAL_MAX_PEERS = 8
 
 
 class FocalCfg(C.Structure):
@@ -31,8 +34,12 @@ class FocalCfg(C.Structure):
         ("no_private", C.c_int32), ("need_grad", C.c_int32), ("terms", C.c_int32), ("precision", C.c_int32),
         ("seq_begin", C.c_int32), ("seq_end", C.c_int32), ("num_sms", C.c_int32),
         ("in_block_rows", C.c_int32), ("in_block_stride", C.c_int32),
-        ("reserved", C.c_int32 * 1),
+        ("local_rows", C.c_int32),
     ]
+
+
+class FocalPeers(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ws", C.c_void_p * 8)]
 
 
 class FocalWsInfo(C.Structure):
@@ -81,6 +88,11 @@ def load(path: str | None = None) -> C.CDLL:
     lib.focal_b200_temporal.argtypes = [cfgp, vp, C.c_size_t, vp]
     lib.focal_b200_finalize.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
     lib.focal_b200_loss.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
+    lib.focal_b200_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.focal_b200_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.focal_b200_peer_close.argtypes = [vp]
+    lib.focal_b200_peer_free.argtypes = [vp]
+    lib.focal_b200_loss_sharded.argtypes = [cfgp, C.POINTER(vp), C.POINTER(FocalPeers), C.c_size_t, vp, C.POINTER(vp), vp]
     lib.focal_b200_debug_umma.argtypes = [vp, C.c_uint32, vp, C.c_uint32] + [C.c_uint32] * 10 + [vp, vp]
     for name in EXPORTS:
         if name != "focal_b200_strerror":

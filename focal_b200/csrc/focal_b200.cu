@@ -1,5 +1,6 @@
 // C ABI of the B200-native FOCAL loss hot path (see include/focal_b200.h).
 #include <cstdio>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include "../../include/focal_b200.h"
@@ -115,23 +116,24 @@ int fast_row_vw(const Plan& p, int no_private) {
 }
 
 template <int VW>
-int launch_prologue_fast_vw(const Plan& p, const FeatPtrs& f, uint8_t* w, size_t smem, int grid, int fuse, cudaStream_t st) {
+int launch_prologue_fast_vw(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, size_t smem, int grid, int fuse,
+                            cudaStream_t st) {
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     if (cudaFuncSetAttribute(prologue_fast_kernel<VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return cuda_ok("cudaFuncSetAttribute(prologue_fast_kernel)");
     configured = smem;
   }
-  prologue_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, w, fuse);
+  prologue_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, pw, w, fuse);
   return cuda_ok("prologue_fast_kernel");
 }
-int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, uint8_t* w, size_t smem, int grid, int fuse,
-                         cudaStream_t st) {
+int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, size_t smem, int grid,
+                         int fuse, cudaStream_t st) {
   switch (vw) {
-    case 1: return launch_prologue_fast_vw<1>(p, f, w, smem, grid, fuse, st);
-    case 2: return launch_prologue_fast_vw<2>(p, f, w, smem, grid, fuse, st);
-    case 3: return launch_prologue_fast_vw<3>(p, f, w, smem, grid, fuse, st);
-    case 4: return launch_prologue_fast_vw<4>(p, f, w, smem, grid, fuse, st);
+    case 1: return launch_prologue_fast_vw<1>(p, f, pw, w, smem, grid, fuse, st);
+    case 2: return launch_prologue_fast_vw<2>(p, f, pw, w, smem, grid, fuse, st);
+    case 3: return launch_prologue_fast_vw<3>(p, f, pw, w, smem, grid, fuse, st);
+    case 4: return launch_prologue_fast_vw<4>(p, f, pw, w, smem, grid, fuse, st);
   }
   return FOCAL_ESHAPE;
 }
@@ -158,14 +160,95 @@ int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtr
   return FOCAL_ESHAPE;
 }
 
+// local_rows: the caller's tensors start at the first owned row; the kernels index rows globally, so hand them the
+// (virtual) address of row 0 -- only owned rows are ever dereferenced.
 int fill_feats(const Plan& p, const float* const* feats, FeatPtrs& f) {
   if (!feats) return FOCAL_EINVAL;
+  const ptrdiff_t shift = p.local_rows ? (ptrdiff_t)p.seq0 * p.S * p.D : 0;
   for (int t = 0; t < p.nT; ++t) {
     if (!feats[t] || (reinterpret_cast<uintptr_t>(feats[t]) & 15)) return FOCAL_EINVAL;
-    f.x[t] = feats[t];
+    f.x[t] = feats[t] - shift;
   }
   for (int t = p.nT; t < kMaxT; ++t) f.x[t] = nullptr;
   return FOCAL_OK;
+}
+int fill_grads(const Plan& p, float* const* grads, GradPtrs& g) {
+  if (!grads) return FOCAL_EINVAL;
+  const ptrdiff_t shift = p.local_rows ? (ptrdiff_t)p.seq0 * p.S * p.D : 0;
+  for (int t = 0; t < kMaxT; ++t) g.g[t] = nullptr;
+  for (int t = 0; t < p.nT; ++t) {
+    if (!grads[t] || (reinterpret_cast<uintptr_t>(grads[t]) & 15)) return FOCAL_EINVAL;
+    g.g[t] = grads[t] - shift;
+  }
+  return FOCAL_OK;
+}
+PeerWs solo(void* ws) {
+  PeerWs pw{};
+  pw.rank = 0; pw.world = 1;
+  pw.ws[0] = static_cast<uint8_t*>(ws);
+  return pw;
+}
+
+int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st) {
+  int rc;
+  if (p.bpad != p.b || p.Bpad != p.B) {
+    zero_pad_kernel<<<64, 256, 0, st>>>(p, w);
+    if ((rc = cuda_ok("zero_pad_kernel"))) return rc;
+  }
+  const int vw = fast_row_vw(p, no_private);
+  bool fused_intra = false;
+  if (vw) {
+    fused_intra = (p.S == 2 || p.S == 4);
+    const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT + 4 * kMaxT) * sizeof(float);
+    if ((rc = launch_prologue_fast(vw, p, f, pw, w, smem, p.nblk1, fused_intra ? 1 : 0, st))) return rc;
+  } else {
+    if (pw.world > 1 || p.local_rows) return FOCAL_ESHAPE;      // the generic row kernels have no peer path
+    const size_t smem = (size_t)kRowsPerBlock * p.nT * p.D * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      if (cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return cuda_ok("cudaFuncSetAttribute(prologue_kernel)");
+      configured = smem;
+    }
+    prologue_kernel<<<p.nblk1, 32 * kRowsPerBlock, smem, st>>>(p, f, w);
+    if ((rc = cuda_ok("prologue_kernel"))) return rc;
+  }
+  if (!fused_intra && (p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p)) {
+    if (pw.world > 1 || p.local_rows) return FOCAL_ESHAPE;
+    const long warps = (long)p.nT * p.b;
+    intra_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(p, f, w);
+    if ((rc = cuda_ok("intra_kernel"))) return rc;
+  }
+  return FOCAL_OK;
+}
+
+int do_finalize(const Plan& p, int no_private, const float* const* feats, float* const* grads, const PeerWs& pw,
+                uint8_t* w, float* loss5, cudaStream_t st) {
+  int rc;
+  if (p.need_grad) {
+    FeatPtrs f;
+    if ((rc = fill_feats(p, feats, f))) return rc;
+    GradPtrs g;
+    if ((rc = fill_grads(p, grads, g))) return rc;
+    const int rows = (p.seq1 - p.seq0) * p.S;
+    const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, no_private) : 0;
+    if (vw) {
+      const size_t smem = ((size_t)8 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);
+      if ((rc = launch_finalize_fast(vw, p, f, g, w, smem, (rows + 3) / 4, st))) return rc;
+    } else {
+      const size_t smem = (size_t)kRowsPerBlock * (2 * p.nT + 1) * p.D * sizeof(float);
+      static size_t configured = 0;
+      if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+          return cuda_ok("cudaFuncSetAttribute(finalize_kernel)");
+        configured = smem;
+      }
+      finalize_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, smem, st>>>(p, f, g, w);
+      if ((rc = cuda_ok("finalize_kernel"))) return rc;
+    }
+  }
+  loss_reduce_kernel<<<1, 256, 0, st>>>(p, pw, w, loss5, p.nblk2, temporal_degenerate(p) ? 1 : 0);
+  return cuda_ok("loss_reduce_kernel");
 }
 
 }  // namespace
@@ -212,38 +295,11 @@ int focal_b200_prologue(const FocalCfg* cfg, const float* const* feats, void* ws
   Plan p;
   int rc = make_plan(cfg, p);
   if (rc) return rc;
+  if (p.local_rows) return FOCAL_EINVAL;               // local_rows belongs to focal_b200_loss_sharded
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
   FeatPtrs f;
   if ((rc = fill_feats(p, feats, f))) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint8_t* w = static_cast<uint8_t*>(ws);
-  if (p.bpad != p.b || p.Bpad != p.B) {
-    zero_pad_kernel<<<64, 256, 0, st>>>(p, w);
-    if ((rc = cuda_ok("zero_pad_kernel"))) return rc;
-  }
-  const int vw = fast_row_vw(p, cfg->no_private);
-  bool fused_intra = false;
-  if (vw) {
-    fused_intra = (p.S == 2 || p.S == 4);
-    const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT + 4 * kMaxT) * sizeof(float);
-    if ((rc = launch_prologue_fast(vw, p, f, w, smem, p.nblk1, fused_intra ? 1 : 0, st))) return rc;
-  } else {
-    const size_t smem = (size_t)kRowsPerBlock * p.nT * p.D * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      if (cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return cuda_ok("cudaFuncSetAttribute(prologue_kernel)");
-      configured = smem;
-    }
-    prologue_kernel<<<p.nblk1, 32 * kRowsPerBlock, smem, st>>>(p, f, w);
-    if ((rc = cuda_ok("prologue_kernel"))) return rc;
-  }
-  if (!fused_intra && (p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p)) {
-    const long warps = (long)p.nT * p.b;
-    intra_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(p, f, w);
-    if ((rc = cuda_ok("intra_kernel"))) return rc;
-  }
-  return FOCAL_OK;
+  return do_prologue(p, cfg->no_private, f, solo(ws), static_cast<uint8_t*>(ws), static_cast<cudaStream_t>(stream));
 }
 
 int focal_b200_nce_rowsum(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* stream) {
@@ -261,7 +317,7 @@ int focal_b200_nce_lse(const FocalCfg* cfg, void* ws, size_t ws_bytes, int all_r
   if (rc) return rc;
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
   if (!(p.terms & FOCAL_TERM_NCE)) return FOCAL_OK;
-  nce_lse_kernel<<<p.nblk2, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<uint8_t*>(ws), all_rows);
+  nce_lse_kernel<<<p.nblk2, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, solo(ws), static_cast<uint8_t*>(ws), all_rows);
   return cuda_ok("nce_lse_kernel");
 }
 
@@ -290,39 +346,11 @@ int focal_b200_finalize(const FocalCfg* cfg, const float* const* feats, void* ws
   Plan p;
   int rc = make_plan(cfg, p);
   if (rc) return rc;
+  if (p.local_rows) return FOCAL_EINVAL;
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
   if (!loss5) return FOCAL_EINVAL;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint8_t* w = static_cast<uint8_t*>(ws);
-  if (p.need_grad) {
-    FeatPtrs f;
-    if ((rc = fill_feats(p, feats, f))) return rc;
-    if (!grads) return FOCAL_EINVAL;
-    GradPtrs g;
-    for (int t = 0; t < kMaxT; ++t) g.g[t] = nullptr;
-    for (int t = 0; t < p.nT; ++t) {
-      if (!grads[t] || (reinterpret_cast<uintptr_t>(grads[t]) & 15)) return FOCAL_EINVAL;
-      g.g[t] = grads[t];
-    }
-    const int rows = (p.seq1 - p.seq0) * p.S;
-    const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, cfg->no_private) : 0;
-    if (vw) {
-      const size_t smem = ((size_t)8 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);
-      if ((rc = launch_finalize_fast(vw, p, f, g, w, smem, (rows + 3) / 4, st))) return rc;
-    } else {
-      const size_t smem = (size_t)kRowsPerBlock * (2 * p.nT + 1) * p.D * sizeof(float);
-      static size_t configured = 0;
-      if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-          return cuda_ok("cudaFuncSetAttribute(finalize_kernel)");
-        configured = smem;
-      }
-      finalize_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, smem, st>>>(p, f, g, w);
-      if ((rc = cuda_ok("finalize_kernel"))) return rc;
-    }
-  }
-  loss_reduce_kernel<<<1, 256, 0, st>>>(p, w, loss5, p.nblk2, temporal_degenerate(p) ? 1 : 0);
-  return cuda_ok("loss_reduce_kernel");
+  return do_finalize(p, cfg->no_private, feats, grads, solo(ws), static_cast<uint8_t*>(ws), loss5,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int focal_b200_loss(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,
@@ -334,6 +362,88 @@ int focal_b200_loss(const FocalCfg* cfg, const float* const* feats, void* ws, si
   if ((rc = focal_b200_nce_grad(cfg, ws, ws_bytes, stream))) return rc;
   if ((rc = focal_b200_temporal(cfg, ws, ws_bytes, stream))) return rc;
   return focal_b200_finalize(cfg, feats, ws, ws_bytes, loss5, grads, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// row-sharded path over NVLink peer memory
+// ---------------------------------------------------------------------------------------------------------
+int focal_b200_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!ptr || !handle || !bytes) return FOCAL_EINVAL;
+  void* d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) return cuda_ok("cudaMalloc(peer workspace)");
+  if (cudaMemset(d, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaFree(d);
+    return cuda_ok("cudaMemset(peer workspace)");
+  }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, d) != cudaSuccess) {
+    cudaFree(d);
+    return cuda_ok("cudaIpcGetMemHandle");
+  }
+  std::memcpy(handle, &h, 64);
+  *ptr = d;
+  return FOCAL_OK;
+}
+
+int focal_b200_peer_open(const unsigned char handle[64], void** ptr) {
+  if (!ptr || !handle) return FOCAL_EINVAL;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  void* d = nullptr;
+  if (cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return cuda_ok("cudaIpcOpenMemHandle");
+  *ptr = d;
+  return FOCAL_OK;
+}
+
+int focal_b200_peer_close(void* ptr) {
+  if (!ptr) return FOCAL_EINVAL;
+  return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? FOCAL_OK : cuda_ok("cudaIpcCloseMemHandle");
+}
+
+int focal_b200_peer_free(void* ptr) {
+  if (!ptr) return FOCAL_EINVAL;
+  return cudaFree(ptr) == cudaSuccess ? FOCAL_OK : cuda_ok("cudaFree(peer workspace)");
+}
+
+int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, const FocalPeers* peers, size_t ws_bytes,
+                            float* loss5, float* const* grads, void* stream) {
+  Plan p;
+  int rc = make_plan(cfg, p);
+  if (rc) return rc;
+  if (!peers || !loss5 || !p.local_rows) return FOCAL_EINVAL;
+  if (peers->world < 1 || peers->world > kMaxPeers || peers->rank < 0 || peers->rank >= peers->world) return FOCAL_EINVAL;
+  PeerWs pw{};
+  pw.rank = peers->rank; pw.world = peers->world;
+  for (int r = 0; r < pw.world; ++r) {
+    if ((rc = check_ws(p, peers->ws[r], ws_bytes))) return rc;
+    pw.ws[r] = static_cast<uint8_t*>(peers->ws[r]);
+  }
+  uint8_t* w = pw.ws[pw.rank];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FeatPtrs f;
+  if ((rc = fill_feats(p, feats, f))) return rc;
+  // phase 1: operands of the owned rows -> every workspace
+  if ((rc = do_prologue(p, cfg->no_private, f, pw, w, st))) return rc;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(p, pw);
+  if ((rc = cuda_ok("peer_barrier_kernel"))) return rc;
+  // phase 2: row sums of the owned rows -> every workspace
+  if (p.terms & FOCAL_TERM_NCE) {
+    if ((rc = launch_nce<NCE_FWD>(p, w, st))) return rc;
+    nce_lse_kernel<<<p.nblk2, 256, 0, st>>>(p, pw, w, 0);
+    if ((rc = cuda_ok("nce_lse_kernel"))) return rc;
+    if (p.need_grad) {
+      peer_barrier_kernel<<<1, 32, 0, st>>>(p, pw);
+      if ((rc = cuda_ok("peer_barrier_kernel"))) return rc;
+      if ((rc = launch_nce<NCE_BWD>(p, w, st))) return rc;
+    }
+  }
+  if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p)) {
+    rc = p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp);
+    if (rc) return rc;
+  }
+  // phase 3: gradients of the owned rows; loss partials all-reduced inside loss_reduce_kernel (third barrier)
+  return do_finalize(p, cfg->no_private, feats, grads, pw, w, loss5, st);
 }
 
 }  // extern "C"

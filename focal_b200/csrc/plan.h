@@ -54,6 +54,7 @@ struct Plan {
   // block is cut into; piece k of a block accumulates into the k-th copy of the output buffers
   int32_t sk_nce, sk_tmp, np_nce, np_tmp, grid_tmp, grid_nce[5];
   int32_t in_rb, in_bs;                                 // row-blocked inputs: rows per block, block stride (floats)
+  int32_t local_rows;                                   // sharded path: the prologue handles the owned rows only
   float T, margin, w_shared, w_private, w_orth, w_rank;
   float alpha;                                          // sqrt(log2(e)/T): operand pre-scale, Gram = log2-domain logit
   OpDesc ops[kMaxOps];
@@ -78,8 +79,17 @@ struct Plan {
   uint64_t dz2_delta, dx2_delta, rho2_delta, cnt2_delta;   // byte distance between the buffers of consecutive pieces
   uint64_t flag_tmp_off;   // int32 [2M][Bpad/128]: number of secondary pieces of the row block (temporal)
   uint64_t flag_nce_off;   // int32 [nProb][S][2][bpad/128]: same for the InfoNCE backward pass
+  uint64_t bar_off;        // uint32 [16]: [r] = last barrier epoch rank r announced here, [8] = own epoch counter
+  uint64_t lossx_off;      // double [kMaxPeers][8]: loss partials of every rank (sharded path)
   uint64_t total_bytes;
   int32_t nblk1, nblk2, nitems3;
+};
+
+// Workspaces of all ranks of a row-sharded job as mapped into this process (plain launches: world = 1, ws[0] = own).
+constexpr int kMaxPeers = 8;
+struct PeerWs {
+  int32_t rank, world;
+  uint8_t* ws[kMaxPeers];
 };
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -156,6 +166,8 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.in_rb = c.in_block_rows > 0 ? c.in_block_rows : c.B;
   p.in_bs = c.in_block_rows > 0 ? c.in_block_stride : 0;
   if (p.in_rb % c.S || c.B % p.in_rb) return FOCAL_EINVAL;
+  p.local_rows = c.local_rows ? 1 : 0;
+  if (p.local_rows && c.in_block_rows > 0) return FOCAL_EINVAL;
   p.num_sms = num_sms;
   p.T = c.temperature; p.margin = c.margin;
   p.w_shared = c.w_shared; p.w_private = c.w_private; p.w_orth = c.w_orth; p.w_rank = c.w_rank;
@@ -257,13 +269,15 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.cnt_off = take_n((uint64_t)p.nT * p.bpad * 4, p.np_tmp, &p.cnt2_delta);
   p.flag_tmp_off = take((uint64_t)p.nT * (p.Bpad / kTileM) * 4);
   p.flag_nce_off = take((uint64_t)p.nProb * p.S * 2 * (p.bpad / kTileM) * 4);
-  p.nblk1 = (p.B + kRowsPerBlock - 1) / kRowsPerBlock;
+  p.nblk1 = ((p.local_rows ? (p.seq1 - p.seq0) * p.S : p.B) + kRowsPerBlock - 1) / kRowsPerBlock;
   p.nblk2 = (int32_t)((rowsNce * 2 * p.nProb + 255) / 256);
   p.nitems3 = p.np_tmp * p.nT * (p.Bpad / kTileM);   // one hinge-partial slot per piece of a row block
   p.part1_off = take((uint64_t)p.nblk1 * 4 * 4);
   p.part2_off = take((uint64_t)p.nblk2 * 2 * 4);
   p.part3_off = take((uint64_t)p.nitems3 * 4);
   p.lossd_off = take(8 * 8);
+  p.bar_off = take(16 * 4);
+  p.lossx_off = take((uint64_t)kMaxPeers * 8 * 8);
   p.total_bytes = off;
   return FOCAL_OK;
 }

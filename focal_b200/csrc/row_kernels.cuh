@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan
 // K2r: reduce the column-split row sums of the owned rows, publish r, 1/r and the log-sum partials.
 // all_rows != 0: only rebuild 1/r for every valid row from r (after the multi-GPU exchange of r).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws,
+__global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Plan p,
+                                                      const __grid_constant__ PeerWs pw, uint8_t* __restrict__ ws,
                                                       int all_rows) {
   __shared__ float red[8][2];
   const long n = (long)p.nProb * p.S * 2 * p.bpad;
@@ -259,8 +260,11 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
       const float* rp = reinterpret_cast<const float*>(ws + p.rpart_off);
       float r = 0.f;
       for (int sp = 0; sp < p.nsplit_fwd; ++sp) r += rp[(long)sp * n + e];
-      rsum[e] = r;
-      rinv[e] = 1.f / r;
+      // row-sharded jobs: every rank needs r and 1/r of every row -> store into all workspaces (pw.world == 1 otherwise)
+      for (int rk = 0; rk < pw.world; ++rk) {
+        reinterpret_cast<float*>(pw.ws[rk] + p.rsum_off)[e] = r;
+        reinterpret_cast<float*>(pw.ws[rk] + p.rinv_off)[e] = 1.f / r;
+      }
       const float lg = logf(r) / ((float)p.S * (float)(2 * p.b));          // ln sum_{j != k} exp(s_kj) / (S N)
       if (p.probs[q].kind == 0) ls = lg; else lp = lg;
     }
@@ -442,7 +446,49 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------
 // K5: deterministic reduction of the per-block partials -> {total, shared, private, orth, temporal}
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws,
+// Device-side barrier over the ranks of a row-sharded job.  Called by ONE block of >= kMaxPeers threads per rank, all
+// ranks in step.  Rank r announces epoch e by storing it into slot r of every peer's flag array (release, system
+// scope: everything this rank's earlier kernels and this block wrote to peer memory is visible before the flag) and
+// waits until every peer has announced e in its own array.  Bounded spin: a lost rank traps instead of hanging.
+__device__ __forceinline__ void peer_barrier(const Plan& p, const PeerWs& pw) {
+  __shared__ uint32_t epoch_sh;
+  uint32_t* mine = reinterpret_cast<uint32_t*>(pw.ws[pw.rank] + p.bar_off);
+  __syncthreads();
+  if (threadIdx.x == 0) { epoch_sh = mine[8] + 1; mine[8] = epoch_sh; }
+  __syncthreads();
+  const uint32_t e = epoch_sh;
+  if ((int)threadIdx.x < pw.world) {
+    __threadfence_system();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(pw.ws[threadIdx.x] + p.bar_off) + pw.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(e) : "memory");
+    const uint32_t* src = mine + threadIdx.x;
+    uint64_t t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      if ((int32_t)(v - e) >= 0) break;
+      if ((spins & 1023) == 1023) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 20000000000ull) {          // 20 s: a rank died or fell out of step
+          printf("focal_b200: peer barrier timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n", pw.rank,
+                 (int)threadIdx.x, e, v);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ Plan p,
+                                                          const __grid_constant__ PeerWs pw) {
+  peer_barrier(p, pw);
+}
+
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant__ Plan p,
+                                                          const __grid_constant__ PeerWs pw, uint8_t* __restrict__ ws,
                                                           float* __restrict__ loss5, int nce_blocks_valid,
                                                           int temporal_nan) {
   __shared__ double red[256];
@@ -475,6 +521,20 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant_
     }
     out[a] = red[0];
     __syncthreads();
+  }
+  if (pw.world > 1) {
+    // all-reduce over the ranks: publish the partial sums of the owned rows, barrier, add them in rank order
+    if ((int)threadIdx.x < pw.world) {
+      double* slot = reinterpret_cast<double*>(pw.ws[threadIdx.x] + p.lossx_off) + pw.rank * 8;
+      for (int a = 0; a < 4; ++a) slot[a] = out[a];
+    }
+    peer_barrier(p, pw);
+    const volatile double* all = reinterpret_cast<const volatile double*>(ws + p.lossx_off);
+    for (int a = 0; a < 4; ++a) {
+      double s = 0;
+      for (int r = 0; r < pw.world; ++r) s += all[r * 8 + a];
+      out[a] = s;
+    }
   }
   if (threadIdx.x == 0) {
     if (temporal_nan && (p.terms & FOCAL_TERM_TEMPORAL)) out[3] = __longlong_as_double(0x7ff8000000000000LL);

@@ -74,15 +74,19 @@ __device__ __forceinline__ void stage_rows(const Plan& p, const FeatPtrs& f, int
 template <int VW>
 __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constant__ Plan p,
                                                             const __grid_constant__ FeatPtrs f,
+                                                            const __grid_constant__ PeerWs pw,
                                                             uint8_t* __restrict__ ws, int fuse_intra) {
+  // Row-sharded jobs (p.local_rows): only the owned rows are processed, and everything the Gram kernels of ANY rank
+  // read (operands, squared norms, m_II) is stored into every rank's workspace (pw.ws[r], NVLink peer stores).
   extern __shared__ float smem_f[];
   __shared__ float red[4][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 4 + warp;
+  const int row_lo = p.local_rows ? p.seq0 * p.S : 0, row_hi = p.local_rows ? p.seq1 * p.S : p.B;
+  const int i = row_lo + blockIdx.x * 4 + warp;
   const int D = p.D, d = p.d;
   float* xs = smem_f + (size_t)warp * p.nT * D;
   float acc_orth = 0.f, acc_ps = 0.f, acc_pp = 0.f;
-  const bool live = i < p.B;
+  const bool live = i < row_hi;
   if (live) stage_rows(p, f, i, xs, lane);
   __syncthreads();
   if (live) {
@@ -106,19 +110,24 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
         float zs[VW], zp[VW];
 #pragma unroll
         for (int e = 0; e < VW; ++e) { zs[e] = sh[e] * fa; zp[e] = pr[e] * fb2; }
-        st_operand<VW>(ws + p.ops[2 * t].off, rowsNce, rowN, c0, zs);
-        st_operand<VW>(ws + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp);
-        if (VW & 1) {
-          // d = 32 or 96: the last K block is half full -- its 32 padding columns must read as zeros
-          const float z1[1] = {0.f};
-          st_operand<1>(ws + p.ops[2 * t].off, rowsNce, rowN, d + lane, z1);
-          st_operand<1>(ws + p.ops[2 * t + 1].off, rowsNce, rowN, d + lane, z1);
+        for (int r = 0; r < pw.world; ++r) {
+          uint8_t* w = pw.ws[r];
+          st_operand<VW>(w + p.ops[2 * t].off, rowsNce, rowN, c0, zs);
+          st_operand<VW>(w + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp);
+          if (VW & 1) {
+            // d = 32 or 96: the last K block is half full -- its 32 padding columns must read as zeros
+            const float z1[1] = {0.f};
+            st_operand<1>(w + p.ops[2 * t].off, rowsNce, rowN, d + lane, z1);
+            st_operand<1>(w + p.ops[2 * t + 1].off, rowsNce, rowN, d + lane, z1);
+          }
         }
       }
       if (p.terms & FOCAL_TERM_TEMPORAL) {
-        uint8_t* xt = ws + p.xt_off + (uint64_t)t * p.kbFull * p.Bpad * 128;
-        st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, c0, sh);
-        st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, d + c0, pr);
+        for (int r = 0; r < pw.world; ++r) {
+          uint8_t* xt = pw.ws[r] + p.xt_off + (uint64_t)t * p.kbFull * p.Bpad * 128;
+          st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, c0, sh);
+          st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, d + c0, pr);
+        }
         float sq = 0.f;
 #pragma unroll
         for (int e = 0; e < VW; ++e) {
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
           sq = fmaf(r0, r0, fmaf(r1, r1, sq));
         }
         sq = warp_sum(sq);
-        if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
+        if (lane < pw.world) reinterpret_cast<float*>(pw.ws[lane] + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
       }
     }
     __syncwarp();
@@ -207,7 +216,8 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
     const float* rs = smem_f + (size_t)4 * p.nT * D + 4 * 2 * kMaxT;
     float m = 0.f;
     for (int j = 0; j < S; ++j) m += rs[(w0 + j) * kMaxT + lane];
-    reinterpret_cast<float*>(ws + p.mintra_off)[(uint64_t)lane * p.Bpad + i] = m / (float)(S * S - S);
+    for (int r = 0; r < pw.world; ++r)
+      reinterpret_cast<float*>(pw.ws[r] + p.mintra_off)[(uint64_t)lane * p.Bpad + i] = m / (float)(S * S - S);
   }
 }
 

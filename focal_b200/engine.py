@@ -6,10 +6,16 @@ There is no CPU path and no PyTorch fallback: inputs that are not CUDA tensors r
 
 Multi-GPU: R ranks each hold B/R rows (whole sequences) of every feature tensor.  The
 result equals the single-GPU loss on the rank-major concatenation; every rank gets the global scalar and
-d loss_global / d (its own rows).  Exchange steps: one all-gather of the raw features (operands are then
-rebuilt bit-identically on every rank), one all-gather of the InfoNCE row sums (because logits are
-symmetric, a rank that knows every row sum can form P_kj + P_jk for its own rows -- no gradient
-reduce-scatter is needed), one all-reduce of the five loss partials.
+d loss_global / d (its own rows).  Because logits are symmetric, a rank that knows every row sum can form
+P_kj + P_jk for its own rows -- no gradient reduce-scatter is needed.  Two implementations:
+
+* peer path (default on one NVSwitch box, ``focal_b200_loss_sharded``): the workspaces are mapped into every
+  process (CUDA IPC); the prologue of each rank handles its own rows and stores their bf16 operands straight into all
+  workspaces over NVLink, row sums and loss partials travel the same way, three device-side barriers order the
+  phases.  No collective library call on the data path, so the whole step is one CUDA graph.
+* collective path (any process group; also what the CPU ``gloo`` tests drive): all-gather of the raw features
+  (operands rebuilt bit-identically on every rank), all-gather of the InfoNCE row sums, all-reduce of the five
+  loss partials.
 """
 from __future__ import annotations
 
@@ -54,6 +60,7 @@ class CudaBackend:
         self.lib = _cabi.load()          # raises ImportError when the extension is missing -- no fallback
         self._ws: Dict[tuple, Tuple[torch.Tensor, torch.Tensor, _cabi.FocalWsInfo]] = {}
         self._plans: Dict[tuple, tuple] = {}
+        self._peers: Dict[tuple, Optional[tuple]] = {}
 
     # -- helpers ------------------------------------------------------------------------------------
     def _cfg(self, hp: FocalHyper, B: int, D: int, need_grad: bool, seq: Tuple[int, int]) -> _cabi.FocalCfg:
@@ -138,6 +145,77 @@ class CudaBackend:
         return loss5, grads
 
 
+    # -- row-sharded path over NVLink peer memory ------------------------------------------------------
+    @staticmethod
+    def peer_eligible(hp: FocalHyper, D: int, world: int) -> bool:
+        """Shapes focal_b200_loss_sharded handles (the vectorised row kernels with fused intra-sequence means)."""
+        d = D // 2
+        return (world <= _cabi.FOCAL_MAX_PEERS and not hp.no_private and D % 2 == 0 and d % 32 == 0 and 32 <= d <= 128
+                and hp.seq_len in (2, 4))
+
+    def peer_setup(self, cfg: _cabi.FocalCfg, group, dev: torch.device):
+        """Collective over ``group``: allocate this rank's workspace, exchange IPC handles, map the peers'.
+        Returns (FocalPeers, total_bytes) or None when any rank could not (then every rank gets None)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        key = (cfg.B, cfg.S, cfg.M, cfg.D, cfg.no_private, cfg.terms, world, dev.index)
+        if key in self._peers:
+            return self._peers[key]
+        lib = self.lib
+        info = _cabi.FocalWsInfo()
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ok = lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info)) == 0
+        ok = ok and lib.focal_b200_peer_alloc(info.total_bytes, C.byref(own), handle) == 0
+        got: List[Optional[tuple]] = [None] * world
+        dist.all_gather_object(got, (bool(ok), handle.raw, int(info.total_bytes)), group=group)
+        ok = all(g[0] for g in got) and len({g[2] for g in got}) == 1
+        peers = _cabi.FocalPeers(rank=rank, world=world)
+        opened = []
+        if ok:
+            for r in range(world):
+                if r == rank:
+                    peers.ws[r] = own.value
+                    continue
+                p = C.c_void_p()
+                if lib.focal_b200_peer_open(got[r][1], C.byref(p)) != 0:
+                    ok = False
+                    break
+                opened.append(p)
+                peers.ws[r] = p.value
+        flags: List[Optional[bool]] = [None] * world
+        dist.all_gather_object(flags, bool(ok), group=group)
+        if not all(flags):
+            for p in opened:
+                lib.focal_b200_peer_close(p)
+            if own.value:
+                lib.focal_b200_peer_free(own)
+            self._peers[key] = None
+            return None
+        dist.barrier(group=group)            # nobody starts storing into a workspace that is not mapped / zeroed yet
+        self._peers[key] = (peers, int(info.total_bytes), opened, own)
+        return self._peers[key]
+
+    def run_sharded(self, hp: FocalHyper, local: Sequence[torch.Tensor], B: int, seq: Tuple[int, int], need_grad: bool,
+                    peer) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
+        """local: 2M fp32 CUDA tensors holding the owned rows.  Returns (GLOBAL loss5, grads of the owned rows)."""
+        x0 = local[0]
+        D, dev = x0.shape[1], x0.device
+        cfg = self._cfg(hp, B, D, need_grad, seq)
+        cfg.local_rows = 1
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        fptr = _cabi.ptr_array([t.data_ptr() for t in local])
+        loss5 = torch.empty(5, dtype=torch.float32, device=dev)
+        grads = gptr = None
+        if need_grad:
+            grads = [torch.empty_like(t) for t in local]
+            gptr = _cabi.ptr_array([g.data_ptr() for g in grads])
+        _cabi.check(self.lib.focal_b200_loss_sharded(C.byref(cfg), fptr, C.byref(peer[0]), C.c_size_t(peer[1]),
+                                                     C.c_void_p(loss5.data_ptr()), gptr, stream),
+                    "focal_b200_loss_sharded")
+        return loss5, grads
+
+
 class FocalEngine:
     """Validates inputs, shards rows over the process group, drives a backend."""
 
@@ -150,6 +228,9 @@ class FocalEngine:
         import os
         self.use_cuda_graph = (use_cuda_graph and getattr(self.backend, "name", "") == "cuda"
                                and os.environ.get("FOCAL_B200_CUDA_GRAPH", "1") != "0")
+        # row-sharded jobs: exchange over NVLink peer memory instead of collectives (one box, <= 8 ranks, CUDA backend)
+        self.use_peer = (getattr(self.backend, "name", "") == "cuda" and hasattr(self.backend, "run_sharded")
+                         and os.environ.get("FOCAL_B200_PEER", "1") != "0")
         self._graphs: Dict[tuple, tuple] = {}
         self._seen: Dict[tuple, int] = {}
         self.graph_replays = 0
@@ -230,6 +311,12 @@ class FocalEngine:
         import torch.distributed as dist
         Bl, D = local[0].shape
         nT = len(local)
+        if self.use_peer and self.backend.peer_eligible(hp, D, world):
+            B = world * Bl
+            seq = shard_sequences(B // hp.seq_len, world, rank)
+            peer = self.backend.peer_setup(self.backend._cfg(hp, B, D, need_grad, seq), self.group, local[0].device)
+            if peer is not None:
+                return self.backend.run_sharded(hp, local, B, seq, need_grad, peer)
         # (1) all-gather the raw features: per-rank [2M, Bl, D] -> [R, 2M, Bl, D]
         mine = torch.stack(local, dim=0)
         gathered = torch.empty((world * nT, Bl, D), dtype=mine.dtype, device=mine.device)

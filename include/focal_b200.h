@@ -60,7 +60,9 @@ typedef struct FocalCfg {
    * in_block_rows == 0 means plain contiguous [B, D] tensors.  Sequences never straddle blocks. */
   int32_t in_block_rows;
   int32_t in_block_stride;
-  int32_t reserved[1];
+  /* local_rows != 0 (only with focal_b200_loss_sharded): feats[t] / grads[t] hold just the owned rows
+   * [seq_begin*S, seq_end*S) of the B-row tensors, i.e. what a rank of a row-sharded job has in hand. */
+  int32_t local_rows;
 } FocalCfg;
 
 /* Byte offsets (from the workspace base) and extents of the buffers a host may need to look at:
@@ -118,6 +120,35 @@ int focal_b200_finalize(const FocalCfg* cfg, const float* const* feats, void* ws
 /* All stages in order on one stream (single-GPU call of FOCALLoss.forward + backward). */
 int focal_b200_loss(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,
                     float* const* grads, void* stream);
+
+/*
+ * Row-sharded multi-GPU path over NVLink peer memory (one process per GPU, all on one NVSwitch box).  The reference is
+ * single-GPU; semantics: R ranks each hold B/R rows (whole sequences, rank-major); every rank gets the
+ * loss of the global batch and d loss_global / d (its own rows).  No collective library on the data path: each rank
+ * allocates its workspace with focal_b200_peer_alloc, ships the 64-byte handle to the other ranks (any host channel),
+ * maps theirs with focal_b200_peer_open, and the kernels exchange what they produce with plain stores into the
+ * peers' workspaces: the prologue runs on the owned rows only and writes their bf16 operands into every workspace;
+ * nce_lse publishes the owned rows' row sums the same way; the loss partials are all-reduced inside the last kernel.
+ * Three device-side barriers (flags in the workspaces, bounded spin, trap on timeout) order the phases.
+ */
+#define FOCAL_MAX_PEERS 8
+typedef struct FocalPeers {
+  int32_t rank, world;
+  void* ws[FOCAL_MAX_PEERS];   /* this process's mapping of every rank's workspace; ws[rank] is its own */
+} FocalPeers;
+
+/* cudaMalloc + zero-fill + cudaIpcGetMemHandle; the workspace must come from here so that peers can map it. */
+int focal_b200_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int focal_b200_peer_open(const unsigned char handle[64], void** ptr);
+int focal_b200_peer_close(void* ptr);
+int focal_b200_peer_free(void* ptr);
+
+/* All stages of one rank's share (cfg->seq_begin/seq_end = owned sequences, cfg->local_rows = 1, cfg identical on all
+ * ranks otherwise).  Every rank must call it the same number of times, in step; ws_bytes as for focal_b200_loss.
+ * loss5 receives the GLOBAL loss.  Returns FOCAL_ESHAPE for shapes off the vectorised row-kernel path (D/2 a multiple
+ * of 32, S in {2, 4}, no noPrivate) -- callers then use the staged functions with a collective library. */
+int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, const FocalPeers* peers, size_t ws_bytes,
+                            float* loss5, float* const* grads, void* stream);
 
 /* Bring-up probe: runs `ksteps` tcgen05.mma (M=128) on caller-provided shared-memory images and returns
  * the 128 x ncols fp32 accumulator.  Used by tests to pin the descriptor encodings on real hardware. */

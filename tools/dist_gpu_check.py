@@ -29,22 +29,26 @@ def main():
         full5, fullg = single.loss_and_grads({m: v.to(dev) for m, v in f1.items()},
                                              {m: v.to(dev) for m, v in f2.items()}, True)
         full5, fullg = full5.clone(), [g.clone() for g in fullg]
-        sharded = FocalEngine(hp, process_group=dist.group.WORLD)
         Bl = B // world
         l1 = {m: v[rank * Bl:(rank + 1) * Bl].to(dev) for m, v in f1.items()}
         l2 = {m: v[rank * Bl:(rank + 1) * Bl].to(dev) for m, v in f2.items()}
-        loss5, grads = sharded.loss_and_grads(l1, l2, True)
-        torch.cuda.synchronize()
-        # total loss relative; the sub-loss sums are compared with an absolute floor (at T = 0.07 the InfoNCE parts are
-        # ~1e-3 differences of ~13-sized fp32 sums, so their last bits depend on the per-rank summation split)
-        lerr = max(float((loss5[0] - full5[0]).abs() / full5[0].abs()),
-                   float(((loss5[1:] - full5[1:]).abs() / full5[1:].abs().clamp_min(1.0)).max()))
-        gerr = max(float((g - fg[rank * Bl:(rank + 1) * Bl]).norm() / fg[rank * Bl:(rank + 1) * Bl].norm())
-                   for g, fg in zip(grads, fullg))
-        good = lerr < 2e-6 and gerr < 1e-5
-        ok = ok and good
-        print(f"[rank {rank}/{world}] B={B} D={D} M={len(mods)}: loss5 rel diff {lerr:.2e}, grad rel diff {gerr:.2e} "
-              f"{'OK' if good else 'MISMATCH'}", flush=True)
+        for mode in ("peer", "collective"):
+            os.environ["FOCAL_B200_PEER"] = "1" if mode == "peer" else "0"
+            sharded = FocalEngine(hp, process_group=dist.group.WORLD)
+            for _ in range(4):                      # eager, capture, replays: barrier epochs must stay in step
+                loss5, grads = sharded.loss_and_grads(l1, l2, True)
+            torch.cuda.synchronize()
+            # total loss relative; the sub-loss sums are compared with an absolute floor (at T = 0.07 the InfoNCE parts
+            # are ~1e-3 differences of ~13-sized fp32 sums, so their last bits depend on the per-rank summation split)
+            lerr = max(float((loss5[0] - full5[0]).abs() / full5[0].abs()),
+                       float(((loss5[1:] - full5[1:]).abs() / full5[1:].abs().clamp_min(1.0)).max()))
+            gerr = max(float((g - fg[rank * Bl:(rank + 1) * Bl]).norm() / fg[rank * Bl:(rank + 1) * Bl].norm())
+                       for g, fg in zip(grads, fullg))
+            good = lerr < 2e-6 and gerr < 1e-5
+            ok = ok and good
+            print(f"[rank {rank}/{world}] {mode:10s} B={B} D={D} M={len(mods)}: loss5 rel diff {lerr:.2e}, "
+                  f"grad rel diff {gerr:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+            sharded._graphs.clear()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
