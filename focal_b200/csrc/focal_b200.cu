@@ -49,6 +49,12 @@ int cuda_ok(const char* what) {
 
 bool temporal_degenerate(const Plan& p) { return p.b <= 1 || p.S <= 1; }
 
+// blocks of nce_lse_kernel: the owned (problem, position, side, sequence) entries, or every entry when all_rows
+int lse_blocks(const Plan& p, int all_rows) {
+  if (all_rows) return p.nblk2;
+  return (int)(((long)p.nProb * p.S * 2 * (p.seq1 - p.seq0) + 255) / 256);
+}
+
 template <int MODE, int KB, int SEQ>
 int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int grid) {
   using G = GramCfg<MODE, KB, SEQ>;
@@ -247,7 +253,7 @@ int do_finalize(const Plan& p, int no_private, const float* const* feats, float*
       if ((rc = cuda_ok("finalize_kernel"))) return rc;
     }
   }
-  loss_reduce_kernel<<<1, 256, 0, st>>>(p, pw, w, loss5, p.nblk2, temporal_degenerate(p) ? 1 : 0);
+  loss_reduce_kernel<<<1, 256, 0, st>>>(p, pw, w, loss5, lse_blocks(p, 0), temporal_degenerate(p) ? 1 : 0);
   return cuda_ok("loss_reduce_kernel");
 }
 
@@ -317,7 +323,7 @@ int focal_b200_nce_lse(const FocalCfg* cfg, void* ws, size_t ws_bytes, int all_r
   if (rc) return rc;
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
   if (!(p.terms & FOCAL_TERM_NCE)) return FOCAL_OK;
-  nce_lse_kernel<<<p.nblk2, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, solo(ws), static_cast<uint8_t*>(ws), all_rows);
+  nce_lse_kernel<<<lse_blocks(p, all_rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, solo(ws), static_cast<uint8_t*>(ws), all_rows);
   return cuda_ok("nce_lse_kernel");
 }
 
@@ -427,20 +433,22 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   if ((rc = do_prologue(p, cfg->no_private, f, pw, w, st))) return rc;
   peer_barrier_kernel<<<1, 32, 0, st>>>(p, pw);
   if ((rc = cuda_ok("peer_barrier_kernel"))) return rc;
-  // phase 2: row sums of the owned rows -> every workspace
-  if (p.terms & FOCAL_TERM_NCE) {
+  // phase 2: row sums of the owned rows -> every workspace.  The temporal launch needs nothing from the peers beyond
+  // phase 1, so it runs between the stores and the barrier that waits for them: the barrier finds everybody there.
+  const bool nce = (p.terms & FOCAL_TERM_NCE) != 0;
+  if (nce) {
     if ((rc = launch_nce<NCE_FWD>(p, w, st))) return rc;
-    nce_lse_kernel<<<p.nblk2, 256, 0, st>>>(p, pw, w, 0);
+    nce_lse_kernel<<<lse_blocks(p, 0), 256, 0, st>>>(p, pw, w, 0);
     if ((rc = cuda_ok("nce_lse_kernel"))) return rc;
-    if (p.need_grad) {
-      peer_barrier_kernel<<<1, 32, 0, st>>>(p, pw);
-      if ((rc = cuda_ok("peer_barrier_kernel"))) return rc;
-      if ((rc = launch_nce<NCE_BWD>(p, w, st))) return rc;
-    }
   }
   if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p)) {
     rc = p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp);
     if (rc) return rc;
+  }
+  if (nce && p.need_grad) {
+    peer_barrier_kernel<<<1, 32, 0, st>>>(p, pw);
+    if ((rc = cuda_ok("peer_barrier_kernel"))) return rc;
+    if ((rc = launch_nce<NCE_BWD>(p, w, st))) return rc;
   }
   // phase 3: gradients of the owned rows; loss partials all-reduced inside loss_reduce_kernel (third barrier)
   return do_finalize(p, cfg->no_private, feats, grads, pw, w, loss5, st);

@@ -247,16 +247,19 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
                                                       int all_rows) {
   __shared__ float red[8][2];
   const long n = (long)p.nProb * p.S * 2 * p.bpad;
-  const long e = (long)blockIdx.x * 256 + threadIdx.x;
   float ls = 0.f, lp = 0.f;
-  if (e < n) {
-    const int k = (int)(e % p.bpad);
-    const int q = (int)(e / ((long)p.S * 2 * p.bpad));
-    float* rsum = reinterpret_cast<float*>(ws + p.rsum_off);
-    float* rinv = reinterpret_cast<float*>(ws + p.rinv_off);
-    if (all_rows) {
-      if (k < p.b) rinv[e] = 1.f / rsum[e];
-    } else if (k >= p.seq0 && k < p.seq1) {
+  if (all_rows) {
+    const long e = (long)blockIdx.x * 256 + threadIdx.x;
+    if (e < n && (int)(e % p.bpad) < p.b)
+      reinterpret_cast<float*>(ws + p.rinv_off)[e] = 1.f / reinterpret_cast<const float*>(ws + p.rsum_off)[e];
+  } else {
+    // the grid covers the owned sequences only: thread -> ((problem, position, side), k in [seq0, seq1))
+    const int per = p.seq1 - p.seq0;
+    const long t = (long)blockIdx.x * 256 + threadIdx.x;
+    if (t < (long)p.nProb * p.S * 2 * per) {
+      const long grp = t / per;
+      const long e = grp * p.bpad + p.seq0 + (int)(t - grp * per);
+      const int q = (int)(grp / (p.S * 2));
       const float* rp = reinterpret_cast<const float*>(ws + p.rpart_off);
       float r = 0.f;
       for (int sp = 0; sp < p.nsplit_fwd; ++sp) r += rp[(long)sp * n + e];

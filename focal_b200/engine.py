@@ -151,7 +151,7 @@ class CudaBackend:
         """Shapes focal_b200_loss_sharded handles (the vectorised row kernels with fused intra-sequence means)."""
         d = D // 2
         return (world <= _cabi.FOCAL_MAX_PEERS and not hp.no_private and D % 2 == 0 and d % 32 == 0 and 32 <= d <= 128
-                and hp.seq_len in (2, 4))
+                and hp.seq_len in (1, 2, 4))
 
     def peer_setup(self, cfg: _cabi.FocalCfg, group, dev: torch.device):
         """Collective over ``group``: allocate this rank's workspace, exchange IPC handles, map the peers'.

@@ -146,7 +146,7 @@ int focal_b200_peer_free(void* ptr);
 /* All stages of one rank's share (cfg->seq_begin/seq_end = owned sequences, cfg->local_rows = 1, cfg identical on all
  * ranks otherwise).  Every rank must call it the same number of times, in step; ws_bytes as for focal_b200_loss.
  * loss5 receives the GLOBAL loss.  Returns FOCAL_ESHAPE for shapes off the vectorised row-kernel path (D/2 a multiple
- * of 32, S in {2, 4}, no noPrivate) -- callers then use the staged functions with a collective library. */
+ * of 32, S in {1, 2, 4}, no noPrivate) -- callers then use the staged functions with a collective library. */
 int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, const FocalPeers* peers, size_t ws_bytes,
                             float* loss5, float* const* grads, void* stream);
 

@@ -357,13 +357,14 @@ def test_row_blocked_inputs_match_contiguous():
         assert torch.equal(a, b2)
 
 
-@pytest.mark.parametrize("world,B,D,mods,T,need_grad", [
-    (1, 512, 256, ("seismic", "audio"), 0.5, True),
-    (2, 2048, 256, ("seismic", "audio"), 0.5, True),
-    (4, 1536, 128, ("acc", "gyr", "mag"), 0.07, True),
-    (2, 1024, 64, ("seismic", "audio"), 0.5, False),
+@pytest.mark.parametrize("world,B,D,mods,T,need_grad,S", [
+    (1, 512, 256, ("seismic", "audio"), 0.5, True, 4),
+    (2, 2048, 256, ("seismic", "audio"), 0.5, True, 4),
+    (4, 1536, 128, ("acc", "gyr", "mag"), 0.07, True, 4),
+    (2, 1024, 64, ("seismic", "audio"), 0.5, False, 2),
+    (2, 1024, 128, ("seismic", "audio"), 0.5, True, 1),       # "global" InfoNCE (cfg 4 shape): temporal term is NaN
 ])
-def test_sharded_peer_path_on_one_gpu(world, B, D, mods, T, need_grad):
+def test_sharded_peer_path_on_one_gpu(world, B, D, mods, T, need_grad, S):
     """focal_b200_loss_sharded (prologue of the owned rows storing into every rank's workspace, device-side
     barriers, in-kernel loss all-reduce) with all `world` ranks emulated on ONE GPU: one workspace and one stream per
     rank, the barrier kernels of the ranks spin concurrently.  Every rank must report the single-GPU loss and the
@@ -372,7 +373,6 @@ def test_sharded_peer_path_on_one_gpu(world, B, D, mods, T, need_grad):
     import ctypes as C
     from focal_b200 import _cabi
     from focal_b200.engine import CudaBackend, FocalHyper, shard_sequences
-    S = 4
     f1, f2 = fo.make_structured(11, list(mods), B, D, S)
     hp = FocalHyper(tuple(mods), S, T, 1.0, 1.0, 1.0, 3.0, 5.0)
     be = CudaBackend()
@@ -416,7 +416,8 @@ def test_sharded_peer_path_on_one_gpu(world, B, D, mods, T, need_grad):
                 _cabi.check(rc, "focal_b200_loss_sharded")
             torch.cuda.synchronize()
             for r, (loss5, grads) in enumerate(outs):
-                assert torch.allclose(loss5, want5, rtol=2e-6, atol=1e-6), (step, r, loss5.tolist(), want5.tolist())
+                assert torch.allclose(loss5, want5, rtol=2e-6, atol=1e-6, equal_nan=True), \
+                    (step, r, loss5.tolist(), want5.tolist())
                 if need_grad:
                     for g, wg in zip(grads, wantg):
                         ref = wg[r * Bl:(r + 1) * Bl]
