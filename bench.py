@@ -374,16 +374,26 @@ def run_ours(args):
                 kname, F_k, t_k = "gram_kernel<TMP_BWD> (temporal ranking fwd+bwd, fused)", 12.0 * M * B * B * D, stages["temporal"]
             else:
                 kname, F_k, t_k = "gram_kernel<NCE_BWD> (InfoNCE backward)", 8.0 * M * M * B * B * D / S, stages["nce_grad"]
-            traffic = None
+            traffic = ncu_tensor = None
             tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
             if args.workload == "headline" and os.path.exists(tpath):
                 with open(tpath) as fh:
-                    traffic = json.load(fh).get("gram_kernel_tmp_bwd_dram_bytes_per_launch")
+                    tj = json.load(fh)
+                traffic = tj.get("gram_kernel_tmp_bwd_dram_bytes_per_launch")
+                ncu_tensor = tj.get("gram_kernel_tmp_bwd_tensor_pipe_active_pct_elapsed")
             t_s = max(t_k, 1e-6) * 1e-3
+            # SURVEY 8d counts 3 GEMM-equivalents per contraction; the fused temporal pass executes 2 of them (the
+            # symmetric column-side gradient comes for free), the InfoNCE backward pass executes what it counts
+            executed = (2.0 / 3.0) if (w["terms"] & 4) else 1.0
             roof = {"bound": "tensor", "kernel": kname, "achieved": F_k / t_s / 1e12, "peak": peaks["tflops"],
                     "unit": "TFLOP/s", "frac": F_k / t_s / 1e12 / peaks["tflops"],
                     "peak_source": peaks["source"] + " (sustained bf16)", "traffic": traffic,
-                    "alg_flops_per_launch": F_k, "launch_ms": t_k}
+                    "alg_flops_per_launch": F_k, "launch_ms": t_k,
+                    "executed_frac": executed * F_k / t_s / 1e12 / peaks["tflops"],
+                    "ncu_tensor_pipe_active_pct": ncu_tensor,
+                    "note": "achieved = ALGORITHMIC FLOPs (SURVEY 8d: 3 GEMM-equivalents per contraction) / measured "
+                            "launch time; executed_frac counts the FLOPs the kernel really issues; ncu's "
+                            "sm__pipe_tensor_cycles_active (profiles/r1_ncu_summary.md) is quoted beside it"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -406,7 +416,7 @@ def run_ours(args):
                        "l2": f"inputs rotate over {nsets} batches ({nsets * 2 * M * B * D * 4 / 2 ** 20:.0f} MiB"
                              + (" > 126 MiB L2)" if nsets * 2 * M * B * D * 4 > L2_BYTES else ", fits L2: small side workload)"),
                        "tiles": "bf16 operands, fp32 accumulation (tcgen05 kind::f16)"},
-            "tensor_roofline_frac": F / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+            "tensor_roofline_frac": F / (ms_step * 1e-3) / 1e12 / (peaks["tflops"] * world),   # of the N GPUs' peak
             "alg_tflops": F / (ms_step * 1e-3) / 1e12,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": args.steps * launches_per_step(engine, B, D, world),

@@ -155,8 +155,30 @@ int launch_finalize_fast_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g,
   finalize_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, g, w);
   return cuda_ok("finalize_fast_kernel");
 }
+#ifndef FB_FINALIZE_RT
+#define FB_FINALIZE_RT 1          // 1: one warp per (row, tensor) (finalize_rt_kernel); 0: one warp per row
+#endif
+template <int VW, int MAXT>
+int launch_finalize_rt_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
+  const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);       // <= 33 KB
+  finalize_rt_kernel<VW, MAXT><<<grid, 128 * p.nT, smem, st>>>(p, f, g, w);
+  return cuda_ok("finalize_rt_kernel");
+}
+template <int VW>
+int launch_finalize_rt_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
+  // <= 4 tensors (M <= 2): 512-thread blocks, 128 registers per thread available; else 1024-thread blocks
+  return p.nT <= 4 ? launch_finalize_rt_t<VW, 4>(p, f, g, w, grid, st) : launch_finalize_rt_t<VW, 8>(p, f, g, w, grid, st);
+}
 int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, size_t smem,
                          int grid, cudaStream_t st) {
+  if (FB_FINALIZE_RT && p.nT <= 8) {
+    switch (vw) {
+      case 1: return launch_finalize_rt_vw<1>(p, f, g, w, grid, st);
+      case 2: return launch_finalize_rt_vw<2>(p, f, g, w, grid, st);
+      case 3: return launch_finalize_rt_vw<3>(p, f, g, w, grid, st);
+      case 4: return launch_finalize_rt_vw<4>(p, f, g, w, grid, st);
+    }
+  }
   switch (vw) {
     case 1: return launch_finalize_fast_vw<1>(p, f, g, w, smem, grid, st);
     case 2: return launch_finalize_fast_vw<2>(p, f, g, w, smem, grid, st);
