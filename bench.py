@@ -447,7 +447,8 @@ def run_ours(args):
 
 def launches_per_step(engine, B, D, world):
     """Kernels of libfocal_b200.so per step: [zero_pad], prologue (fused intra), nce_rowsum, nce_lse, nce_grad, temporal,
-    finalize, loss_reduce (+ nce_lse(all rows) when row-sharded).  Counted from the plan of this workload."""
+    finalize, loss_reduce (+ nce_lse(all rows) on the collective multi-GPU path; the peer path has no extra launches:
+    its barriers are split into the producing and consuming kernels).  Counted from the plan of this workload."""
     import ctypes as C
 
     from focal_b200 import _cabi
@@ -456,15 +457,15 @@ def launches_per_step(engine, B, D, world):
     cfg = be._cfg(hp, B, D, True, (0, B // hp.seq_len))
     info = _cabi.FocalWsInfo()
     _cabi.check(be.lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info)), "workspace_info")
+    peer = world > 1 and any(v is not None for v in getattr(be, "_peers", {}).values())
     n = 0
-    n += 1 if (info.bpad != info.b or info.Bpad != B) else 0        # zero_pad_kernel
+    if not peer:
+        n += 1 if (info.bpad != info.b or info.Bpad != B) else 0    # zero_pad_kernel (peer workspaces start zeroed)
     n += 1                                                          # prologue (m_II fused for S in {2, 4})
     n += 0 if hp.seq_len in (2, 4) or not (hp.terms & 4) else 1     # separate intra_kernel otherwise
-    peer = world > 1 and any(v is not None for v in getattr(be, "_peers", {}).values())
     if hp.terms & 1:
-        n += 3 + (1 if world > 1 else 0)                            # nce_rowsum, nce_lse, nce_grad + (sharded) either
-    if peer:                                                        # nce_lse(all rows) or the 2nd peer barrier
-        n += 1                                                      # peer barrier after the prologue
+        n += 3                                                      # nce_rowsum, nce_lse, nce_grad
+        n += 1 if (world > 1 and not peer) else 0                   # collective path: nce_lse again over all rows
     if (hp.terms & 4) and hp.seq_len > 1:
         n += 1                                                      # temporal
     n += 2                                                          # finalize, loss_reduce

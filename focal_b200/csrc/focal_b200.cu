@@ -86,8 +86,9 @@ int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t 
 }
 
 template <int MODE>
-int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid) {
+int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid, int peer_wait = 0) {
   ProbSel sel{};
+  sel.peer_wait = peer_wait;
   switch (p.S) {
     case 4: return launch_gram_kb<MODE, 4>(p, sel, ws, st, p.kbFull, grid);
 #ifndef FB_FAST_BUILD                 // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
@@ -103,9 +104,10 @@ int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid) {
 // InfoNCE problems are launched in groups of equal operand width (they differ only under noPrivate, where the
 // shared problems use the full D columns and the private ones D/2).
 template <int MODE>
-int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st) {
+int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st, int peer_wait = 0) {
   for (int kb = 1; kb <= 4; ++kb) {
     ProbSel sel{};
+    sel.peer_wait = peer_wait;
     for (int q = 0; q < p.nProb; ++q)
       if (p.ops[p.probs[q].opA].kb == kb) sel.idx[sel.n++] = q;
     if (!sel.n) continue;
@@ -220,9 +222,10 @@ PeerWs solo(void* ws) {
   return pw;
 }
 
-int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st) {
+int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st,
+                bool zero_pads = true) {
   int rc;
-  if (p.bpad != p.b || p.Bpad != p.B) {
+  if (zero_pads && (p.bpad != p.b || p.Bpad != p.B)) {
     zero_pad_kernel<<<64, 256, 0, st>>>(p, w);
     if ((rc = cuda_ok("zero_pad_kernel"))) return rc;
   }
@@ -437,6 +440,25 @@ int focal_b200_peer_free(void* ptr) {
   return cudaFree(ptr) == cudaSuccess ? FOCAL_OK : cuda_ok("cudaFree(peer workspace)");
 }
 
+namespace {
+// Do two ranks of this peer table keep their workspace on the same device (several ranks emulated on one GPU)?
+bool ranks_share_a_device(const FocalPeers* peers) {
+  static FocalPeers seen{};
+  static bool seen_valid = false, seen_result = false;
+  if (seen_valid && std::memcmp(&seen, peers, sizeof(FocalPeers)) == 0) return seen_result;
+  bool shared = false;
+  int dev[FOCAL_MAX_PEERS];
+  for (int r = 0; r < peers->world; ++r) {
+    cudaPointerAttributes a{};
+    dev[r] = (cudaPointerGetAttributes(&a, peers->ws[r]) == cudaSuccess) ? a.device : -1 - r;
+    for (int q = 0; q < r; ++q) shared = shared || dev[q] == dev[r];
+  }
+  cudaGetLastError();
+  seen = *peers; seen_valid = true; seen_result = shared;
+  return shared;
+}
+}  // namespace
+
 int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, const FocalPeers* peers, size_t ws_bytes,
                             float* loss5, float* const* grads, void* stream) {
   Plan p;
@@ -454,26 +476,38 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FeatPtrs f;
   if ((rc = fill_feats(p, feats, f))) return rc;
-  // phase 1: operands of the owned rows -> every workspace
-  if ((rc = do_prologue(p, cfg->no_private, f, pw, w, st))) return rc;
-  peer_barrier_kernel<<<1, 32, 0, st>>>(p, pw);
-  if ((rc = cuda_ok("peer_barrier_kernel"))) return rc;
-  // phase 2: row sums of the owned rows -> every workspace.  The temporal launch needs nothing from the peers beyond
-  // phase 1, so it runs between the stores and the barrier that waits for them: the barrier finds everybody there.
+  // phase 1: operands of the owned rows -> every workspace; the last block of the prologue announces epoch 1 and the
+  // first Gram launch waits for every rank's announcement before it reads operands.  (No zero_pad launch: workspaces
+  // from focal_b200_peer_alloc start zeroed and nobody ever writes a padding row.)
+  if ((rc = do_prologue(p, cfg->no_private, f, pw, w, st, /*zero_pads=*/false))) return rc;
+  // several ranks on one device: the waits become one-block launches of their own (see peer_wait_kernel)
+  const bool split_wait = pw.world > 1 && ranks_share_a_device(peers);
+  const int nwait = (pw.world > 1 && !split_wait) ? pw.world : 0;
+  auto wait_launch = [&]() -> int {
+    if (!split_wait) return FOCAL_OK;
+    peer_wait_kernel<<<1, 32, 0, st>>>(p, pw);
+    return cuda_ok("peer_wait_kernel");
+  };
   const bool nce = (p.terms & FOCAL_TERM_NCE) != 0;
+  const bool tmp = (p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p);
+  // phase 2: row sums of the owned rows -> every workspace (announced by the last block of nce_lse).  The temporal launch
+  // needs nothing from the peers beyond phase 1, so it runs between those stores and the launch that waits for them.
+  if (nce || tmp) {
+    if ((rc = wait_launch())) return rc;
+  }
   if (nce) {
-    if ((rc = launch_nce<NCE_FWD>(p, w, st))) return rc;
+    if ((rc = launch_nce<NCE_FWD>(p, w, st, nwait))) return rc;
     nce_lse_kernel<<<lse_blocks(p, 0), 256, 0, st>>>(p, pw, w, 0);
     if ((rc = cuda_ok("nce_lse_kernel"))) return rc;
   }
-  if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p)) {
-    rc = p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp);
+  if (tmp) {
+    const int wt = nce ? 0 : nwait;
+    rc = p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp, wt) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp, wt);
     if (rc) return rc;
   }
   if (nce && p.need_grad) {
-    peer_barrier_kernel<<<1, 32, 0, st>>>(p, pw);
-    if ((rc = cuda_ok("peer_barrier_kernel"))) return rc;
-    if ((rc = launch_nce<NCE_BWD>(p, w, st))) return rc;
+    if ((rc = wait_launch())) return rc;
+    if ((rc = launch_nce<NCE_BWD>(p, w, st, nwait))) return rc;
   }
   // phase 3: gradients of the owned rows; loss partials all-reduced inside loss_reduce_kernel (third barrier)
   return do_finalize(p, cfg->no_private, feats, grads, pw, w, loss5, st);

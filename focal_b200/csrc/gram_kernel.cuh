@@ -25,6 +25,7 @@
 // instruction occupies the tensor pipe N/2 clk, so N >= 96 is needed to stay tensor-bound; the issue loop below is
 // fully unrolled with precomputed descriptors for that reason.  Row tile = 128 rows (UMMA M), column tile = BN.
 #pragma once
+#include "peer.cuh"
 #include "plan.h"
 #include "ptx.cuh"
 
@@ -272,6 +273,12 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   if (warp == 1) {
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
+  }
+  if (sel.peer_wait > 0) {
+    // row-sharded path: the operands / row sums this launch reads were stored by the peers; wait for their
+    // announcements (the last block of their producing launch sent them), then order the TMA reads behind the wait
+    peer_wait(ws, p, sel.peer_wait, -1);
+    asm volatile("fence.proxy.async;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();

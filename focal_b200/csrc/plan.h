@@ -44,6 +44,7 @@ constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : (kb == 4 ? FB_KB4_BN : 64
 struct ProbSel {
   int32_t n;
   int32_t idx[kMaxProb];
+  int32_t peer_wait;   // row-sharded path: number of ranks whose barrier announcement this launch waits for (0 = none)
 };
 
 struct Plan {
@@ -79,7 +80,8 @@ struct Plan {
   uint64_t dz2_delta, dx2_delta, rho2_delta, cnt2_delta;   // byte distance between the buffers of consecutive pieces
   uint64_t flag_tmp_off;   // int32 [2M][Bpad/128]: number of secondary pieces of the row block (temporal)
   uint64_t flag_nce_off;   // int32 [nProb][S][2][bpad/128]: same for the InfoNCE backward pass
-  uint64_t bar_off;        // uint32 [16]: [r] = last barrier epoch rank r announced here, [8] = own epoch counter
+  uint64_t bar_off;        // uint32 [16]: [r] = last barrier epoch rank r announced here, [8] = own epoch counter,
+                           //              [9] = blocks-done counter of the launch that announces next
   uint64_t lossx_off;      // double [kMaxPeers][8]: loss partials of every rank (sharded path)
   uint64_t total_bytes;
   int32_t nblk1, nblk2, nitems3;

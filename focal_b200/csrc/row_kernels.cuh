@@ -1,6 +1,7 @@
 // Single-pass row kernels (HBM-bound): prologue, intra-sequence distances, log-row-sums, gradient assembly,
 // loss reduction.  One warp per row, rows staged in shared memory, warp-shuffle reductions, coalesced stores.
 #pragma once
+#include "peer.cuh"
 #include "plan.h"
 #include "ptx.cuh"
 
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
       for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
       reinterpret_cast<float*>(ws + p.part2_off)[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
     }
+    if (pw.world > 1) peer_announce_when_launch_done(p, pw);      // row sums of the owned rows are out
   }
 }
 
@@ -449,45 +451,11 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------
 // K5: deterministic reduction of the per-block partials -> {total, shared, private, orth, temporal}
 // ---------------------------------------------------------------------------------------------------------
-// Device-side barrier over the ranks of a row-sharded job.  Called by ONE block of >= kMaxPeers threads per rank, all
-// ranks in step.  Rank r announces epoch e by storing it into slot r of every peer's flag array (release, system
-// scope: everything this rank's earlier kernels and this block wrote to peer memory is visible before the flag) and
-// waits until every peer has announced e in its own array.  Bounded spin: a lost rank traps instead of hanging.
-__device__ __forceinline__ void peer_barrier(const Plan& p, const PeerWs& pw) {
-  __shared__ uint32_t epoch_sh;
-  uint32_t* mine = reinterpret_cast<uint32_t*>(pw.ws[pw.rank] + p.bar_off);
-  __syncthreads();
-  if (threadIdx.x == 0) { epoch_sh = mine[8] + 1; mine[8] = epoch_sh; }
-  __syncthreads();
-  const uint32_t e = epoch_sh;
-  if ((int)threadIdx.x < pw.world) {
-    __threadfence_system();
-    uint32_t* dst = reinterpret_cast<uint32_t*>(pw.ws[threadIdx.x] + p.bar_off) + pw.rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(e) : "memory");
-    const uint32_t* src = mine + threadIdx.x;
-    uint64_t t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
-      uint32_t v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-      if ((int32_t)(v - e) >= 0) break;
-      if ((spins & 1023) == 1023) {
-        uint64_t now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 20000000000ull) {          // 20 s: a rank died or fell out of step
-          printf("focal_b200: peer barrier timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n", pw.rank,
-                 (int)threadIdx.x, e, v);
-          __trap();
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ Plan p,
-                                                          const __grid_constant__ PeerWs pw) {
-  peer_barrier(p, pw);
+// Wait phase alone, as a one-block launch: used instead of the wait inside the persistent Gram kernels when several ranks
+// share one device (tests), where a spinning 148-CTA launch would keep the other ranks' kernels off the SMs.
+__global__ void __launch_bounds__(32) peer_wait_kernel(const __grid_constant__ Plan p,
+                                                       const __grid_constant__ PeerWs pw) {
+  peer_wait(pw.ws[pw.rank], p, pw.world, pw.rank);
 }
 
 __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant__ Plan p,

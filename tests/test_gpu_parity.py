@@ -397,6 +397,23 @@ def test_sharded_peer_path_on_one_gpu(world, B, D, mods, T, need_grad, S):
         Bl = B // world
         local = [[t[r * Bl:(r + 1) * Bl].contiguous() for t in feats] for r in range(world)]
         streams = [torch.cuda.Stream() for _ in range(world)]
+        # Load every kernel this shard shape uses BEFORE ranks start waiting for each other: with CUDA's lazy module
+        # loading the first launch of a kernel can block the host until running kernels finish, and here (one process
+        # driving all ranks) a rank's spinning wait only finishes once the host has launched the other ranks.
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _cabi.check(lib.focal_b200_peer_alloc(info.total_bytes, C.byref(ptr), handle), "peer_alloc")
+        solo = _cabi.FocalPeers(rank=0, world=1)
+        solo.ws[0] = ptr.value
+        l5 = torch.empty(5, device="cuda")
+        gw = [torch.empty_like(t) for t in local[0]]
+        c0 = be._cfg(hp, B, D, need_grad, shard_sequences(b, world, 0))
+        c0.local_rows = 1
+        _cabi.check(lib.focal_b200_loss_sharded(C.byref(c0), _cabi.ptr_array([t.data_ptr() for t in local[0]]),
+                                                C.byref(solo), C.c_size_t(info.total_bytes), C.c_void_p(l5.data_ptr()),
+                                                _cabi.ptr_array([g.data_ptr() for g in gw]) if need_grad else None,
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "warm-up")
+        torch.cuda.synchronize()
+        lib.focal_b200_peer_free(ptr)
         for step in range(3):
             outs = []
             for r in range(world):
