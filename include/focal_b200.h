@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FOCAL_B200_ABI_VERSION 1
+#define FOCAL_B200_ABI_VERSION 2
 #define FOCAL_MAX_MODALITIES 4
 
 enum {
