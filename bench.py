@@ -37,6 +37,7 @@ WORKLOADS = {
     "cfg3": dict(B=4096, S=4, M=3, D=256, T=0.07, mods=("acc", "gyr", "mag"), terms=7),
     "cfg4": dict(B=65536, S=1, M=2, D=128, T=0.5, mods=("seismic", "audio"), terms=1),      # global InfoNCE only
     "cfg5": dict(B=16384, S=4, M=4, D=256, T=0.5, mods=("m0", "m1", "m2", "m3"), terms=7),
+    "cfg5w": dict(B=16384, S=4, M=4, D=512, T=0.5, mods=("m0", "m1", "m2", "m3"), terms=7),  # shared 256 + private 256
 }
 for _w in WORKLOADS.values():
     _w.update(margin=1.0, weights=(1.0, 1.0, 3.0, 5.0))

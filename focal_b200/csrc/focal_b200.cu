@@ -85,17 +85,26 @@ int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t 
   return FOCAL_ESHAPE;
 }
 
+// temporal launches: operand width 1..4 K blocks, or 8 ("wide": 256 < D <= 512)
+template <int MODE, int SEQ>
+int launch_temporal_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int grid) {
+#ifndef FB_FAST_BUILD
+  if (p.kbFull == 8) return launch_gram<MODE, 8, SEQ>(p, sel, ws, st, grid);
+#endif
+  return launch_gram_kb<MODE, SEQ>(p, sel, ws, st, p.kbFull, grid);
+}
+
 template <int MODE>
 int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid, int peer_wait = 0) {
   ProbSel sel{};
   sel.peer_wait = peer_wait;
   switch (p.S) {
-    case 4: return launch_gram_kb<MODE, 4>(p, sel, ws, st, p.kbFull, grid);
+    case 4: return launch_temporal_kb<MODE, 4>(p, sel, ws, st, grid);
 #ifndef FB_FAST_BUILD                 // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
-    case 2: return launch_gram_kb<MODE, 2>(p, sel, ws, st, p.kbFull, grid);
-    case 8: return launch_gram_kb<MODE, 8>(p, sel, ws, st, p.kbFull, grid);
-    case 16: return launch_gram_kb<MODE, 16>(p, sel, ws, st, p.kbFull, grid);
-    case 32: return launch_gram_kb<MODE, 32>(p, sel, ws, st, p.kbFull, grid);
+    case 2: return launch_temporal_kb<MODE, 2>(p, sel, ws, st, grid);
+    case 8: return launch_temporal_kb<MODE, 8>(p, sel, ws, st, grid);
+    case 16: return launch_temporal_kb<MODE, 16>(p, sel, ws, st, grid);
+    case 32: return launch_temporal_kb<MODE, 32>(p, sel, ws, st, grid);
 #endif
   }
   return FOCAL_ESHAPE;
@@ -296,7 +305,7 @@ const char* focal_b200_strerror(int code) {
     case FOCAL_OK: return "ok";
     case FOCAL_EINVAL: return "invalid argument";
     case FOCAL_ESHAPE:
-      return "unsupported shape: need B % S == 0, S a power of two <= 32, 2 <= D <= 256, 1 <= M <= 4, "
+      return "unsupported shape: need B % S == 0, S a power of two <= 32, 2 <= D <= 512, 1 <= M <= 4, "
              "temperature >= 0.016";
     case FOCAL_ECUDA: return "CUDA error (see stderr)";
     case FOCAL_EWORKSPACE: return "workspace too small or not 1024-byte aligned";

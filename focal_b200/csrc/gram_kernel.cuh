@@ -58,13 +58,14 @@ struct GramCfg {
   static constexpr bool kTmp = (MODE >= 2);
   static constexpr int BN = KB <= 2 ? 128 : (KB == 4 ? FB_KB4_BN : 64);          // column tile
   static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : 4);  // S stages == epilogue warpgroups
-  static constexpr int NB = KB <= 3 ? 5 : FB_KB4_NB;                             // B-tile ring stages (smem budget)
+  static constexpr int NB = KB <= 3 ? 5 : (KB == 4 ? FB_KB4_NB : 1);             // B-tile ring stages (smem budget)
   static constexpr int NW = (KB == 4 && SEQ <= 16) ? FB_KB4_NW : 1;              // warpgroups per S stage
   static constexpr int NG = NS * NW;                                             // epilogue warpgroups in total
   static constexpr int CW = (NG == 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
   static constexpr int kThreads = 64 + 128 * NG;
   static_assert(NG <= 4, "partial-sum arrays and register budget are sized for <= 4 epilogue warpgroups");
-  static_assert((kBwd ? KB * 64 : 0) + NS * BN <= kTmemCols, "TMEM budget");
+  static constexpr int kOKB = KB > 4 ? 4 : KB;       // K blocks of the O accumulator (wide mode: one half per pass)
+  static_assert((kBwd ? kOKB * 64 : 0) + NS * BN <= kTmemCols, "TMEM budget");
 };
 
 template <int BN, int KB, int kNumBStages>
@@ -122,7 +123,7 @@ __device__ __forceinline__ int gram_num_items(const Plan& p, const ProbSel& sel)
     return sel.n * p.S * 2 * (t1 - t0);
   } else {
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
-    return p.nT * (t1 - t0);
+    return p.nT * (t1 - t0) * ((MODE == TMP_BWD && p.kbFull > 4) ? 2 : 1);     // wide mode: one item per output half
   }
 }
 
@@ -150,8 +151,10 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
     x.q = q; x.s = s; x.c = 0;
   } else {
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM, nrt = t1 - t0;
-    const int rt = t0 + it % nrt;
-    const int c = it / nrt;
+    int r = it, half = 0;
+    if (MODE == TMP_BWD && p.kbFull > 4) { half = r & 1; r >>= 1; }
+    const int rt = t0 + r % nrt;
+    const int c = r / nrt;
     x.kstride = (uint64_t)p.Bpad * 128;
     x.b_src0 = x.b_src1 = ws + p.xt_off + (uint64_t)c * p.kbFull * p.Bpad * 128;
     x.a_src = x.b_src0 + (uint64_t)rt * kTileM * 128;
@@ -161,7 +164,7 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
     x.ct_begin = 0; x.ct_end = x.ntc;
     x.row0 = rt * kTileM; x.side = 0; x.ncol_valid = p.B;
     x.row_lo = p.seq0 * p.S; x.row_hi = p.seq1 * p.S;
-    x.q = 0; x.s = 0; x.c = c;
+    x.q = half; x.s = 0; x.c = c;                   // q: which 256-column half of dx this item accumulates (wide mode)
   }
 }
 
@@ -241,7 +244,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   // other warpgroup may not have read yet.
   constexpr int kWStep = (NW > 1) ? 16 : 8;
   static_assert(NW == 1 || CW == 16, "shared stages use 16-column chunks");
-  constexpr int kON = KB * 64;                       // UMMA #2 N = padded operand width
+  constexpr int kON = G::kOKB * 64;                  // UMMA #2 N = padded operand width (wide mode: one half of it)
   constexpr int kKSteps = KB * 4;                    // UMMA #1 K steps (K padded to 64 with zeros)
   constexpr uint32_t kOCol = 0;                      // TMEM: O accumulator at [0, kON) (backward modes only)
   constexpr uint32_t kSCol = kBwd ? kON : 0;         // TMEM: S stage w at kSCol + w * BN
@@ -380,7 +383,9 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               if (ready) {
                 tc_fence_after();
                 if (elect_one()) {
-                  const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4));
+                  // MN-major view of the B tile; wide mode: the K blocks of this item's output half
+                  const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4)) +
+                                      (uint64_t)((KB > 4 ? x.q * 4 * (BN * 128) : 0) >> 4);
                   const uint32_t a = tmem + kSCol + ss * BN;    // W: packed bf16 over the consumed S stage
                   const uint32_t acc = (t2 > 0) ? 1u : 0u;
 #pragma unroll
@@ -596,9 +601,10 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           } else {
 #pragma unroll
             for (int w = 0; w < NG - 1; ++w) { hinge_acc += bars->part_hinge[w][trow]; cnt_i += bars->part_cnt[w][trow]; }
-            if (kBwd && row_ok)
+            const bool first_half = (KB <= 4) || x.q == 0;      // wide mode: scalars are published by the first pass only
+            if (kBwd && row_ok && first_half)
               reinterpret_cast<float*>(ws + p.rho_off + (uint64_t)pk * p.rho2_delta)[(uint64_t)x.c * p.Bpad + row] = rowacc;
-            if (row_ok && (lane & (SQ - 1)) == 0)
+            if (row_ok && first_half && (lane & (SQ - 1)) == 0)
               reinterpret_cast<int32_t*>(ws + p.cnt_off + (uint64_t)pk * p.cnt2_delta)[(uint64_t)x.c * p.bpad + seq_i] = cnt_i;
             // every lane of a sequence accumulated the same hinge values: count each (I, J) once
             const float hs = warp_sum(((lane & (SQ - 1)) == 0) ? hinge_acc : 0.f);
@@ -617,7 +623,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             reinterpret_cast<int32_t*>(ws + p.flag_nce_off)[(((uint64_t)x.q * p.S + x.s) * 2 + side) * (p.bpad / kTileM) +
                                                             row0 / kTileM] = npi - 1;
         } else {
-          out = reinterpret_cast<float*>(ws + p.dx_off + (uint64_t)pk * p.dx2_delta) + ((uint64_t)x.c * p.Bpad + row) * kON;
+          out = reinterpret_cast<float*>(ws + p.dx_off + (uint64_t)pk * p.dx2_delta) +
+                ((uint64_t)x.c * p.Bpad + row) * (KB * 64) + (KB > 4 ? x.q * kON : 0);
           if (!second && trow == 0)
             reinterpret_cast<int32_t*>(ws + p.flag_tmp_off)[(uint64_t)x.c * (p.Bpad / kTileM) + row0 / kTileM] = npi - 1;
         }
@@ -637,7 +644,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       }
       if (MODE != NCE_BWD) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // partial arrays / red[] may be reused now
-        if (!kIsNce && wgi == 0 && trow == 0) {
+        if (!kIsNce && wgi == 0 && trow == 0 && (KB <= 4 || x.q == 0)) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
           const int slot = p.np_tmp * (x.c * nrt + (row0 / kTileM - t0));

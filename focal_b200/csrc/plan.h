@@ -144,13 +144,14 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   if (c.M < 1 || c.M > kMaxM) return FOCAL_ESHAPE;
   if (c.B % c.S) return FOCAL_ESHAPE;                    // loss.py:154 reshape(-1, S, D) would raise
   if (c.S > 32 || (c.S & (c.S - 1))) return FOCAL_ESHAPE;  // sequence = power-of-two rows of one warp
-  if (c.D < 2 || c.D > 256) return FOCAL_ESHAPE;
+  if (c.D < 2 || c.D > 512) return FOCAL_ESHAPE;
   if (!(c.temperature > 0.f)) return FOCAL_EINVAL;
   if (c.precision != FOCAL_PREC_BF16) return FOCAL_EINVAL;
   p.B = c.B; p.S = c.S; p.M = c.M; p.D = c.D; p.d = c.D / 2;
   p.b = c.B / c.S;
   p.nT = 2 * c.M;
-  p.kbFull = (c.D + kKBlk - 1) / kKBlk;
+  // temporal operand width in 64-column K blocks: 1..4, or 8 (zero-padded) for 256 < D <= 512, the "wide" Gram mode
+  p.kbFull = c.D <= 256 ? (c.D + kKBlk - 1) / kKBlk : 8;
   {
     // rows are padded so that every 128-row A tile and every BN-row B tile stays inside the operand arrays
     auto pad_rows = [](int rows, int bn) {
@@ -232,8 +233,11 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     if (np1 > p.np_nce) p.np_nce = np1;
   }
   {
-    const int items = p.nT * tmp_row_tiles(p), bn = tile_bn(p.kbFull);
-    p.sk_tmp = (FB_STREAMK_TMP > 0) || (FB_STREAMK_TMP == 0 && items < num_sms);
+    // wide mode (kbFull == 8): the O accumulator holds half of the columns, so the backward launch visits every row
+    // block twice (one item per output half) and keeps whole row blocks per CTA (no stream-K pieces)
+    const bool wide = p.kbFull > 4;
+    const int items = p.nT * tmp_row_tiles(p) * ((wide && p.need_grad) ? 2 : 1), bn = tile_bn(p.kbFull);
+    p.sk_tmp = !wide && ((FB_STREAMK_TMP > 0) || (FB_STREAMK_TMP == 0 && items < num_sms));
     p.np_tmp = 2;
     int np1 = 1;
     p.grid_tmp = piece_grid(items, (p.B + bn - 1) / bn, num_sms, p.sk_tmp != 0, &np1);

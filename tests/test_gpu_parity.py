@@ -125,6 +125,9 @@ def test_degenerate_batches(name):
     ("iid", 1536, 128, ["seismic", "audio"], 0.5, 3),            # b = 384: three row tiles, K blocks = 1 / 2
     ("structured", 4 * 333, 192, ["a", "b"], 0.2, 4),             # ragged: b = 333, D = 192 (3 K blocks, BN = 64)
     ("iid", 2048, 64, ["m0", "m1", "m2", "m3"], 0.5, 5),          # 4 modalities
+    ("structured", 1024, 512, ["seismic", "audio"], 0.5, 6),      # cfg 5 width (256 + 256): wide temporal mode, 8 K blocks
+    ("iid", 4 * 200, 512, ["a", "b", "c", "d"], 0.5, 7),          # ... with 4 modalities and a ragged batch
+    ("iid", 512, 320, ["a", "b"], 0.5, 8),                        # 256 < D < 512: zero-padded to 8 K blocks
 ])
 def test_against_fp64_oracle(gen, B, D, mods, T, seed):
     """Sizes the reference cannot hold in memory comfortably: compare with the fp64 closed-form oracle (on the GPU)."""
@@ -265,8 +268,8 @@ def test_error_behaviour():
     y = {m: torch.randn(32, 16) for m in ("a", "b")}      # CPU tensors: no fallback
     with pytest.raises(RuntimeError):
         mod(y, y)
-    z = {m: torch.randn(32, 300, device="cuda") for m in ("a", "b")}
-    with pytest.raises(ValueError):                       # D > 256 not supported by the tile configurations yet
+    z = {m: torch.randn(32, 600, device="cuda") for m in ("a", "b")}
+    with pytest.raises(ValueError):                       # D > 512 not supported by the tile configurations
         mod(z, z)
 
 
