@@ -128,8 +128,9 @@ int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st, int peer_wait = 0) {
 
 // lanes own VW = d/32 consecutive columns per half on the vectorised row-kernel path (0 = use the generic kernels)
 int fast_row_vw(const Plan& p, int no_private) {
-  if (no_private || (p.D & 1) || p.d % 32 || p.d > 128 || p.d < 32) return 0;
-  return p.d / 32;
+  if (no_private || (p.D & 1) || p.d % 32 || p.d < 32) return 0;
+  const int vw = p.d / 32;
+  return (vw <= 4 || vw == 8) ? vw : 0;           // D = 64, 128, 192, 256, 512
 }
 
 template <int VW>
@@ -151,6 +152,7 @@ int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, const PeerWs&
     case 2: return launch_prologue_fast_vw<2>(p, f, pw, w, smem, grid, fuse, st);
     case 3: return launch_prologue_fast_vw<3>(p, f, pw, w, smem, grid, fuse, st);
     case 4: return launch_prologue_fast_vw<4>(p, f, pw, w, smem, grid, fuse, st);
+    case 8: return launch_prologue_fast_vw<8>(p, f, pw, w, smem, grid, fuse, st);
   }
   return FOCAL_ESHAPE;
 }
@@ -171,7 +173,13 @@ int launch_finalize_fast_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g,
 #endif
 template <int VW, int MAXT>
 int launch_finalize_rt_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
-  const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);       // <= 33 KB
+  const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(finalize_rt_kernel<VW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return cuda_ok("cudaFuncSetAttribute(finalize_rt_kernel)");
+    configured = smem;
+  }
   finalize_rt_kernel<VW, MAXT><<<grid, 128 * p.nT, smem, st>>>(p, f, g, w);
   return cuda_ok("finalize_rt_kernel");
 }
@@ -185,12 +193,13 @@ int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtr
   // Few rows (a row shard): the launch is one wave of blocks and its time is the dependent chain of one warp -> split
   // every row over nT warps (measured 8192 / 8 rows: 41 -> 32 us).  Many rows: the row-per-warp kernel has the higher
   // occupancy and fewer instructions (measured 8192 rows: 88 vs 116 us).
-  if (FB_FINALIZE_RT && p.nT <= 8 && grid <= 2 * p.num_sms) {
+  if (FB_FINALIZE_RT && p.nT <= 8 && grid <= 2 * p.num_sms && !(vw == 8 && p.nT > 4)) {   // (VW 8, 1024 threads) spills
     switch (vw) {
       case 1: return launch_finalize_rt_vw<1>(p, f, g, w, grid, st);
       case 2: return launch_finalize_rt_vw<2>(p, f, g, w, grid, st);
       case 3: return launch_finalize_rt_vw<3>(p, f, g, w, grid, st);
       case 4: return launch_finalize_rt_vw<4>(p, f, g, w, grid, st);
+      case 8: return launch_finalize_rt_vw<8>(p, f, g, w, grid, st);
     }
   }
   switch (vw) {
@@ -198,6 +207,7 @@ int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtr
     case 2: return launch_finalize_fast_vw<2>(p, f, g, w, smem, grid, st);
     case 3: return launch_finalize_fast_vw<3>(p, f, g, w, smem, grid, st);
     case 4: return launch_finalize_fast_vw<4>(p, f, g, w, smem, grid, st);
+    case 8: return launch_finalize_fast_vw<8>(p, f, g, w, smem, grid, st);
   }
   return FOCAL_ESHAPE;
 }

@@ -1,6 +1,6 @@
 // Vectorised variants of the prologue / finalize row kernels for the common shapes:
-//   D even, D/2 a multiple of 32 (D = 64, 128, 192, 256), standard topology (no "noPrivate"), S in {2, 4}.
-// One warp per row, 4 consecutive rows (= whole sequences) per block.  Each lane owns VW = D/64 consecutive columns
+//   D even, D/2 a multiple of 32 (D = 64, 128, 192, 256, and 512), standard topology (no "noPrivate"), S in {2, 4}.
+// One warp per row, 4 consecutive rows (= whole sequences) per block.  Each lane owns VW = D/64 (1..4, or 8) consecutive columns
 // of the shared half and the matching VW columns of the private half of every tensor, so all per-row dot products are
 // lane-local multiplies + one shuffle reduction, every global access is a coalesced 8/16-byte vector, and the
 // neighbouring windows of a sequence are read from shared memory instead of HBM.  The generic kernels in
@@ -14,7 +14,11 @@ namespace fb {
 
 template <int VW>
 __device__ __forceinline__ void ld_frag(const float* p, float (&v)[VW]) {
-  if (VW == 4) {
+  if (VW == 8) {
+    const float4 t = *reinterpret_cast<const float4*>(p), u = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = t.x; v[1 % VW] = t.y; v[2 % VW] = t.z; v[3 % VW] = t.w;
+    v[4 % VW] = u.x; v[5 % VW] = u.y; v[6 % VW] = u.z; v[7 % VW] = u.w;
+  } else if (VW == 4) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2 % VW] = t.z; v[3 % VW] = t.w;
   } else if (VW == 2) {
@@ -27,7 +31,10 @@ __device__ __forceinline__ void ld_frag(const float* p, float (&v)[VW]) {
 }
 template <int VW>
 __device__ __forceinline__ void st_frag(float* p, const float (&v)[VW]) {
-  if (VW == 4) {
+  if (VW == 8) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1 % VW], v[2 % VW], v[3 % VW]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4 % VW], v[5 % VW], v[6 % VW], v[7 % VW]);
+  } else if (VW == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2 % VW], v[3 % VW]);
   } else if (VW == 2) {
     *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1 % VW]);
@@ -44,7 +51,10 @@ __device__ __forceinline__ void st_operand(uint8_t* op_base, uint64_t kstride_ro
                                            const float (&v)[VW]) {
   uint8_t* dst = op_base + ((uint64_t)(e0 >> 6) * kstride_rows + row) * 128 +
                  ((((uint32_t)(e0 & 63) >> 3) ^ (uint32_t)(row & 7)) << 4) + (e0 & 7) * 2;
-  if (VW == 4) {
+  if (VW == 8) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1 % VW]), pack_bf16x2(v[2 % VW], v[3 % VW]),
+                                                pack_bf16x2(v[4 % VW], v[5 % VW]), pack_bf16x2(v[6 % VW], v[7 % VW]));
+  } else if (VW == 4) {
     *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2 % VW], v[3 % VW]));
   } else if (VW == 2) {
     *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(v[0], v[1 % VW]);

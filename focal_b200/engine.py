@@ -150,7 +150,7 @@ class CudaBackend:
     def peer_eligible(hp: FocalHyper, D: int, world: int) -> bool:
         """Shapes focal_b200_loss_sharded handles (the vectorised row kernels with fused intra-sequence means)."""
         d = D // 2
-        return (world <= _cabi.FOCAL_MAX_PEERS and not hp.no_private and D % 2 == 0 and d % 32 == 0 and 32 <= d <= 128
+        return (world <= _cabi.FOCAL_MAX_PEERS and not hp.no_private and D % 2 == 0 and d % 32 == 0 and (32 <= d <= 128 or d == 256)
                 and hp.seq_len in (1, 2, 4))
 
     def peer_setup(self, cfg: _cabi.FocalCfg, group, dev: torch.device):

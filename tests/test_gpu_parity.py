@@ -366,6 +366,7 @@ def test_row_blocked_inputs_match_contiguous():
     (4, 1536, 128, ("acc", "gyr", "mag"), 0.07, True, 4),
     (2, 1024, 64, ("seismic", "audio"), 0.5, False, 2),
     (2, 1024, 128, ("seismic", "audio"), 0.5, True, 1),       # "global" InfoNCE (cfg 4 shape): temporal term is NaN
+    (2, 1024, 512, ("seismic", "audio"), 0.5, True, 4),       # wide temporal mode (8 K blocks), vectorised rows VW = 8
 ])
 def test_sharded_peer_path_on_one_gpu(world, B, D, mods, T, need_grad, S):
     """focal_b200_loss_sharded (prologue of the owned rows storing into every rank's workspace, device-side
