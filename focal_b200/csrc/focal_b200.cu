@@ -564,14 +564,16 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t a_tmem_col = 256;                 // A operand columns when it lives in tensor memory
+  const bool tf32 = (a_via_st & 0x100u) != 0;      // kind::tf32 instead of kind::f16 (32-bit elements)
+  a_via_st &= 0xffu;
   if (a_via_st == 1) {
     for (uint32_t o = threadIdx.x * 16; o < a_bytes; o += blockDim.x * 16)
       *reinterpret_cast<uint4*>(sa + o) = *reinterpret_cast<const uint4*>(a_img + o);
     fence_proxy_async_smem();
   } else if (a_via_st == 2) {
-    const uint32_t K = a_bytes / 256;               // bf16 elements per row
-    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(a_img) + (size_t)threadIdx.x * (K / 2);
-    for (uint32_t g = 0; g < K / 64; ++g) {
+    const uint32_t W32 = a_bytes / 512;             // 32-bit words per row (2 bf16 or 1 tf32 element each)
+    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(a_img) + (size_t)threadIdx.x * W32;
+    for (uint32_t g = 0; g < W32 / 32; ++g) {
       uint32_t r[32];
       for (int j = 0; j < 32; ++j) r[j] = rowp[g * 32 + j];
       tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + a_tmem_col + g * 32, r);
@@ -588,7 +590,10 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img
     tc_fence_after();
     for (uint32_t k = 0; k < ksteps; ++k) {
       const uint64_t db = umma_smem_desc(smem_u32(sb) + k * b_kstep, b_lbo, b_sbo);
-      if (a_via_st == 2) umma_bf16_ts(tmem, tmem + a_tmem_col + k * 8, db, idesc, k > 0);
+      if (tf32) {
+        if (a_via_st == 2) umma_tf32_ts(tmem, tmem + a_tmem_col + k * 8, db, idesc, k > 0);
+        else umma_tf32(tmem, umma_smem_desc(smem_u32(sa) + k * a_kstep, a_lbo, a_sbo), db, idesc, k > 0);
+      } else if (a_via_st == 2) umma_bf16_ts(tmem, tmem + a_tmem_col + k * 8, db, idesc, k > 0);
       else umma_bf16(tmem, umma_smem_desc(smem_u32(sa) + k * a_kstep, a_lbo, a_sbo), db, idesc, k > 0);
     }
     umma_commit(&bar_mma);

@@ -87,3 +87,58 @@ def test_a_operand_from_tensor_memory(N, b_mn):
         out = run_probe(a_img, swizzled_image(Bm), idesc(128, N), 0, 0, 0, 16, 1024, 32, K // 16, N, 2)
         ref = A.float() @ Bm.float().T
     assert torch.allclose(out, ref, rtol=1e-5, atol=1e-4), float((out - ref).abs().max())
+
+
+def swizzled_image32(mat: torch.Tensor) -> torch.Tensor:
+    """Same byte layout for 32-bit elements: [R, K] fp32 (K multiple of 32) -> [K/32][R][128 B], chunks of 4 elements."""
+    R, K = mat.shape
+    kb = K // 32
+    x = mat.reshape(R, kb, 8, 4).permute(1, 0, 2, 3).contiguous()
+    r = torch.arange(R, device=mat.device)
+    c = torch.arange(8, device=mat.device)
+    src = (c[None, :] ^ (r[:, None] & 7))
+    out = torch.gather(x, 2, src[None, :, :, None].expand(kb, R, 8, 4))
+    return out.contiguous().view(torch.uint8).reshape(-1)
+
+
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest to 10 mantissa bits (what cvt.rna.tf32.f32 does), so the tensor core's truncation is exact."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+TF32 = 0x100
+
+
+@pytest.mark.parametrize("N", [64, 96, 128])
+def test_tf32_kmajor_gram_tile(N):
+    """kind::tf32, both operands K-major: 32 elements per 128-byte swizzle row, K step = 8 elements = 32 bytes."""
+    _require_cuda()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = tf32_round(torch.randn(128, 64, device="cuda", generator=g))
+    Bm = tf32_round(torch.randn(N, 64, device="cuda", generator=g))
+    # two 32-element K blocks: block stride = rows * 128 bytes; 8 K steps of 8 elements, the probe advances the
+    # descriptors linearly, so give it one block (4 steps) per call and add the partial products
+    ref = A.double() @ Bm.double().T
+    out = torch.zeros(128, N, device="cuda")
+    for kb in range(2):
+        a_img = swizzled_image32(A[:, kb * 32:(kb + 1) * 32].contiguous())
+        b_img = swizzled_image32(Bm[:, kb * 32:(kb + 1) * 32].contiguous())
+        out += run_probe(a_img, b_img, idesc(128, N, fmt=2), 16, 1024, 32, 16, 1024, 32, 4, N if N % 32 == 0 else 128,
+                         TF32)[:, :N]
+    assert torch.allclose(out.double(), ref, rtol=1e-5, atol=1e-4), float((out.double() - ref).abs().max())
+
+
+def test_tf32_a_from_tensor_memory_kmajor_b():
+    """kind::tf32 with A in tensor memory (one 32-bit column per element, 8 columns per K step) and a K-major B tile.
+    (Measured while bringing this up: an MN-major B descriptor with kind::tf32 returns all zeros for every LBO / K-step
+    combination tried, so a TF32 mode cannot re-use the K-major tile as the second GEMM's operand the way the bf16
+    kernels do -- it needs a transposed operand copy.  See DESIGN.md, "Not built yet".)"""
+    _require_cuda()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    A = tf32_round(torch.randn(128, 32, device="cuda", generator=g))
+    Bm = tf32_round(torch.randn(64, 32, device="cuda", generator=g))
+    out = run_probe(A.contiguous().view(torch.uint8).reshape(-1), swizzled_image32(Bm), idesc(128, 64, fmt=2), 0, 0, 0,
+                    16, 1024, 32, 4, 64, 2 | TF32)
+    ref = A.double() @ Bm.double().T
+    assert torch.allclose(out.double(), ref, rtol=1e-5, atol=1e-4), float((out.double() - ref).abs().max())
