@@ -6,7 +6,12 @@
 A "step" is one pass of the hot path -- ``loss = FOCALLoss(f1, f2); loss.backward()`` w.r.t. all 2M feature
 tensors -- over one batch of synthetic MOD-shaped embeddings: B = 8192 rows (2048 sequences of S = 4 windows),
 M = 2 modalities, D = 256 (128 shared + 128 private), T = 0.5.  For N > 1 the same global batch is row-sharded
-over the ranks (strong scaling; launched by torchrun, one rank per GPU, NCCL).
+over the ranks (strong scaling; launched by torchrun, one rank per GPU; the ranks exchange operands through NVLink peer
+memory, NCCL carries only the set-up handshake and the timing reductions).
+
+``value`` is device-resident throughput (inputs in HBM, CUDA-graph replays, CUDA events, max over ranks); ``e2e`` is the
+same step through ``FOCALLoss.forward/backward`` with pinned HOST inputs: the H2D copy of every step and the D2H read of
+every step's loss are inside the timed region (copy of step k+1 and read-back of step k-1 overlap the kernels of step k).
 
 ``--impl reference`` times the reference's CPU implementation of the path on the host cores.  The reference is a
 pure-Python/PyTorch module that cannot travel to the GPU box, so its op-for-op port ``oracle/focal_ref_port.py``
@@ -315,24 +320,34 @@ def run_ours(args):
     module = focal_b200.FOCALLoss(args_ns).to(dev)
     if w["terms"] != 7:
         module._engine = FocalEngine(hp, process_group=group)      # sub-set of the terms (cfg4: InfoNCE only)
-    # Two device staging sets (ping-pong) fed from pinned host memory on a copy stream: the H2D copy of step k+1 overlaps the
-    # kernels of step k, like a pinned-memory data loader with non_blocking copies.  Every step still copies its own
-    # inputs host->device and reads its loss back to the host (a host sync per step, like pretrain.py:74).
-    stages_dev = [[torch.empty(Bl, D, device=dev) for _ in range(2 * M)] for _ in range(2)]
+    # Three device staging sets fed from pinned host memory on a copy stream, like a pinned-memory data loader with
+    # non_blocking copies: the H2D copy of step k+1 overlaps the kernels of step k.  Every step copies its own inputs
+    # host->device and reads its own loss back to the host; the read-back is asynchronous (pinned buffer + event) and the
+    # host picks the value of step k up after it has enqueued step k+1, so the GPU never idles on the host round trip.
+    NSLOT = 3
+    stages_dev = [[torch.empty(Bl, D, device=dev) for _ in range(2 * M)] for _ in range(NSLOT)]
     copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(NSLOT)]
+    consumed = [torch.cuda.Event() for _ in range(NSLOT)]
+    landed = [torch.cuda.Event() for _ in range(NSLOT)]
+    host_loss = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(NSLOT)]
+    e2e_losses = []
 
     def prefetch(k):
-        slot = k % 2
+        slot = k % NSLOT
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])            # the step that last used this slot has finished with it
             for dst, src in zip(stages_dev[slot], host_sets[k % nsets]):
                 dst.copy_(src, non_blocking=True)
             copied[slot].record(copy_stream)
 
-    def e2e_step(k):
-        slot = k % 2
+    def collect(k):
+        slot = k % NSLOT
+        landed[slot].synchronize()                            # the loss of step k is in host memory
+        e2e_losses.append(float(host_loss[slot]))
+
+    def e2e_step(k, collect_prev=True):
+        slot = k % NSLOT
         prefetch(k + 1)                                       # next step's inputs travel while this step computes
         torch.cuda.current_stream().wait_event(copied[slot])
         xs = [s_.detach().requires_grad_(True) for s_ in stages_dev[slot]]
@@ -340,17 +355,23 @@ def run_ours(args):
         loss = module(f1, f2)
         loss.backward()
         consumed[slot].record()
-        return float(loss.detach().cpu())          # D2H read of the step's result (host sync, like pretrain.py:74)
+        host_loss[slot].copy_(loss.detach(), non_blocking=True)   # D2H read of the step's result
+        landed[slot].record()
+        if collect_prev:
+            collect(k - 1)                                    # ... picked up one step later
 
     for ev in consumed:
         ev.record()
     prefetch(0)
-    for k in range(3 * nsets):
-        e2e_step(k)
+    n_e2e_warm = 3 * nsets
+    for k in range(n_e2e_warm):
+        e2e_step(k, collect_prev=k > 0)
+    collect(n_e2e_warm - 1)
     sync_all()
     ev0.record()
-    for k in range(3 * nsets, 3 * nsets + args.steps):
-        e2e_step(k)
+    for k in range(n_e2e_warm, n_e2e_warm + args.steps):
+        e2e_step(k, collect_prev=k > n_e2e_warm)
+    collect(n_e2e_warm + args.steps - 1)                      # the last loss is read inside the timed region too
     ev1.record()
     sync_all()
     te = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)

@@ -478,23 +478,16 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         // same sequence index), whose contribution the finalize kernel adds in fp32
         const bool overlap = col0 < row0 + kTileM && col0 + BN > row0;
         const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == side)) : overlap;
-#ifdef FB_EXP_LDTM_SKIP
-#define FB_CH_STEP FB_EXP_LDTM_SKIP      /* experiment only: touch every n-th chunk (wrong results) */
-#else
-#define FB_CH_STEP 1
-#endif
 #pragma unroll 1
-        for (int ch = sub; ch < BN / CW; ch += NW * FB_CH_STEP) {
+        for (int ch = sub; ch < BN / CW; ch += NW) {
           float v[CW];
           tmem_ld_chunk<CW>(s_addr + ch * CW, v);
           tmem_ld_wait();
           const int cbase = col0 + ch * CW;           // column (within side) of v[0]
           if (kIsNce) {
             // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
-#ifndef FB_EXP_TRIVIAL_EPI
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = ((j & 7) >= 8 - FB_POLY_PER8) ? ex2_poly(v[j]) : ex2_approx(v[j]);
-#endif
             if (MODE == NCE_BWD) {
               // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
 #pragma unroll
@@ -517,11 +510,6 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               rowacc += (s0 + s1) + (s2 + s3);
             }
           } else {
-#ifdef FB_EXP_TRIVIAL_EPI
-            // experiment only: no epilogue math (wrong results) -- how fast is the skeleton without it?
-#pragma unroll
-            for (int j = 0; j < CW; ++j) { v[j] *= coef1; rowacc += v[j]; }
-#else
             // ---------------- temporal: delta_ij, S x S block means, hinge, r_ij
             float nj[CW];
 #pragma unroll
@@ -557,7 +545,6 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
               for (int j = 0; j < SQ; ++j) { v[g0 + j] *= coef; rowacc += v[g0 + j]; }
             }
-#endif
           }
           if (kBwd) {
             // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed

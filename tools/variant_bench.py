@@ -14,10 +14,9 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = json.loads(os.environ.get("FB_VARIANTS", "null")) or {
     "base": {},
-    "pipe": {"FB_PIPE_LDTM": 1},
-    "poly1": {"FB_POLY_PER8": 1},
     "poly2": {"FB_POLY_PER8": 2},
-    "st2": {"FB_B_STAGES": 2},
+    "nosk": {"FB_STREAMK_TMP": -1, "FB_STREAMK_NCE": 0},
+    "kb4_3stages": {"FB_KB4_NB": 2},
 }
 
 
