@@ -416,6 +416,21 @@ def run_ours(args):
                     "note": "achieved = ALGORITHMIC FLOPs (SURVEY 8d: 3 GEMM-equivalents per contraction) / measured "
                             "launch time; executed_frac counts the FLOPs the kernel really issues; ncu's "
                             "sm__pipe_tensor_cycles_active (profiles/r1_ncu_summary.md) is quoted beside it"}
+        row_kernels = None
+        if stages is not None:
+            # the O(B D) kernels against the HBM roofline: algorithmic bytes = what must cross HBM once
+            feat_bytes = 2.0 * M * B * D * 4                                   # 2M fp32 [B, D] tensors
+            pro_bytes = feat_bytes + 2 * (2.0 * M * B * D * 2)                 # read features, write both bf16 operand sets
+            fin_bytes = feat_bytes + feat_bytes                                # read features, write gradients
+            if w["terms"] & 1:
+                fin_bytes += 2.0 * M * B * D * 4                               # + the InfoNCE accumulators (dz)
+            if w["terms"] & 4:
+                fin_bytes += 2.0 * M * B * D * 4                               # + the temporal accumulators (dx)
+            row_kernels = {"peak_GBps": peaks["hbm"], "peak_source": peaks["source"]}
+            for name, nbytes, key in (("prologue", pro_bytes, "prologue"), ("finalize", fin_bytes, "finalize")):
+                t_s = max(stages[key], 1e-6) * 1e-3
+                row_kernels[name] = {"alg_bytes": nbytes, "ms": stages[key], "GBps": nbytes / t_s / 1e9,
+                                     "frac_hbm": nbytes / t_s / 1e9 / peaks["hbm"]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -440,7 +455,7 @@ def run_ours(args):
                        "tiles": "bf16 operands, fp32 accumulation (tcgen05 kind::f16)"},
             "tensor_roofline_frac": F / (ms_step * 1e-3) / 1e12 / (peaks["tflops"] * world),   # of the N GPUs' peak
             "alg_tflops": F / (ms_step * 1e-3) / 1e12,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "row_kernels_hbm": row_kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": args.steps * launches_per_step(engine, B, D, world),
             "stages_ms": stages, "host_enqueue_ms_per_step": host_ms,
             "cuda_graph_replays": engine.graph_replays,
