@@ -156,20 +156,8 @@ int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, const PeerWs&
   }
   return FOCAL_ESHAPE;
 }
-template <int VW>
-int launch_finalize_fast_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, size_t smem, int grid,
-                            cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(finalize_fast_kernel<VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return cuda_ok("cudaFuncSetAttribute(finalize_fast_kernel)");
-    configured = smem;
-  }
-  finalize_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, g, w);
-  return cuda_ok("finalize_fast_kernel");
-}
 #ifndef FB_FINALIZE_RT
-#define FB_FINALIZE_RT 1          // 1: one warp per (row, tensor) when the launch is latency-bound; 0: one warp per row
+#define FB_FINALIZE_RT 1          // 1: one warp per (row, tensor) when the launch is latency-bound; 0: always one warp per row
 #endif
 template <int VW, int MAXT>
 int launch_finalize_rt_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
@@ -180,7 +168,7 @@ int launch_finalize_rt_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, co
       return cuda_ok("cudaFuncSetAttribute(finalize_rt_kernel)");
     configured = smem;
   }
-  finalize_rt_kernel<VW, MAXT><<<grid, 128 * p.nT, smem, st>>>(p, f, g, w);
+  finalize_rt_kernel<VW, MAXT><<<grid, MAXT > 0 ? 128 * p.nT : 128, smem, st>>>(p, f, g, w);
   return cuda_ok("finalize_rt_kernel");
 }
 template <int VW>
@@ -188,26 +176,18 @@ int launch_finalize_rt_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g, c
   // <= 4 tensors (M <= 2): 512-thread blocks, 128 registers per thread available; else 1024-thread blocks
   return p.nT <= 4 ? launch_finalize_rt_t<VW, 4>(p, f, g, w, grid, st) : launch_finalize_rt_t<VW, 8>(p, f, g, w, grid, st);
 }
-int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, size_t smem,
-                         int grid, cudaStream_t st) {
-  // Few rows (a row shard): the launch is one wave of blocks and its time is the dependent chain of one warp -> split
-  // every row over nT warps (measured 8192 / 8 rows: 41 -> 32 us).  Many rows: the row-per-warp kernel has the higher
-  // occupancy and fewer instructions (measured 8192 rows: 88 vs 116 us).
-  if (FB_FINALIZE_RT && p.nT <= 8 && grid <= 2 * p.num_sms && !(vw == 8 && p.nT > 4)) {   // (VW 8, 1024 threads) spills
-    switch (vw) {
-      case 1: return launch_finalize_rt_vw<1>(p, f, g, w, grid, st);
-      case 2: return launch_finalize_rt_vw<2>(p, f, g, w, grid, st);
-      case 3: return launch_finalize_rt_vw<3>(p, f, g, w, grid, st);
-      case 4: return launch_finalize_rt_vw<4>(p, f, g, w, grid, st);
-      case 8: return launch_finalize_rt_vw<8>(p, f, g, w, grid, st);
-    }
-  }
+int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid,
+                         cudaStream_t st) {
+  // Few rows (a row shard): the launch is one wave of blocks and its time is the dependent chain of one warp -> one warp
+  // per (row, tensor) (measured 1024 rows: 41 -> 32 us).  Many rows: one warp per row walking the tensors, compiled for
+  // 8 resident blocks per SM (measured 8192 rows: 79 us; (row, tensor) warps 116 us).  (VW 8, 1024 threads) would spill.
+  const bool rt = FB_FINALIZE_RT && p.nT <= 8 && grid <= 2 * p.num_sms && !(vw == 8 && p.nT > 4);
   switch (vw) {
-    case 1: return launch_finalize_fast_vw<1>(p, f, g, w, smem, grid, st);
-    case 2: return launch_finalize_fast_vw<2>(p, f, g, w, smem, grid, st);
-    case 3: return launch_finalize_fast_vw<3>(p, f, g, w, smem, grid, st);
-    case 4: return launch_finalize_fast_vw<4>(p, f, g, w, smem, grid, st);
-    case 8: return launch_finalize_fast_vw<8>(p, f, g, w, smem, grid, st);
+    case 1: return rt ? launch_finalize_rt_vw<1>(p, f, g, w, grid, st) : launch_finalize_rt_t<1, 0>(p, f, g, w, grid, st);
+    case 2: return rt ? launch_finalize_rt_vw<2>(p, f, g, w, grid, st) : launch_finalize_rt_t<2, 0>(p, f, g, w, grid, st);
+    case 3: return rt ? launch_finalize_rt_vw<3>(p, f, g, w, grid, st) : launch_finalize_rt_t<3, 0>(p, f, g, w, grid, st);
+    case 4: return rt ? launch_finalize_rt_vw<4>(p, f, g, w, grid, st) : launch_finalize_rt_t<4, 0>(p, f, g, w, grid, st);
+    case 8: return rt ? launch_finalize_rt_vw<8>(p, f, g, w, grid, st) : launch_finalize_rt_t<8, 0>(p, f, g, w, grid, st);
   }
   return FOCAL_ESHAPE;
 }
@@ -286,8 +266,7 @@ int do_finalize(const Plan& p, int no_private, const float* const* feats, float*
     const int rows = (p.seq1 - p.seq0) * p.S;
     const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, no_private) : 0;
     if (vw) {
-      const size_t smem = ((size_t)8 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);
-      if ((rc = launch_finalize_fast(vw, p, f, g, w, smem, (rows + 3) / 4, st))) return rc;
+      if ((rc = launch_finalize_fast(vw, p, f, g, w, (rows + 3) / 4, st))) return rc;
     } else {
       const size_t smem = (size_t)kRowsPerBlock * (2 * p.nT + 1) * p.D * sizeof(float);
       static size_t configured = 0;

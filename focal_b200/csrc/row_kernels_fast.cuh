@@ -233,232 +233,58 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fast finalize
+// fast finalize: gradient assembly per (row, tensor) -- temporal part, the InfoNCE operands 2t / 2t + 1 of the tensor,
+// the orthogonality pairs it takes part in -- with the gradient row in registers until it is stored.  4 rows per block.
+//   MAXT == 0: one warp per row walks the tensors in turn (4 warps per block, 16 KB of shared memory at D = 256, M = 2,
+//              compiled for 8 resident blocks per SM: the reductions are latency chains and want many warps);
+//   MAXT > 0:  one warp per (row, tensor), 4 * nT warps per block: for launches that are a single wave of blocks (row
+//              shards), where the dependent chain of one warp, not the issue rate, sets the time.
+// Both use the same per-tensor body in the same order, so they produce identical bits.
 // ---------------------------------------------------------------------------------------------------------
-template <int VW>
-__global__ void __launch_bounds__(128) finalize_fast_kernel(const __grid_constant__ Plan p,
-                                                            const __grid_constant__ FeatPtrs f,
-                                                            const __grid_constant__ GradPtrs g,
-                                                            const uint8_t* __restrict__ ws) {
-  extern __shared__ float smem_f[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = p.seq0 * p.S + blockIdx.x * 4 + warp;
-  const int D = p.D, d = p.d, S = p.S;
-  const bool live = i < p.seq1 * S;
-  float* xs = smem_f + (size_t)warp * p.nT * D;
-  float* gs = smem_f + (size_t)4 * p.nT * D + (size_t)warp * p.nT * D;
-  float* nrm = smem_f + (size_t)8 * p.nT * D + warp * 2 * kMaxT;
-  if (live) stage_rows(p, f, i, xs, lane);
-  __syncthreads();
-  if (!live) return;
-  const int I = i / S, s = i % S;
-  const uint64_t rowN = (uint64_t)s * p.bpad + I;
-  const int c0 = VW * lane;
-  const bool do_tmp = (p.terms & FOCAL_TERM_TEMPORAL) && p.b > 1 && S > 1;
-  const float bb = (float)p.b * (float)(p.b - 1);
-  const int Dp = p.kbFull * 64;
-
-  // ---- norms + temporal part (initialises the gradient rows in shared memory)
-  for (int t = 0; t < p.nT; ++t) {
-    float sh[VW], pr[VW];
-    ld_frag<VW>(xs + t * D + c0, sh);
-    ld_frag<VW>(xs + t * D + d + c0, pr);
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int e = 0; e < VW; ++e) { a = fmaf(sh[e], sh[e], a); b = fmaf(pr[e], pr[e], b); }
-    a = warp_sum(a); b = warp_sum(b);
-    if (lane == 0) { nrm[2 * t] = a; nrm[2 * t + 1] = b; }
-    float gsh[VW], gpr[VW];
-#pragma unroll
-    for (int e = 0; e < VW; ++e) { gsh[e] = 0.f; gpr[e] = 0.f; }
-    if (do_tmp) {
-      // a row block whose column tiles were split over several CTAs (stream-K) has one set of accumulators per piece
-      const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off) + (uint64_t)t * (p.Bpad / kTileM) + i / kTileM);
-      float rho = __ldg(reinterpret_cast<const float*>(ws + p.rho_off) + (uint64_t)t * p.Bpad + i);
-      const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
-      int cnt = __ldg(reinterpret_cast<const int32_t*>(ws + p.cnt_off) + (uint64_t)t * p.bpad + I);
-      float ysh[VW], ypr[VW];
-      ld_frag<VW>(y + c0, ysh);
-      ld_frag<VW>(y + d + c0, ypr);
-      for (int k = 1; k <= extra; ++k) {
-        const float* y2 = reinterpret_cast<const float*>(ws + p.dx_off + k * p.dx2_delta) + ((uint64_t)t * p.Bpad + i) * Dp;
-        float zsh[VW], zpr[VW];
-        ld_frag<VW>(y2 + c0, zsh);
-        ld_frag<VW>(y2 + d + c0, zpr);
-#pragma unroll
-        for (int e = 0; e < VW; ++e) { ysh[e] += zsh[e]; ypr[e] += zpr[e]; }
-        rho += __ldg(reinterpret_cast<const float*>(ws + p.rho_off + k * p.rho2_delta) + (uint64_t)t * p.Bpad + i);
-        cnt += __ldg(reinterpret_cast<const int32_t*>(ws + p.cnt_off + k * p.cnt2_delta) + (uint64_t)t * p.bpad + I);
-      }
-      float rsh[VW], rpr[VW];
-#pragma unroll
-      for (int e = 0; e < VW; ++e) {
-        rsh[e] = bf16_round(sh[e]); rpr[e] = bf16_round(pr[e]);
-        gsh[e] = p.w_rank * (rsh[e] * rho - ysh[e]);
-        gpr[e] = p.w_rank * (rpr[e] * rho - ypr[e]);
-      }
-      // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
-      const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
-      if (cnt > 0) {
-        const int w0 = warp - s;
-        for (int j = 0; j < S; ++j) {
-          if (j == s) continue;
-          const float* xo = smem_f + (size_t)(w0 + j) * p.nT * D + t * D;
-          float osh[VW], opr[VW];
-          ld_frag<VW>(xo + c0, osh);
-          ld_frag<VW>(xo + d + c0, opr);
-          float d2 = 0.f;
-#pragma unroll
-          for (int e = 0; e < VW; ++e) {
-            osh[e] = rsh[e] - bf16_round(osh[e]); opr[e] = rpr[e] - bf16_round(opr[e]);
-            d2 = fmaf(osh[e], osh[e], fmaf(opr[e], opr[e], d2));
-          }
-          d2 = warp_sum(d2);
-          if (d2 > 0.f) {
-            const float r = coef * rsqrtf(d2);
-#pragma unroll
-            for (int e = 0; e < VW; ++e) { gsh[e] = fmaf(r, osh[e], gsh[e]); gpr[e] = fmaf(r, opr[e], gpr[e]); }
-          }
-        }
-      }
-    }
-    st_frag<VW>(gs + t * D + c0, gsh);
-    st_frag<VW>(gs + t * D + d + c0, gpr);
-  }
-  __syncwarp();
-
-  // ---- InfoNCE (standard topology: operand o = 2 t + half, width d)
-  if (p.terms & FOCAL_TERM_NCE) {
-    const float inv_tsn = 1.f / (p.T * (float)S * (float)(2 * p.b));
-    const float inv_alpha = 1.f / p.alpha;
-    for (int o = 0; o < p.nOps; ++o) {
-      const OpDesc& op = p.ops[o];
-      if (op.nuse == 0) continue;
-      const int wp = op.kb * 64;
-      const float ssk = nrm[2 * op.tensor + (op.col0 ? 1 : 0)];
-      const float inv_nk = fminf(rsqrtf(ssk), 1.f / kNceEps);        // 1 / max(|z|, eps)
-      const float fk = p.alpha * inv_nk;
-      float x[VW], tmp[VW];
-      ld_frag<VW>(xs + op.tensor * D + op.col0 + c0, x);
-#pragma unroll
-      for (int e = 0; e < VW; ++e) tmp[e] = 0.f;
-      for (int u = 0; u < op.nuse; ++u) {
-        const int q = op.use_prob[u], side = op.use_side[u];
-        const ProbDesc& pr = p.probs[q];
-        const OpDesc& po = p.ops[op.use_partner[u]];                  // partner operand: positive row p(k)
-        const float fp = p.alpha * fminf(rsqrtf(nrm[2 * po.tensor + (po.col0 ? 1 : 0)]), 1.f / kNceEps);
-        float px[VW], acc[VW];
-        ld_frag<VW>(xs + po.tensor * D + po.col0 + c0, px);
-        ld_frag<VW>(reinterpret_cast<const float*>(ws + pr.dz_off) + ((uint64_t)side * S * p.bpad + rowN) * wp + c0, acc);
-        const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_nce_off) +
-                                (((uint64_t)q * S + s) * 2 + side) * (p.bpad / kTileM) + I / kTileM);
-        for (int k = 1; k <= extra; ++k) {
-          float acc2[VW];
-          ld_frag<VW>(reinterpret_cast<const float*>(ws + pr.dz_off + k * p.dz2_delta) + ((uint64_t)side * S * p.bpad + rowN) * wp + c0, acc2);
-#pragma unroll
-          for (int e = 0; e < VW; ++e) acc[e] += acc2[e];
-        }
-        const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
-        const float r_k = __ldg(rs + (uint64_t)side * p.bpad + I), r_p = __ldg(rs + (uint64_t)(1 - side) * p.bpad + I);
-        // positive column in fp32 (masked out of the tiles): W_kp - 2 is a tiny difference when the positive dominates
-        float gpos = 0.f;
-#pragma unroll
-        for (int e = 0; e < VW; ++e) { px[e] = bf16_round(px[e] * fp); gpos = fmaf(bf16_round(x[e] * fk), px[e], gpos); }
-        gpos = warp_sum(gpos);
-        const float wkp = ex2_approx(gpos) * (__frcp_rn(r_k) + __frcp_rn(r_p));
-        const float wq = pr.weight * inv_tsn * inv_alpha;
-#pragma unroll
-        for (int e = 0; e < VW; ++e) tmp[e] = fmaf(wq, fmaf(wkp - 2.f, px[e], acc[e]), tmp[e]);
-      }
-      float dot = 0.f;                                // d zh / d z = (I - zh zh^T) / n
-#pragma unroll
-      for (int e = 0; e < VW; ++e) dot = fmaf(tmp[e], x[e], dot);
-      dot = warp_sum(dot) * inv_nk * inv_nk;
-      float go[VW];
-      ld_frag<VW>(gs + op.tensor * D + op.col0 + c0, go);
-#pragma unroll
-      for (int e = 0; e < VW; ++e) go[e] = fmaf(fmaf(-dot, x[e], tmp[e]), inv_nk, go[e]);
-      st_frag<VW>(gs + op.tensor * D + op.col0 + c0, go);
-    }
-  }
-
-  // ---- orthogonality
-  if (p.terms & FOCAL_TERM_ORTH) {
-    for (int k = 0; k < p.nOrth; ++k) {
-      const OrthDesc& od = p.orth[k];
-      float u[VW], v[VW];
-      ld_frag<VW>(xs + od.tu * D + od.cu + c0, u);
-      ld_frag<VW>(xs + od.tv * D + od.cv + c0, v);
-      float dot = 0.f;
-#pragma unroll
-      for (int e = 0; e < VW; ++e) dot = fmaf(u[e], v[e], dot);
-      dot = warp_sum(dot);
-      const float nu = nrm[2 * od.tu + (od.cu ? 1 : 0)] + kOrthEps;
-      const float nv = nrm[2 * od.tv + (od.cv ? 1 : 0)] + kOrthEps;
-      const float inv_den = rsqrtf(nu * nv);
-      const float cs = dot * inv_den;
-      if (cs >= 0.f) {                                    // clamp_min passes gradient at equality
-        const float a = p.w_orth / (float)p.B;
-        const float ad = a * inv_den, au = -a * cs * __frcp_rn(nu), av = -a * cs * __frcp_rn(nv);
-        float gu[VW], gv[VW];
-        ld_frag<VW>(gs + od.tu * D + od.cu + c0, gu);
-        ld_frag<VW>(gs + od.tv * D + od.cv + c0, gv);
-#pragma unroll
-        for (int e = 0; e < VW; ++e) {
-          gu[e] = fmaf(ad, v[e], fmaf(au, u[e], gu[e]));
-          gv[e] = fmaf(ad, u[e], fmaf(av, v[e], gv[e]));
-        }
-        st_frag<VW>(gs + od.tu * D + od.cu + c0, gu);
-        st_frag<VW>(gs + od.tv * D + od.cv + c0, gv);
-      }
-    }
-  }
-  __syncwarp();
-  const int nv4 = D >> 2;
-  for (int t = 0; t < p.nT; ++t) {
-    float4* out = reinterpret_cast<float4*>(g.g[t] + (size_t)i * D);
-    const float4* src = reinterpret_cast<const float4*>(gs + t * D);
-    for (int c = lane; c < nv4; c += 32) out[c] = src[c];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// fast finalize, one warp per (row, tensor): 4 rows x nT tensors per block.  Same arithmetic as
-// finalize_fast_kernel in the same order per (row, tensor), so both produce identical bits; the dependent chain
-// per warp is 1/nT as long (a row shard's finalize is latency-bound: 256 blocks for 148 SMs) and the gradient row
-// never leaves the registers until it is stored.
-// ---------------------------------------------------------------------------------------------------------
+#ifndef FB_FIN_MINB
+#define FB_FIN_MINB 8            // resident blocks per SM the row-walk variant is compiled for (measured: 4 / 6 / 8 / 10
+#endif                           // blocks -> 107 / 94 / 79 / 92 us at 8192 rows; 8 = 64 registers, small spill)
 template <int VW, int MAXT>
-__global__ void __launch_bounds__(128 * MAXT) finalize_rt_kernel(const __grid_constant__ Plan p,
+__global__ void __launch_bounds__(MAXT > 0 ? 128 * MAXT : 128, MAXT > 0 ? 1 : (VW > 4 ? 4 : FB_FIN_MINB))
+finalize_rt_kernel(const __grid_constant__ Plan p,
                                                            const __grid_constant__ FeatPtrs f,
                                                            const __grid_constant__ GradPtrs g,
                                                            const uint8_t* __restrict__ ws) {
   extern __shared__ float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nT = p.nT, D = p.D, d = p.d, S = p.S;
-  const int r = warp / nT, t = warp - r * nT;        // row within the block, tensor
+  const int r = MAXT > 0 ? warp / nT : warp;         // row within the block
+  const int t_begin = MAXT > 0 ? warp - r * nT : 0, t_end = MAXT > 0 ? t_begin + 1 : nT;      // tensors of this warp
   const int i = p.seq0 * S + blockIdx.x * 4 + r;
   const bool live = i < p.seq1 * S;
   float* xs = smem_f + (size_t)r * nT * D;           // the nT tensors of this row
   float* nrm = smem_f + (size_t)4 * nT * D + r * 2 * kMaxT;
   const int c0 = VW * lane;
-  float sh[VW], pr[VW];
   if (live) {
-    const float* src = f.x[t] + feat_row_off(p, i);
-    ld_frag<VW>(src + c0, sh);
-    ld_frag<VW>(src + d + c0, pr);
-    st_frag<VW>(xs + t * D + c0, sh);
-    st_frag<VW>(xs + t * D + d + c0, pr);
-    float a = 0.f, b = 0.f;
+    const size_t roff = feat_row_off(p, i);
+    for (int t = t_begin; t < t_end; ++t) {
+      float sh[VW], pr[VW];
+      const float* src = f.x[t] + roff;
+      ld_frag<VW>(src + c0, sh);
+      ld_frag<VW>(src + d + c0, pr);
+      st_frag<VW>(xs + t * D + c0, sh);
+      st_frag<VW>(xs + t * D + d + c0, pr);
+      float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int e = 0; e < VW; ++e) { a = fmaf(sh[e], sh[e], a); b = fmaf(pr[e], pr[e], b); }
-    a = warp_sum(a); b = warp_sum(b);
-    if (lane == 0) { nrm[2 * t] = a; nrm[2 * t + 1] = b; }
+      for (int e = 0; e < VW; ++e) { a = fmaf(sh[e], sh[e], a); b = fmaf(pr[e], pr[e], b); }
+      a = warp_sum(a); b = warp_sum(b);
+      if (lane == 0) { nrm[2 * t] = a; nrm[2 * t + 1] = b; }
+    }
   }
   __syncthreads();
   if (!live) return;
   const int I = i / S, s = i % S;
   const uint64_t rowN = (uint64_t)s * p.bpad + I;
+#pragma unroll 1
+  for (int t = t_begin; t < t_end; ++t) {
+  float sh[VW], pr[VW];
+  ld_frag<VW>(xs + t * D + c0, sh);
+  ld_frag<VW>(xs + t * D + d + c0, pr);
   float gsh[VW], gpr[VW];
 #pragma unroll
   for (int e = 0; e < VW; ++e) { gsh[e] = 0.f; gpr[e] = 0.f; }
@@ -610,6 +436,7 @@ __global__ void __launch_bounds__(128 * MAXT) finalize_rt_kernel(const __grid_co
   float* out = g.g[t] + (size_t)i * D;
   st_frag<VW>(out + c0, gsh);
   st_frag<VW>(out + d + c0, gpr);
+  }  // tensors of this warp
 }
 
 }  // namespace fb
