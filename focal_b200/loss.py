@@ -39,9 +39,11 @@ class _FocalLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out: torch.Tensor):
         grads = ctx.saved_tensors
-        # grad_out is a 0-dim device tensor: scale on the device, no host sync
-        out = tuple(g * grad_out if need else None for g, need in zip(grads, ctx.needs_input_grad[2:]))
-        return (None, None) + out
+        needs = ctx.needs_input_grad[2:]
+        # grad_out is a 0-dim device tensor: scale on the device, no host sync; one multi-tensor launch for all inputs
+        wanted = [g for g, need in zip(grads, needs) if need]
+        scaled = iter(torch._foreach_mul(wanted, grad_out)) if wanted else iter(())
+        return (None, None) + tuple(next(scaled) if need else None for need in needs)
 
 
 class FOCALLoss(nn.Module):
