@@ -49,6 +49,10 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_POLY_PER8
 #define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
 #endif
+#ifndef FB_POLY_FWD_PER8
+#define FB_POLY_FWD_PER8 2      // same, for the row-sum pass only: that pass is MUFU-bound (67 % XU), and a degree-4
+#endif                          // polynomial (rel. error 2.7e-6) for 2 of 8 columns took it from 93 to 84 us (0/1/2/3/4
+                                // of 8: 93.3 / 89.1 / 84.0 / 84.8 / 87.1 us); the backward pass gains nothing from it
 constexpr int kTmemCols = 512;
 
 // Tile configuration as a function of the mode and the operand width in 64-element K blocks (see header comment).
@@ -487,7 +491,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           if (kIsNce) {
             // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
 #pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = ((j & 7) >= 8 - FB_POLY_PER8) ? ex2_poly(v[j]) : ex2_approx(v[j]);
+            for (int j = 0; j < CW; ++j)
+              v[j] = ((j & 7) >= 8 - (MODE == NCE_FWD ? FB_POLY_FWD_PER8 : FB_POLY_PER8)) ? ex2_poly(v[j]) : ex2_approx(v[j]);
             if (MODE == NCE_BWD) {
               // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
 #pragma unroll
