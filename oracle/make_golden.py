@@ -52,6 +52,9 @@ CASES = [
          seq_len=1),
     dict(name="edge_ragged_b", gen="structured", seed=12, mods=["seismic", "audio"], B=4 * 37, D=96,
          model="SW_Transformer"),
+    # cfg 5 embedding width (shared 256 + private 256): the wide temporal mode of the CUDA path
+    dict(name="kat6_d512", gen="structured", seed=13, mods=["seismic", "audio"], B=128, D=512, model="DeepSense"),
+    dict(name="kat7_d320_m3", gen="iid", seed=14, mods=["acc", "gyr", "mag"], B=4 * 21, D=320, model="DeepSense"),
 ]
 
 
@@ -145,7 +148,10 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    only = set(sys.argv[1:])          # optional: regenerate just the named cases
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         f1, f2 = build_inputs(case)
         rec = {}
         r32 = run_reference(case, torch.float32)
