@@ -53,6 +53,12 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #define FB_POLY_FWD_PER8 2      // same, for the row-sum pass only: that pass is MUFU-bound (67 % XU), and a degree-4
 #endif                          // polynomial (rel. error 2.7e-6) for 2 of 8 columns took it from 93 to 84 us (0/1/2/3/4
                                 // of 8: 93.3 / 89.1 / 84.0 / 84.8 / 87.1 us); the backward pass gains nothing from it
+#ifndef FB_KB8_NS
+#define FB_KB8_NS 2             // wide mode (8 K blocks): with one B stage the tiles are serial, so what counts is the
+#endif                          // latency of one tile's epilogue: two warpgroups share it (NS x NW = 4 x 1 -> 2 x 2 took
+#ifndef FB_KB8_NW               // the temporal launch of B = 4096, M = 4, D = 512 from 1118 to 899 us)
+#define FB_KB8_NW 2
+#endif
 constexpr int kTmemCols = 512;
 
 // Tile configuration as a function of the mode and the operand width in 64-element K blocks (see header comment).
@@ -60,10 +66,10 @@ template <int MODE, int KB, int SEQ>
 struct GramCfg {
   static constexpr bool kBwd = (MODE == 1 || MODE == 3);
   static constexpr bool kTmp = (MODE >= 2);
-  static constexpr int BN = KB <= 2 ? 128 : (KB == 4 ? FB_KB4_BN : 64);          // column tile
-  static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : 4);  // S stages == epilogue warpgroups
+  static constexpr int BN = tile_bn(KB);                                         // column tile
+  static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : (KB == 8 ? FB_KB8_NS : 4));  // S stages
   static constexpr int NB = KB <= 3 ? 5 : (KB == 4 ? FB_KB4_NB : 1);             // B-tile ring stages (smem budget)
-  static constexpr int NW = (KB == 4 && SEQ <= 16) ? FB_KB4_NW : 1;              // warpgroups per S stage
+  static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? FB_KB4_NW : (KB == 8 ? FB_KB8_NW : 1));   // warpgroups per S stage
   static constexpr int NG = NS * NW;                                             // epilogue warpgroups in total
   static constexpr int CW = (NG == 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
   static constexpr int kThreads = 64 + 128 * NG;

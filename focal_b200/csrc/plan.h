@@ -38,7 +38,10 @@ struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
 #ifndef FB_KB4_BN
 #define FB_KB4_BN 96
 #endif
-constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : (kb == 4 ? FB_KB4_BN : 64); }
+#ifndef FB_KB8_BN
+#define FB_KB8_BN 64
+#endif
+constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : (kb == 4 ? FB_KB4_BN : (kb == 8 ? FB_KB8_BN : 64)); }
 
 // Problems handled by one InfoNCE launch (all with the same operand width / K-block count).
 struct ProbSel {

@@ -26,12 +26,14 @@ def build():
     for f in glob.glob(os.path.join(ROOT, "focal_b200", "libfocal_b200_*.so")):
         os.remove(f)
     with ThreadPoolExecutor(max_workers=4) as ex:
-        futs = {tag: ex.submit(b.build_variant, tag, dict(d, FB_FAST_BUILD=1)) for tag, d in VARIANTS.items()}
+        fast = {} if os.environ.get('FB_FULL_BUILD') else {'FB_FAST_BUILD': 1}
+        futs = {tag: ex.submit(b.build_variant, tag, dict(d, **fast)) for tag, d in VARIANTS.items()}
         for tag, f in futs.items():
             print(tag, f.result())
 
 
-def run(B=8192, D=256, M=2, S=4, steps=30):
+def run(B=int(os.environ.get('FB_B', 8192)), D=int(os.environ.get('FB_D', 256)), M=int(os.environ.get('FB_M', 2)), S=4,
+        steps=int(os.environ.get('FB_STEPS', 30))):
     import torch
     from focal_b200 import _cabi
     mods = [f"m{i}" for i in range(M)]
