@@ -184,42 +184,6 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
 // leaves fewer row blocks than SMs.  All SMs stay busy until the end of the launch (with whole row blocks 256 equal
 // items on 148 SMs ran 2 rounds for 1.73 rounds of work).  Piece k writes to its own copy of the accumulators
 // (dz / dx / rho / cnt / row sums + k * delta) and finalize adds them in piece order, so the result is deterministic.
-struct PieceIter {
-  long u, u1, share;
-  int T, item_, n_items_;
-  bool streamk;
-  __device__ __forceinline__ PieceIter(int n_items, int tiles_per_item, bool use_streamk) {
-    T = tiles_per_item;
-    streamk = use_streamk;
-    n_items_ = n_items;
-    item_ = blockIdx.x;
-    const long total = (long)n_items * T;
-    share = (total + gridDim.x - 1) / gridDim.x;
-    u = (long)blockIdx.x * share;
-    u1 = u + share < total ? u + share : total;
-  }
-  // next piece of this CTA: row block `item`, column tiles [t0, t1); pk = index of the piece within its row block,
-  // npi = number of pieces the row block is cut into
-  __device__ __forceinline__ bool next(int& item, int& t0, int& t1, int& pk, int& npi) {
-    if (!streamk) {                       // whole row blocks, CTA-strided
-      if (item_ >= n_items_) return false;
-      item = item_; t0 = 0; t1 = T; pk = 0; npi = 1;
-      item_ += gridDim.x;
-      return true;
-    }
-    if (u >= u1) return false;
-    item = (int)(u / T);
-    const long i0 = (long)item * T;
-    t0 = (int)(u - i0);
-    const long rest = u1 - u;
-    t1 = (long)(T - t0) <= rest ? T : (int)(t0 + rest);
-    const int cfirst = (int)(i0 / share);
-    pk = (int)blockIdx.x - cfirst;
-    npi = (int)((i0 + T - 1) / share) - cfirst + 1;
-    u += t1 - t0;
-    return true;
-  }
-};
 template <int MODE, int BN>
 __device__ __forceinline__ int gram_tiles_per_item(const Plan& p) {
   return (MODE == NCE_FWD || MODE == NCE_BWD) ? 2 * ((p.b + BN - 1) / BN) : (p.B + BN - 1) / BN;
@@ -310,7 +274,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     // =============================== TMA producer ===============================
     {
       uint32_t nb = 0, ni = 0;
-      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
+      PieceIter pieces((int)blockIdx.x, (int)gridDim.x, n_items, gram_tiles_per_item<MODE, BN>(p),
+                       (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
       for (int it, pt0, pt1, pk, npi; pieces.next(it, pt0, pt1, pk, npi); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
@@ -353,7 +318,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
       const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
       uint32_t nb = 0, ni = 0;
-      PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
+      PieceIter pieces((int)blockIdx.x, (int)gridDim.x, n_items, gram_tiles_per_item<MODE, BN>(p),
+                       (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
       for (int it, pt0, pt1, pk, npi; pieces.next(it, pt0, pt1, pk, npi); ++ni) {
         Item x;
         gram_decode<MODE, BN>(p, sel, ws, it, x);
@@ -456,7 +422,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     const uint32_t cv_base = smem_u32(smem + L::kBOff + L::kBTile);
     const uint32_t s_addr = tmem + tlane + kSCol + wg * BN;
     uint32_t nb = 0, ni = 0;
-    PieceIter pieces(n_items, gram_tiles_per_item<MODE, BN>(p), (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
+    PieceIter pieces((int)blockIdx.x, (int)gridDim.x, n_items, gram_tiles_per_item<MODE, BN>(p),
+                       (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
     for (int it, pt0, pt1, pk, npi; pieces.next(it, pt0, pt1, pk, npi); ++ni) {
       Item x;
       gram_decode<MODE, BN>(p, sel, ws, it, x);

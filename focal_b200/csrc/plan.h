@@ -1,10 +1,17 @@
 // Host-side plan: problem topology (loss.py:162-209 loop structure) and workspace layout in HBM.
 #pragma once
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
 
 #include "../../include/focal_b200.h"
+
+#ifdef __CUDACC__
+#define FB_HD __host__ __device__ __forceinline__
+#else
+#define FB_HD inline
+#endif
 
 namespace fb {
 
@@ -100,7 +107,7 @@ struct PeerWs {
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // element offset of row i inside a (possibly row-blocked) feature tensor
-__host__ __device__ inline size_t feat_row_off(const Plan& p, int i) {
+FB_HD size_t feat_row_off(const Plan& p, int i) {
   return (size_t)(i / p.in_rb) * (size_t)p.in_bs + (size_t)(i % p.in_rb) * (size_t)p.D;
 }
 
@@ -130,8 +137,47 @@ inline int piece_grid(int n_items, int T, int num_sms, bool streamk, int* np) {
     if (worst <= kMaxPieces || grid == 1) { *np = worst; return (int)grid; }
   }
 }
-__host__ __device__ inline int nce_row_tiles(const Plan& p) { return (p.seq1 + kTileM - 1) / kTileM - p.seq0 / kTileM; }
-__host__ __device__ inline int tmp_row_tiles(const Plan& p) {
+// The share of one CTA of a stream-K launch, piece by piece (device: the three roles of gram_kernel walk it in step;
+// host: tests/csrc/test_plan.cpp checks that the pieces of all CTAs tile the launch exactly once).
+struct PieceIter {
+  long u, u1, share;
+  int T, item_, n_items_, cta_, grid_;
+  bool streamk;
+  FB_HD PieceIter(int cta, int grid, int n_items, int tiles_per_item, bool use_streamk) {
+    T = tiles_per_item;
+    streamk = use_streamk;
+    n_items_ = n_items;
+    item_ = cta; cta_ = cta; grid_ = grid;
+    const long total = (long)n_items * T;
+    share = (total + grid - 1) / grid;
+    u = (long)cta * share;
+    u1 = u + share < total ? u + share : total;
+  }
+  // next piece of this CTA: row block `item`, column tiles [t0, t1); pk = index of the piece within its row block,
+  // npi = number of pieces the row block is cut into
+  FB_HD bool next(int& item, int& t0, int& t1, int& pk, int& npi) {
+    if (!streamk) {                       // whole row blocks, CTA-strided
+      if (item_ >= n_items_) return false;
+      item = item_; t0 = 0; t1 = T; pk = 0; npi = 1;
+      item_ += grid_;
+      return true;
+    }
+    if (u >= u1) return false;
+    item = (int)(u / T);
+    const long i0 = (long)item * T;
+    t0 = (int)(u - i0);
+    const long rest = u1 - u;
+    t1 = (long)(T - t0) <= rest ? T : (int)(t0 + rest);
+    const int cfirst = (int)(i0 / share);
+    pk = cta_ - cfirst;
+    npi = (int)((i0 + T - 1) / share) - cfirst + 1;
+    u += t1 - t0;
+    return true;
+  }
+};
+
+FB_HD int nce_row_tiles(const Plan& p) { return (p.seq1 + kTileM - 1) / kTileM - p.seq0 / kTileM; }
+FB_HD int tmp_row_tiles(const Plan& p) {
   return (p.seq1 * p.S + kTileM - 1) / kTileM - (p.seq0 * p.S) / kTileM;
 }
 #ifndef FB_STREAMK_TMP
