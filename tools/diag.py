@@ -3,9 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oracle import focal_oracle as fo
-from tests._golden import CASE_BY_NAME, config_of, load_case
+from tests._golden import config_of, load_case
 from focal_b200.engine import CudaBackend, FocalHyper
-from focal_b200 import _cabi
 import dataclasses
 
 names = sys.argv[1:] or ["kat4_m4"]
