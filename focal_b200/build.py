@@ -13,13 +13,13 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libfocal_b200.so")
 SOURCES = [os.path.join(CSRC, "focal_b200.cu")]
-HEADERS = [os.path.join(CSRC, n) for n in ("ptx.cuh", "plan.h", "gram_kernel.cuh", "row_kernels.cuh")] + [
+HEADERS = sorted(os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cuh", ".h"))) + [
     os.path.join(os.path.dirname(PKG_DIR), "include", "focal_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--use_fast_math=false" if False else "-Xptxas=-v",
+    "-Xptxas=-v",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
