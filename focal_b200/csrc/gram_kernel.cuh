@@ -11,15 +11,20 @@
 // laid out in HBM exactly as the UMMA wants them in shared memory (K-block-major, 128-byte rows, SWIZZLE_128B),
 // so each tile is a single linear TMA bulk copy per K block.
 //
-// Roles (64 + 128*NS threads): warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM owner), then NS epilogue
-// warpgroups; warpgroup w owns S stage w in TMEM and handles the column tiles n with n % NS == w (within a warpgroup
-// each warp owns one TMEM lane quarter).  NS = 3 or 4 puts 3-4 epilogue warps on every SM sub-partition (their
-// MUFU / FMA dependency chains hide behind each other) and lets UMMA #1 run NS-1 tiles ahead of the epilogue, so
-// the issuer <-> epilogue round trip is off the critical path (with NS = 2 it was the bound: profiles/r1_ncu_summary.md).
+// Roles (64 + 128*NS*NW threads): warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM owner), then NS*NW epilogue
+// warpgroups; S stage w in TMEM belongs to NW warpgroups (they split its 16-column chunks) and takes the column tiles n
+// with n % NS == w (within a warpgroup each warp owns one TMEM lane quarter).  Narrow operands (<= 128 columns): NS =
+// 3 or 4, NW = 1: 3-4 epilogue warps on every SM sub-partition (their MUFU / FMA dependency chains hide behind each
+// other) and UMMA #1 runs NS-1 tiles ahead of the epilogue.  256-column operands: the O accumulator leaves room for
+// NS = 2 stages only, so two warpgroups share each tile's epilogue (GramCfg).
 //
-// Tensor memory (512 columns): backward modes: O accumulator [0, KB*64), S stages at KB*64 + w*BN; forward modes:
-// S stages at w*BN.  In the backward modes the epilogue overwrites the S stage it just consumed with W as packed
+// Tensor memory (512 columns): backward modes: O accumulator [0, min(KB,4)*64), S stages behind it at w*BN; forward
+// modes: S stages at w*BN.  In the backward modes the epilogue overwrites the S stage it just consumed with W as packed
 // bf16 (tcgen05.st) and UMMA #2 reads its A operand straight from TMEM -- W never touches shared memory.
+//
+// Work split: stream-K over (row block, column tile) pairs (PieceIter in plan.h), one accumulator copy per piece.
+// Wide mode (KB = 8, 256 < D <= 512): A tile 128 KB resident, one B stage, O holds one 256-column half of dx per
+// pass.  Row-sharded multi-GPU launches wait at their start for the peers' announcements (peer.cuh).
 //
 // Measured on B200 (tools/umma_rate.py): one thread can issue a tcgen05.mma about every 45 clk and an M=128, K=16
 // instruction occupies the tensor pipe N/2 clk, so N >= 96 is needed to stay tensor-bound; the issue loop below is
