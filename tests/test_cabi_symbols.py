@@ -55,6 +55,33 @@ def test_struct_layouts_match_the_header():
     assert fields == [f[0] for f in _cabi.FocalCfg._fields_]
 
 
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """Sizes and field offsets of every struct of include/focal_b200.h as a C compiler lays them out == the ctypes mirror."""
+    import shutil
+    import subprocess
+    from focal_b200 import _cabi
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"FocalCfg": _cabi.FocalCfg, "FocalWsInfo": _cabi.FocalWsInfo, "FocalPeers": _cabi.FocalPeers}
+    lines = []
+    for sname, cls in structs.items():
+        lines.append(f'printf("{sname} %zu\\n", sizeof({sname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{sname}.{fname} %zu\\n", offsetof({sname}, {fname}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "focal_b200.h"\nint main(void) {\n'
+                   + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = str(tmp_path / "layout")
+    res = subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines())
+    for sname, cls in structs.items():
+        assert int(out[sname]) == C.sizeof(cls), sname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{sname}.{fname}"]) == getattr(cls, fname).offset, f"{sname}.{fname}"
+
+
 def test_workspace_info_and_error_codes_without_a_gpu(lib):
     from focal_b200 import _cabi
 
