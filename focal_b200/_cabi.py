@@ -11,15 +11,15 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libfocal_b200.so")
 
 FOCAL_TERM_NCE, FOCAL_TERM_ORTH, FOCAL_TERM_TEMPORAL, FOCAL_TERM_ALL = 1, 2, 4, 7
-FOCAL_PREC_BF16 = 0
+FOCAL_PREC_BF16, FOCAL_PREC_TF32 = 0, 1
 FOCAL_MAX_MODALITIES = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 FOCAL_OK, FOCAL_EINVAL, FOCAL_ESHAPE, FOCAL_ECUDA, FOCAL_EWORKSPACE = 0, -1, -2, -3, -4
 
 EXPORTS = (
     "focal_b200_abi_version", "focal_b200_strerror", "focal_b200_workspace_info", "focal_b200_prologue",
     "focal_b200_nce_rowsum", "focal_b200_nce_lse", "focal_b200_nce_grad", "focal_b200_temporal",
-    "focal_b200_finalize", "focal_b200_loss", "focal_b200_debug_umma",
+    "focal_b200_finalize", "focal_b200_loss", "focal_b200_set_ptrs",
     "focal_b200_peer_alloc", "focal_b200_peer_open", "focal_b200_peer_close", "focal_b200_peer_free",
     "focal_b200_loss_sharded",
 )
@@ -34,7 +34,7 @@ class FocalCfg(C.Structure):
         ("no_private", C.c_int32), ("need_grad", C.c_int32), ("terms", C.c_int32), ("precision", C.c_int32),
         ("seq_begin", C.c_int32), ("seq_end", C.c_int32), ("num_sms", C.c_int32),
         ("in_block_rows", C.c_int32), ("in_block_stride", C.c_int32),
-        ("local_rows", C.c_int32),
+        ("local_rows", C.c_int32), ("indirect_ptrs", C.c_int32),
     ]
 
 
@@ -88,12 +88,12 @@ def load(path: str | None = None) -> C.CDLL:
     lib.focal_b200_temporal.argtypes = [cfgp, vp, C.c_size_t, vp]
     lib.focal_b200_finalize.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
     lib.focal_b200_loss.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
+    lib.focal_b200_set_ptrs.argtypes = [cfgp, vp, C.c_size_t, C.POINTER(vp), vp, C.POINTER(vp), vp]
     lib.focal_b200_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
     lib.focal_b200_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     lib.focal_b200_peer_close.argtypes = [vp]
     lib.focal_b200_peer_free.argtypes = [vp]
     lib.focal_b200_loss_sharded.argtypes = [cfgp, C.POINTER(vp), C.POINTER(FocalPeers), C.c_size_t, vp, C.POINTER(vp), vp]
-    lib.focal_b200_debug_umma.argtypes = [vp, C.c_uint32, vp, C.c_uint32] + [C.c_uint32] * 10 + [vp, vp]
     for name in EXPORTS:
         if name != "focal_b200_strerror":
             getattr(lib, name).restype = C.c_int
@@ -102,6 +102,27 @@ def load(path: str | None = None) -> C.CDLL:
     if path == LIB_PATH:
         _lib = lib
     return lib
+
+
+BRINGUP_PATH = os.path.join(_PKG, "libfocal_bringup.so")
+_bringup = None
+
+
+def load_bringup() -> C.CDLL:
+    """Hardware probes / micro-benchmarks (focal_b200/csrc/bringup.h): tests and tools only, never the product path."""
+    global _bringup
+    if _bringup is None:
+        if not os.path.exists(BRINGUP_PATH):
+            raise ImportError(f"{BRINGUP_PATH} not found: build it with `python -m focal_b200.build`")
+        lib = C.CDLL(BRINGUP_PATH)
+        vp = C.c_void_p
+        lib.focal_b200_debug_umma.argtypes = [vp, C.c_uint32, vp, C.c_uint32] + [C.c_uint32] * 10 + [vp, vp]
+        lib.focal_b200_debug_umma_rate.argtypes = [C.c_uint32] * 5 + [vp, vp]
+        lib.focal_b200_debug_tma_rate.argtypes = [vp] + [C.c_uint32] * 6 + [vp, vp]
+        for name in ("focal_b200_debug_umma", "focal_b200_debug_umma_rate", "focal_b200_debug_tma_rate"):
+            getattr(lib, name).restype = C.c_int
+        _bringup = lib
+    return _bringup
 
 
 def strerror(code: int) -> str:

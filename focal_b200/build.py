@@ -1,4 +1,5 @@
-"""Build libfocal_b200.so in-tree with nvcc for sm_100a (no torch headers, plain C ABI).
+"""Build libfocal_b200.so (the product: C ABI of include/focal_b200.h) and libfocal_bringup.so (hardware probes and
+micro-benchmarks used by tests/test_gpu_probe.py and tools/) in-tree with nvcc for sm_100a -- no torch headers.
 
     python -m focal_b200.build [--force]
 """
@@ -12,7 +13,9 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libfocal_b200.so")
+BRINGUP_PATH = os.path.join(PKG_DIR, "libfocal_bringup.so")
 SOURCES = [os.path.join(CSRC, "focal_b200.cu")]
+BRINGUP_SOURCES = [os.path.join(CSRC, "bringup.cu")]
 HEADERS = sorted(os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cuh", ".h"))) + [
     os.path.join(os.path.dirname(PKG_DIR), "include", "focal_b200.h")]
 
@@ -31,11 +34,15 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libfocal_b200.so")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _stale(out: str, sources) -> bool:
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS)
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in list(sources) + HEADERS)
+
+
+def needs_build() -> bool:
+    return _stale(LIB_PATH, SOURCES) or _stale(BRINGUP_PATH, BRINGUP_SOURCES)
 
 
 def build_variant(tag: str, defines: dict) -> str:
@@ -49,19 +56,31 @@ def build_variant(tag: str, defines: dict) -> str:
     return out
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+def _compile(out: str, sources, log_name: str, verbose: bool) -> None:
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", out] + list(sources)
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(PKG_DIR, "build.log"), "w") as fh:
+    with open(os.path.join(PKG_DIR, log_name), "w") as fh:
         fh.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libfocal_b200.so")
+        raise RuntimeError(f"nvcc failed building {os.path.basename(out)}")
     if verbose:
         print(log)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile whatever is out of date; the two libraries build concurrently."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = []
+    if force or _stale(LIB_PATH, SOURCES):
+        jobs.append((LIB_PATH, SOURCES, "build.log"))
+    if force or _stale(BRINGUP_PATH, BRINGUP_SOURCES):
+        jobs.append((BRINGUP_PATH, BRINGUP_SOURCES, "build_bringup.log"))
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            for f in [ex.submit(_compile, out, src, log, verbose) for out, src, log in jobs]:
+                f.result()
     return LIB_PATH
 
 

@@ -13,6 +13,8 @@ using namespace fb;
 
 namespace {
 
+int cuda_ok(const char* what);
+
 int device_sms() {
   static int cached[64] = {0};          // SM count per device ordinal (never changes; avoid a driver query per call)
   int dev = 0;
@@ -25,10 +27,41 @@ int device_sms() {
   return cached[dev];
 }
 
+// Every entry point rebuilds the plan from the cfg; the last few are cached per thread (the stream-K geometry search in
+// build_plan is the expensive part, and a step calls six entry points with the same cfg).
 int make_plan(const FocalCfg* cfg, Plan& p) {
   if (!cfg) return FOCAL_EINVAL;
   const int sms = cfg->num_sms > 0 ? cfg->num_sms : device_sms();
-  return build_plan(*cfg, p, sms);
+  struct Slot { FocalCfg cfg; int sms; int rc; bool valid; Plan plan; };
+  constexpr int kSlots = 8;
+  thread_local Slot slots[kSlots];
+  thread_local int next = 0;
+  for (int i = 0; i < kSlots; ++i)
+    if (slots[i].valid && slots[i].sms == sms && std::memcmp(&slots[i].cfg, cfg, sizeof(FocalCfg)) == 0) {
+      if (slots[i].rc == FOCAL_OK) p = slots[i].plan;
+      return slots[i].rc;
+    }
+  Slot& s = slots[next];
+  next = (next + 1) % kSlots;
+  s.cfg = *cfg; s.sms = sms; s.valid = true;
+  s.rc = build_plan(*cfg, s.plan, sms);
+  if (s.rc == FOCAL_OK) p = s.plan;
+  return s.rc;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember what was set per device
+// ordinal and kernel, so a second GPU driven from the same process gets its own call.
+template <class K>
+int ensure_dyn_smem(K kfn, size_t bytes, const char* what) {
+  if (bytes <= 48 * 1024) return FOCAL_OK;
+  static size_t configured[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (bytes > configured[dev]) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return cuda_ok(what);
+    configured[dev] = bytes;
+  }
+  return FOCAL_OK;
 }
 
 int check_ws(const Plan& p, const void* ws, size_t ws_bytes) {
@@ -61,12 +94,7 @@ int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st,
   static_assert(G::BN == tile_bn(KB), "plan.h and gram_kernel.cuh must agree on the column tile");
   using L = GramSmem<G::BN, KB, G::NB>;
   auto kfn = gram_kernel<MODE, KB, SEQ>;
-  static bool configured = false;     // per instantiation; the attribute is sticky per context
-  if (!configured) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kDynamic) != cudaSuccess)
-      return cuda_ok("cudaFuncSetAttribute(gram_kernel)");
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(kfn, L::kDynamic, "cudaFuncSetAttribute(gram_kernel)")) return rc;
   if (grid <= 0) return FOCAL_OK;                                 // persistent: at most one CTA per SM (plan.h)
   kfn<<<grid, G::kThreads, L::kDynamic, st>>>(p, sel, ws);
   return cuda_ok("gram_kernel launch");
@@ -136,12 +164,7 @@ int fast_row_vw(const Plan& p, int no_private) {
 template <int VW>
 int launch_prologue_fast_vw(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, size_t smem, int grid, int fuse,
                             cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(prologue_fast_kernel<VW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return cuda_ok("cudaFuncSetAttribute(prologue_fast_kernel)");
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem(prologue_fast_kernel<VW>, smem, "cudaFuncSetAttribute(prologue_fast_kernel)")) return rc;
   prologue_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, pw, w, fuse);
   return cuda_ok("prologue_fast_kernel");
 }
@@ -162,12 +185,7 @@ int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, const PeerWs&
 template <int VW, int MAXT>
 int launch_finalize_rt_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
   const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(finalize_rt_kernel<VW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return cuda_ok("cudaFuncSetAttribute(finalize_rt_kernel)");
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem(finalize_rt_kernel<VW, MAXT>, smem, "cudaFuncSetAttribute(finalize_rt_kernel)")) return rc;
   finalize_rt_kernel<VW, MAXT><<<grid, MAXT > 0 ? 128 * p.nT : 128, smem, st>>>(p, f, g, w);
   return cuda_ok("finalize_rt_kernel");
 }
@@ -195,6 +213,10 @@ int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtr
 // local_rows: the caller's tensors start at the first owned row; the kernels index rows globally, so hand them the
 // (virtual) address of row 0 -- only owned rows are ever dereferenced.
 int fill_feats(const Plan& p, const float* const* feats, FeatPtrs& f) {
+  if (p.indirect) {                       // the kernels read the table focal_b200_set_ptrs filled
+    for (int t = 0; t < kMaxT; ++t) f.x[t] = nullptr;
+    return FOCAL_OK;
+  }
   if (!feats) return FOCAL_EINVAL;
   const ptrdiff_t shift = p.local_rows ? (ptrdiff_t)p.seq0 * p.S * p.D : 0;
   for (int t = 0; t < p.nT; ++t) {
@@ -205,6 +227,10 @@ int fill_feats(const Plan& p, const float* const* feats, FeatPtrs& f) {
   return FOCAL_OK;
 }
 int fill_grads(const Plan& p, float* const* grads, GradPtrs& g) {
+  if (p.indirect) {
+    for (int t = 0; t < kMaxT; ++t) g.g[t] = nullptr;
+    return FOCAL_OK;
+  }
   if (!grads) return FOCAL_EINVAL;
   const ptrdiff_t shift = p.local_rows ? (ptrdiff_t)p.seq0 * p.S * p.D : 0;
   for (int t = 0; t < kMaxT; ++t) g.g[t] = nullptr;
@@ -237,12 +263,7 @@ int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& 
   } else {
     if (pw.world > 1 || p.local_rows) return FOCAL_ESHAPE;      // the generic row kernels have no peer path
     const size_t smem = (size_t)kRowsPerBlock * p.nT * p.D * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      if (cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return cuda_ok("cudaFuncSetAttribute(prologue_kernel)");
-      configured = smem;
-    }
+    if ((rc = ensure_dyn_smem(prologue_kernel, smem, "cudaFuncSetAttribute(prologue_kernel)"))) return rc;
     prologue_kernel<<<p.nblk1, 32 * kRowsPerBlock, smem, st>>>(p, f, w);
     if ((rc = cuda_ok("prologue_kernel"))) return rc;
   }
@@ -269,12 +290,7 @@ int do_finalize(const Plan& p, int no_private, const float* const* feats, float*
       if ((rc = launch_finalize_fast(vw, p, f, g, w, (rows + 3) / 4, st))) return rc;
     } else {
       const size_t smem = (size_t)kRowsPerBlock * (2 * p.nT + 1) * p.D * sizeof(float);
-      static size_t configured = 0;
-      if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-          return cuda_ok("cudaFuncSetAttribute(finalize_kernel)");
-        configured = smem;
-      }
+      if ((rc = ensure_dyn_smem(finalize_kernel, smem, "cudaFuncSetAttribute(finalize_kernel)"))) return rc;
       finalize_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, smem, st>>>(p, f, g, w);
       if ((rc = cuda_ok("finalize_kernel"))) return rc;
     }
@@ -380,9 +396,32 @@ int focal_b200_finalize(const FocalCfg* cfg, const float* const* feats, void* ws
   if (rc) return rc;
   if (p.local_rows) return FOCAL_EINVAL;
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
-  if (!loss5) return FOCAL_EINVAL;
+  if (!loss5 && !p.indirect) return FOCAL_EINVAL;
   return do_finalize(p, cfg->no_private, feats, grads, solo(ws), static_cast<uint8_t*>(ws), loss5,
                      static_cast<cudaStream_t>(stream));
+}
+
+int focal_b200_set_ptrs(const FocalCfg* cfg, void* ws, size_t ws_bytes, const float* const* feats, float* loss5,
+                        float* const* grads, void* stream) {
+  Plan p;
+  int rc = make_plan(cfg, p);
+  if (rc) return rc;
+  if ((rc = check_ws(p, ws, ws_bytes))) return rc;
+  if (!p.indirect || !feats || !loss5 || (p.need_grad && !grads)) return FOCAL_EINVAL;
+  const ptrdiff_t shift = p.local_rows ? (ptrdiff_t)p.seq0 * p.S * p.D : 0;
+  PtrTable t{};
+  for (int i = 0; i < p.nT; ++i) {
+    if (!feats[i] || (reinterpret_cast<uintptr_t>(feats[i]) & 15)) return FOCAL_EINVAL;
+    t.x[i] = feats[i] - shift;
+    if (p.need_grad) {
+      if (!grads[i] || (reinterpret_cast<uintptr_t>(grads[i]) & 15)) return FOCAL_EINVAL;
+      t.g[i] = grads[i] - shift;
+    }
+  }
+  t.loss5 = loss5;
+  set_ptrs_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<PtrTable*>(static_cast<uint8_t*>(ws) + p.ptrs_off), t);
+  return cuda_ok("set_ptrs_kernel");
 }
 
 int focal_b200_loss(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,
@@ -462,7 +501,7 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   Plan p;
   int rc = make_plan(cfg, p);
   if (rc) return rc;
-  if (!peers || !loss5 || !p.local_rows) return FOCAL_EINVAL;
+  if (!peers || (!loss5 && !p.indirect) || !p.local_rows) return FOCAL_EINVAL;
   if (peers->world < 1 || peers->world > kMaxPeers || peers->rank < 0 || peers->rank >= peers->world) return FOCAL_EINVAL;
   PeerWs pw{};
   pw.rank = peers->rank; pw.world = peers->world;
@@ -512,247 +551,3 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
 }
 
 }  // extern "C"
-
-// ---------------------------------------------------------------------------------------------------------
-// bring-up probe
-// ---------------------------------------------------------------------------------------------------------
-namespace {
-__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* a_img, uint32_t a_bytes, const uint8_t* b_img,
-                                                            uint32_t b_bytes, uint32_t idesc, uint32_t a_lbo,
-                                                            uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo,
-                                                            uint32_t b_sbo, uint32_t b_kstep, uint32_t ksteps,
-                                                            uint32_t ncols, uint32_t a_via_st, float* d_out) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_load, bar_mma;
-  __shared__ uint32_t tmem_slot;
-  uint8_t* sa = smem;
-  uint8_t* sb = smem + ((a_bytes + 1023) & ~1023u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(&bar_load, 1);
-    mbar_init(&bar_mma, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(&tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t a_tmem_col = 256;                 // A operand columns when it lives in tensor memory
-  const bool tf32 = (a_via_st & 0x100u) != 0;      // kind::tf32 instead of kind::f16 (32-bit elements)
-  a_via_st &= 0xffu;
-  if (a_via_st == 1) {
-    for (uint32_t o = threadIdx.x * 16; o < a_bytes; o += blockDim.x * 16)
-      *reinterpret_cast<uint4*>(sa + o) = *reinterpret_cast<const uint4*>(a_img + o);
-    fence_proxy_async_smem();
-  } else if (a_via_st == 2) {
-    const uint32_t W32 = a_bytes / 512;             // 32-bit words per row (2 bf16 or 1 tf32 element each)
-    const uint32_t* rowp = reinterpret_cast<const uint32_t*>(a_img) + (size_t)threadIdx.x * W32;
-    for (uint32_t g = 0; g < W32 / 32; ++g) {
-      uint32_t r[32];
-      for (int j = 0; j < 32; ++j) r[j] = rowp[g * 32 + j];
-      tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + a_tmem_col + g * 32, r);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(&bar_load, (a_via_st ? 0 : a_bytes) + b_bytes);
-    if (!a_via_st) tma_load_1d(sa, a_img, a_bytes, &bar_load);
-    tma_load_1d(sb, b_img, b_bytes, &bar_load);
-    mbar_wait(&bar_load, 0);
-    tc_fence_after();
-    for (uint32_t k = 0; k < ksteps; ++k) {
-      const uint64_t db = umma_smem_desc(smem_u32(sb) + k * b_kstep, b_lbo, b_sbo);
-      if (tf32) {
-        if (a_via_st == 2) umma_tf32_ts(tmem, tmem + a_tmem_col + k * 8, db, idesc, k > 0);
-        else umma_tf32(tmem, umma_smem_desc(smem_u32(sa) + k * a_kstep, a_lbo, a_sbo), db, idesc, k > 0);
-      } else if (a_via_st == 2) umma_bf16_ts(tmem, tmem + a_tmem_col + k * 8, db, idesc, k > 0);
-      else umma_bf16(tmem, umma_smem_desc(smem_u32(sa) + k * a_kstep, a_lbo, a_sbo), db, idesc, k > 0);
-    }
-    umma_commit(&bar_mma);
-  }
-  mbar_wait(&bar_mma, 0);
-  tc_fence_after();
-  const int row = warp * 32 + lane;
-  for (uint32_t c = 0; c < ncols; c += 32) {
-    float v[32];
-    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
-    tmem_ld_wait();
-    for (int j = 0; j < 32; ++j) d_out[(size_t)row * ncols + c + j] = v[j];
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
-}  // namespace
-
-extern "C" int focal_b200_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,
-                                     uint32_t idesc, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep_bytes,
-                                     uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep_bytes, uint32_t ksteps,
-                                     uint32_t ncols, uint32_t a_via_st, float* d_out, void* stream) {
-  if (!a_img || !b_img || !d_out || (a_bytes & 15) || (b_bytes & 15) || ncols % 32 || ncols > 256 || ncols == 0)
-    return FOCAL_EINVAL;
-  const uint32_t smem = ((a_bytes + 1023) & ~1023u) + b_bytes + 1024;
-  if (smem > 220 * 1024) return FOCAL_EINVAL;
-  if (cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return cuda_ok("cudaFuncSetAttribute(umma_probe_kernel)");
-  umma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint8_t*>(a_img), a_bytes, static_cast<const uint8_t*>(b_img), b_bytes, idesc, a_lbo, a_sbo,
-      a_kstep_bytes, b_lbo, b_sbo, b_kstep_bytes, ksteps, ncols, a_via_st, d_out);
-  return cuda_ok("umma_probe_kernel");
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// bring-up micro-benchmark: cycles per tcgen05.mma (M = 128) for a given N / operand placement.
-// The issue loop is fully unrolled with precomputed descriptors so that the tensor pipe, not the issuing
-// thread, is what is measured.
-// ---------------------------------------------------------------------------------------------------------
-namespace {
-template <int N, int B_MN, int A_TMEM>
-__global__ void __launch_bounds__(128, 1) umma_rate_kernel(uint32_t iters, long long* cycles, uint32_t sync_mode = 0) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int warp = threadIdx.x >> 5;
-  for (uint32_t o = threadIdx.x * 16; o < 64 * 1024 + 128 * 1024; o += blockDim.x * 16)
-    *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
-  fence_proxy_async_smem();
-  __shared__ uint64_t bar_done[2], bar_ready;
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1); mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1); mbar_init(&bar_ready, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-  // CUTLASS-style issue: the whole warp runs the (warp-uniform) loop and one elected lane issues.  Every operand of
-  // tcgen05.mma is derived from values the compiler can prove warp-uniform (shfl broadcast, kernel parameters,
-  // shared-memory base), otherwise ptxas wraps each instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall.
-  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-  if (__shfl_sync(0xffffffffu, warp, 0) == 0) {
-    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 64 * 1024);
-    constexpr uint32_t idesc = umma_idesc(UMMA_BF16, 128, N, 0, B_MN);
-    const uint64_t da0 = umma_smem_desc(a_addr, 16, 1024);
-    const uint64_t db0 = B_MN ? umma_smem_desc(b_addr, 128 * 128, 1024) : umma_smem_desc(b_addr, 16, 1024);
-    const long long t0 = clock64();
-    for (uint32_t it = 0; it < iters; ++it) {
-      if (sync_mode >= 1 && it >= 2) mbar_wait(&bar_done[it & 1], ((it >> 1) - 1) & 1);   // like s_empty / w_full
-      if (sync_mode >= 2) tc_fence_after();
-      const uint32_t d = tmem_u + (it & 1) * (A_TMEM ? 128 : 256) * (N > 128 && A_TMEM ? 0 : 1);
-      if (elect_one()) {
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-          const uint64_t da = da0 + (((k >> 2) * 16384 + (k & 3) * 32) >> 4);
-          const uint64_t db = db0 + ((B_MN ? k * 2048 : (k >> 2) * (N * 128) + (k & 3) * 32) >> 4);
-          if (A_TMEM) umma_bf16_ts(d, tmem_u + 384 + k * 8, db, idesc, k > 0);
-          else umma_bf16(d, da, db, idesc, k > 0);
-        }
-        if (sync_mode >= 1) umma_commit(&bar_done[it & 1]);                                // like s_full
-        if (sync_mode >= 3) umma_commit(&bar_ready);                                       // like b_empty (never waited)
-      }
-      __syncwarp();
-    }
-    if (elect_one()) umma_commit(&bar);
-    __syncwarp();
-    mbar_wait(&bar, 0);
-    const long long t1 = clock64();
-    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
-template <int N, int B_MN, int A_TMEM>
-int launch_rate(uint32_t iters, uint32_t grid, long long* cycles, cudaStream_t st, uint32_t sync_mode) {
-  const uint32_t smem = 64 * 1024 + 128 * 1024 + 1024;
-  auto k = umma_rate_kernel<N, B_MN, A_TMEM>;
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return cuda_ok("cudaFuncSetAttribute(umma_rate_kernel)");
-  k<<<grid, 128, smem, st>>>(iters, cycles, sync_mode);
-  return cuda_ok("umma_rate_kernel");
-}
-}  // namespace
-
-// 8 MMAs (K = 16 each) per iteration; returns per-CTA cycles for `iters` iterations.
-extern "C" int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t iters, uint32_t sync_mode, uint32_t grid,
-                                          long long* cycles, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const uint32_t b_mn = flags & 1, a_tmem = (flags >> 1) & 1;
-#define FB_RATE(NN)                                                                      \
-  if (N == NN) {                                                                         \
-    if (!b_mn && !a_tmem) return launch_rate<NN, 0, 0>(iters, grid, cycles, st, sync_mode);         \
-    if (b_mn && !a_tmem) return launch_rate<NN, 1, 0>(iters, grid, cycles, st, sync_mode);          \
-    if (!b_mn && a_tmem) return launch_rate<NN, 0, 1>(iters, grid, cycles, st, sync_mode);          \
-    return launch_rate<NN, 1, 1>(iters, grid, cycles, st, sync_mode);                               \
-  }
-  FB_RATE(32) FB_RATE(64) FB_RATE(96) FB_RATE(128) FB_RATE(192) FB_RATE(256)
-#undef FB_RATE
-  return FOCAL_EINVAL;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// bring-up micro-benchmark: L2 -> shared-memory throughput of linear bulk copies (cp.async.bulk) per SM
-// ---------------------------------------------------------------------------------------------------------
-namespace {
-__global__ void __launch_bounds__(64, 1) tma_rate_kernel(const uint8_t* src, uint32_t span_bytes, uint32_t copy_bytes,
-                                                         uint32_t copies_per_stage, uint32_t stages, uint32_t iters,
-                                                         long long* cycles) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full[8], empty[8];
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  const uint32_t stage_bytes = copy_bytes * copies_per_stage;
-  const int warp_u = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  if (warp_u == 0) {                              // producer: warp-uniform loop, one elected lane issues
-    const long long t0 = clock64();
-    uint32_t off = blockIdx.x * 65536u;
-    for (uint32_t n = 0; n < iters; ++n) {
-      const uint32_t st = n % stages;
-      mbar_wait(&empty[st], ((n / stages) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&full[st], stage_bytes);
-        for (uint32_t c = 0; c < copies_per_stage; ++c) {
-          tma_load_1d(smem + st * stage_bytes + c * copy_bytes, src + (off & (span_bytes - 1)), copy_bytes, &full[st]);
-          off += copy_bytes;
-        }
-      }
-      off = __shfl_sync(0xffffffffu, off, 0);
-    }
-    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x * 2] = clock64() - t0;
-  } else if (threadIdx.x == 32) {                 // consumer: frees the stage as soon as the bytes have landed
-    const long long t0 = clock64();
-    for (uint32_t n = 0; n < iters; ++n) {
-      const uint32_t st = n % stages;
-      mbar_wait(&full[st], (n / stages) & 1);
-      mbar_arrive(&empty[st]);
-    }
-    cycles[blockIdx.x * 2 + 1] = clock64() - t0;
-  }
-}
-}  // namespace
-
-extern "C" int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, uint32_t copy_bytes,
-                                         uint32_t copies_per_stage, uint32_t stages, uint32_t iters, uint32_t grid,
-                                         long long* cycles, void* stream) {
-  const uint32_t smem = copy_bytes * copies_per_stage * stages + 1024;
-  if (smem > 220 * 1024 || stages > 8) return FOCAL_EINVAL;
-  if (cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return cuda_ok("cudaFuncSetAttribute(tma_rate_kernel)");
-  tma_rate_kernel<<<grid, 64, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(src), span_bytes,
-                                                                        copy_bytes, copies_per_stage, stages, iters,
-                                                                        cycles);
-  return cuda_ok("tma_rate_kernel");
-}

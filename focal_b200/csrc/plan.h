@@ -66,6 +66,7 @@ struct Plan {
   int32_t sk_nce, sk_tmp, np_nce, np_tmp, grid_tmp, grid_nce[5];
   int32_t in_rb, in_bs;                                 // row-blocked inputs: rows per block, block stride (floats)
   int32_t local_rows;                                   // sharded path: the prologue handles the owned rows only
+  int32_t indirect;                                     // caller pointers come from the table at ptrs_off (CUDA graphs)
   float T, margin, w_shared, w_private, w_orth, w_rank;
   float alpha;                                          // sqrt(log2(e)/T): operand pre-scale, Gram = log2-domain logit
   OpDesc ops[kMaxOps];
@@ -93,8 +94,19 @@ struct Plan {
   uint64_t bar_off;        // uint32 [16]: [r] = last barrier epoch rank r announced here, [8] = own epoch counter,
                            //              [9] = blocks-done counter of the launch that announces next
   uint64_t lossx_off;      // double [kMaxPeers][8]: loss partials of every rank (sharded path)
+  uint64_t ptrs_off;       // PtrTable: the caller's feature / gradient / loss pointers of this step (indirect mode)
   uint64_t total_bytes;
   int32_t nblk1, nblk2, nitems3;
+};
+
+// Caller-owned pointers of one step.  Plain launches pass them by value as kernel arguments; in indirect mode
+// (FocalCfg.indirect_ptrs, used when the launch sequence is replayed from a CUDA graph) the row kernels read them from
+// this table in the workspace, which focal_b200_set_ptrs refreshes before every replay -- so a captured graph serves
+// freshly allocated inputs and outputs every step.
+struct PtrTable {
+  const float* x[kMaxT];
+  float* g[kMaxT];
+  float* loss5;
 };
 
 // Workspaces of all ranks of a row-sharded job as mapped into this process (plain launches: world = 1, ws[0] = own).
@@ -219,6 +231,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.in_bs = c.in_block_rows > 0 ? c.in_block_stride : 0;
   if (p.in_rb % c.S || c.B % p.in_rb) return FOCAL_EINVAL;
   p.local_rows = c.local_rows ? 1 : 0;
+  p.indirect = c.indirect_ptrs ? 1 : 0;
   if (p.local_rows && c.in_block_rows > 0) return FOCAL_EINVAL;
   p.num_sms = num_sms;
   p.T = c.temperature; p.margin = c.margin;
@@ -333,6 +346,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.lossd_off = take(8 * 8);
   p.bar_off = take(16 * 4);
   p.lossx_off = take((uint64_t)kMaxPeers * 8 * 8);
+  p.ptrs_off = take(sizeof(PtrTable));
   p.total_bytes = off;
   return FOCAL_OK;
 }

@@ -201,13 +201,17 @@ __device__ __forceinline__ void tmem_st_packed(uint32_t taddr, const uint32_t (&
 // K-major tile (rows = M or N index, 128 B of K per row, 8-row groups 1024 B apart): SBO = 1024, LBO unused.
 // MN-major tile (rows = K index, 128 B = 64 elements of MN per row): SBO = 1024 (next 8 K rows),
 //   LBO = byte distance between consecutive 64-element MN groups.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout types: 0 = no swizzle (interleaved 8 x 16 B core matrices), 1 = SWIZZLE_128B with 32-byte atoms
+//   (Swizzle<2,5,2>: 32-byte chunk ^= row & 3; what 32-bit MN-major operands need), 2 = SWIZZLE_128B (16-byte atoms)
+enum : uint32_t { UMMA_LAYOUT_NONE = 0, UMMA_LAYOUT_SW128_B32 = 1, UMMA_LAYOUT_SW128 = 2 };
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = UMMA_LAYOUT_SW128) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout & 7) << 61;
   return d;
 }
 

@@ -14,22 +14,38 @@ struct GradPtrs {
   float* g[kMaxT];
 };
 
+// caller pointers: kernel arguments, or (indirect mode) the table focal_b200_set_ptrs wrote into the workspace
+__device__ __forceinline__ const float* feat_base(const Plan& p, const FeatPtrs& f, const uint8_t* ws, int t) {
+  if (!p.indirect) return f.x[t];
+  return reinterpret_cast<const float*>(
+      __ldg(reinterpret_cast<const unsigned long long*>(&reinterpret_cast<const PtrTable*>(ws + p.ptrs_off)->x[t])));
+}
+__device__ __forceinline__ float* grad_base(const Plan& p, const GradPtrs& g, const uint8_t* ws, int t) {
+  if (!p.indirect) return g.g[t];
+  return reinterpret_cast<float*>(
+      __ldg(reinterpret_cast<const unsigned long long*>(&reinterpret_cast<const PtrTable*>(ws + p.ptrs_off)->g[t])));
+}
+__global__ void set_ptrs_kernel(PtrTable* __restrict__ dst, const PtrTable src) {
+  if (threadIdx.x == 0) *dst = src;
+}
+
 constexpr float kNceEps = 1e-8f;    // nn.CosineSimilarity eps (loss.py:15)
 constexpr float kOrthEps = 1e-12f;  // cosine_embedding_loss EPSILON (loss.py:16)
 
 // Cooperative (one warp) load of the nT rows `i` into shared memory: xs[t * D + c].
-__device__ __forceinline__ void load_rows(const Plan& p, const FeatPtrs& f, int i, float* xs, int lane) {
+__device__ __forceinline__ void load_rows(const Plan& p, const FeatPtrs& f, const uint8_t* ws, int i, float* xs,
+                                          int lane) {
   const int D = p.D;
   if ((D & 3) == 0) {
     const int nv = D >> 2;
     for (int t = 0; t < p.nT; ++t) {
-      const float4* src = reinterpret_cast<const float4*>(f.x[t] + feat_row_off(p, i));
+      const float4* src = reinterpret_cast<const float4*>(feat_base(p, f, ws, t) + feat_row_off(p, i));
       float4* dst = reinterpret_cast<float4*>(xs + t * D);
       for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
     }
   } else {
     for (int t = 0; t < p.nT; ++t)
-      for (int c = lane; c < D; c += 32) xs[t * D + c] = __ldg(f.x[t] + feat_row_off(p, i) + c);
+      for (int c = lane; c < D; c += 32) xs[t * D + c] = __ldg(feat_base(p, f, ws, t) + feat_row_off(p, i) + c);
   }
   __syncwarp();
 }
@@ -113,7 +129,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
   float* xs = smem_f + (size_t)warp * p.nT * p.D;
   float acc_orth = 0.f, acc_ps = 0.f, acc_pp = 0.f;
   if (i < p.B) {
-    load_rows(p, f, i, xs, lane);
+    load_rows(p, f, ws, i, xs, lane);
     const int D = p.D, d = p.d;
     const int I = i / p.S, s = i % p.S;
     const uint64_t rowN = (uint64_t)s * p.bpad + I;          // position-major row of the InfoNCE operands
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan
   if (w >= (long)p.nT * p.b) return;
   const int t = (int)(w / p.b), I = (int)(w % p.b);
   const int S = p.S, D = p.D;
-  const float* x = f.x[t] + feat_row_off(p, I * S);
+  const float* x = feat_base(p, f, ws, t) + feat_row_off(p, I * S);
   float tot = 0.f;
   for (int a = 0; a < S; ++a)
     for (int b2 = a + 1; b2 < S; ++b2) {
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
   float* xs = smem_f + (size_t)warp * (2 * p.nT + 1) * D;
   float* gs = xs + (size_t)p.nT * D;
   float* tmp = gs + (size_t)p.nT * D;
-  load_rows(p, f, i, xs, lane);
+  load_rows(p, f, ws, i, xs, lane);
   for (int c = lane; c < p.nT * D; c += 32) gs[c] = 0.f;
   const int I = i / S, s = i % S;
   const uint64_t rowN = (uint64_t)s * p.bpad + I;
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
       // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
       const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
       if (cnt > 0) {
-        const float* base = f.x[t] + feat_row_off(p, I * S);
+        const float* base = feat_base(p, f, ws, t) + feat_row_off(p, I * S);
         for (int j = 0; j < S; ++j) {
           if (j == s) continue;
           float d2 = 0.f;
@@ -443,7 +459,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
   }
   __syncwarp();
   for (int t = 0; t < p.nT; ++t) {
-    float* out = g.g[t] + (size_t)i * D;
+    float* out = grad_base(p, g, ws, t) + (size_t)i * D;
     for (int c = lane; c < D; c += 32) out[c] = gs[t * D + c];
   }
 }
@@ -508,6 +524,7 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant_
     }
   }
   if (threadIdx.x == 0) {
+    if (p.indirect) loss5 = reinterpret_cast<const PtrTable*>(ws + p.ptrs_off)->loss5;
     if (temporal_nan && (p.terms & FOCAL_TERM_TEMPORAL)) out[3] = __longlong_as_double(0x7ff8000000000000LL);
     const double total = (double)p.w_shared * out[0] + (double)p.w_private * out[1] + (double)p.w_orth * out[2] +
                          (double)p.w_rank * out[3];

@@ -69,10 +69,11 @@ __device__ __forceinline__ void st_operand(uint8_t* op_base, uint64_t kstride_ro
   }
 }
 
-__device__ __forceinline__ void stage_rows(const Plan& p, const FeatPtrs& f, int i, float* xs, int lane) {
+__device__ __forceinline__ void stage_rows(const Plan& p, const FeatPtrs& f, const uint8_t* ws, int i, float* xs,
+                                           int lane) {
   const int nv = p.D >> 2;                       // D % 4 == 0 on this path
   for (int t = 0; t < p.nT; ++t) {
-    const float4* src = reinterpret_cast<const float4*>(f.x[t] + feat_row_off(p, i));
+    const float4* src = reinterpret_cast<const float4*>(feat_base(p, f, ws, t) + feat_row_off(p, i));
     float4* dst = reinterpret_cast<float4*>(xs + t * p.D);
     for (int c = lane; c < nv; c += 32) dst[c] = __ldg(src + c);
   }
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
   float* xs = smem_f + (size_t)warp * p.nT * D;
   float acc_orth = 0.f, acc_ps = 0.f, acc_pp = 0.f;
   const bool live = i < row_hi;
-  if (live) stage_rows(p, f, i, xs, lane);
+  if (live) stage_rows(p, f, ws, i, xs, lane);
   __syncthreads();
   if (live) {
     const int I = i / p.S, s = i % p.S;
@@ -264,7 +265,7 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
     const size_t roff = feat_row_off(p, i);
     for (int t = t_begin; t < t_end; ++t) {
       float sh[VW], pr[VW];
-      const float* src = f.x[t] + roff;
+      const float* src = feat_base(p, f, ws, t) + roff;
       ld_frag<VW>(src + c0, sh);
       ld_frag<VW>(src + d + c0, pr);
       st_frag<VW>(xs + t * D + c0, sh);
@@ -433,7 +434,7 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
       }
     }
   }
-  float* out = g.g[t] + (size_t)i * D;
+  float* out = grad_base(p, g, ws, t) + (size_t)i * D;
   st_frag<VW>(out + c0, gsh);
   st_frag<VW>(out + d + c0, gpr);
   }  // tensors of this warp

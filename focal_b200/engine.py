@@ -41,6 +41,26 @@ class FocalHyper:
     w_rank: float
     no_private: bool = False
     terms: int = _cabi.FOCAL_TERM_ALL
+    precision: str = "auto"        # "bf16" | "tf32" (north_star's fp32 mode) | "auto" (see resolve_precision)
+
+
+# "auto": batches whose step is launch-latency-sized anyway run the fp32 mode (TF32 tiles); above that the Gram passes
+# are tensor-pipe-bound and run bf16 tiles (north_star's bf16 mode).  FOCAL_B200_PRECISION overrides "auto".
+AUTO_TF32_MAX_ROWS = 0      # TODO(tf32): 2048 once the TF32 tile mode is in
+
+
+def resolve_precision(hp: "FocalHyper", B: int, D: int) -> int:
+    import os
+    want = hp.precision
+    if want == "auto":
+        want = os.environ.get("FOCAL_B200_PRECISION", "auto").lower()
+    if want in ("fp32", "tf32"):
+        return _cabi.FOCAL_PREC_TF32
+    if want == "bf16":
+        return _cabi.FOCAL_PREC_BF16
+    if want != "auto":
+        raise ValueError(f"unknown precision {want!r} (bf16 | tf32 | auto)")
+    return _cabi.FOCAL_PREC_TF32 if B <= AUTO_TF32_MAX_ROWS else _cabi.FOCAL_PREC_BF16
 
 
 def shard_sequences(b: int, world: int, rank: int) -> Tuple[int, int]:
@@ -56,8 +76,9 @@ class CudaBackend:
 
     name = "cuda"
 
-    def __init__(self):
+    def __init__(self, precision: Optional[int] = None):
         self.lib = _cabi.load()          # raises ImportError when the extension is missing -- no fallback
+        self.precision = precision       # None: FocalHyper.precision decides ("auto" -> by batch size)
         self._ws: Dict[tuple, Tuple[torch.Tensor, torch.Tensor, _cabi.FocalWsInfo]] = {}
         self._plans: Dict[tuple, tuple] = {}
         self._peers: Dict[tuple, Optional[tuple]] = {}
@@ -68,7 +89,8 @@ class CudaBackend:
             B=B, S=hp.seq_len, M=len(hp.modalities), D=D, temperature=hp.temperature, margin=hp.margin,
             w_shared=hp.w_shared, w_private=hp.w_private, w_orth=hp.w_orth, w_rank=hp.w_rank,
             no_private=int(hp.no_private), need_grad=int(need_grad), terms=hp.terms,
-            precision=_cabi.FOCAL_PREC_BF16, seq_begin=seq[0], seq_end=seq[1], num_sms=0)
+            precision=resolve_precision(hp, B, D) if self.precision is None else self.precision,
+            seq_begin=seq[0], seq_end=seq[1], num_sms=0)
 
     def workspace(self, cfg: _cabi.FocalCfg, device: torch.device):
         key = (cfg.B, cfg.S, cfg.M, cfg.D, cfg.no_private, cfg.terms, cfg.precision, device.index)
@@ -91,6 +113,21 @@ class CudaBackend:
     def _view(ws: torch.Tensor, off: int, nbytes: int, dtype: torch.dtype, shape) -> torch.Tensor:
         return ws[off: off + nbytes].view(dtype).view(*shape)
 
+    def plan(self, hp: FocalHyper, B: int, D: int, need_grad: bool, seq: Tuple[int, int], dev: torch.device,
+             blocked: Optional[Tuple[int, int, int]] = None, indirect: bool = False):
+        """(cfg, ws, info, ws pointer, ws size) of one call configuration, cached."""
+        key = (hp, B, D, need_grad, seq, dev.index, blocked, indirect)
+        hit = self._plans.get(key)
+        if hit is None:
+            cfg = self._cfg(hp, B, D, need_grad, seq)
+            cfg.indirect_ptrs = int(indirect)
+            if blocked is not None:
+                cfg.in_block_rows, cfg.in_block_stride = blocked[1], blocked[2]
+            ws, info = self.workspace(cfg, dev)
+            hit = (cfg, ws, info, C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()))
+            self._plans[key] = hit
+        return hit
+
     # -- the whole path -----------------------------------------------------------------------------
     supports_blocked = True
 
@@ -105,16 +142,7 @@ class CudaBackend:
         D = x0.shape[1]
         B = blocked[0] if blocked is not None else x0.shape[0]
         dev = x0.device
-        key = (hp, B, D, need_grad, seq, dev.index, blocked)
-        hit = self._plans.get(key)
-        if hit is None:
-            cfg = self._cfg(hp, B, D, need_grad, seq)
-            if blocked is not None:
-                cfg.in_block_rows, cfg.in_block_stride = blocked[1], blocked[2]
-            ws, info = self.workspace(cfg, dev)
-            hit = (cfg, ws, info, C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()))
-            self._plans[key] = hit
-        cfg, ws, info, wsp, wsn = hit
+        cfg, ws, info, wsp, wsn = self.plan(hp, B, D, need_grad, seq, dev, blocked)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         fptr = _cabi.ptr_array([t.data_ptr() for t in feats])
         loss5 = torch.empty(5, dtype=torch.float32, device=dev)
@@ -144,6 +172,40 @@ class CudaBackend:
                         "focal_b200_finalize")
         return loss5, grads
 
+    # -- indirect mode: the launch sequence as a replayable unit (CUDA graphs) --------------------------
+    def launch_indirect(self, hp: FocalHyper, B: int, D: int, need_grad: bool, seq: Tuple[int, int],
+                        dev: torch.device, peer=None) -> None:
+        """Enqueue every stage with cfg.indirect_ptrs = 1: the kernels take the caller's pointers from the workspace
+        table (set_ptrs).  This is what FocalEngine captures into a CUDA graph."""
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if peer is None:
+            cfg, ws, info, wsp, wsn = self.plan(hp, B, D, need_grad, seq, dev, None, True)
+            _cabi.check(self.lib.focal_b200_loss(C.byref(cfg), None, wsp, wsn, None, None, stream),
+                        "focal_b200_loss(indirect)")
+        else:
+            cfg = self._cfg(hp, B, D, need_grad, seq)
+            cfg.local_rows, cfg.indirect_ptrs = 1, 1
+            _cabi.check(self.lib.focal_b200_loss_sharded(C.byref(cfg), None, C.byref(peer[0]), C.c_size_t(peer[1]),
+                                                         None, None, stream), "focal_b200_loss_sharded(indirect)")
+
+    def set_ptrs(self, hp: FocalHyper, B: int, D: int, need_grad: bool, seq: Tuple[int, int], dev: torch.device,
+                 feats: Sequence[torch.Tensor], loss5: torch.Tensor, grads: Optional[Sequence[torch.Tensor]],
+                 peer=None) -> None:
+        """Point the captured launch sequence at this step's inputs / outputs (one tiny launch)."""
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        fptr = _cabi.ptr_array([t.data_ptr() for t in feats])
+        if peer is None:
+            cfg, ws, info, wsp, wsn = self.plan(hp, B, D, need_grad, seq, dev, None, True)
+            # full tensors: row i of the gradient lands at row i - rows0 of the [rows_owned, D] output
+            rows0 = seq[0] * hp.seq_len
+            gptr = _cabi.ptr_array([g.data_ptr() - rows0 * D * 4 for g in grads]) if grads is not None else None
+        else:
+            cfg = self._cfg(hp, B, D, need_grad, seq)
+            cfg.local_rows, cfg.indirect_ptrs = 1, 1
+            wsp, wsn = C.c_void_p(peer[0].ws[peer[0].rank]), C.c_size_t(peer[1])
+            gptr = _cabi.ptr_array([g.data_ptr() for g in grads]) if grads is not None else None
+        _cabi.check(self.lib.focal_b200_set_ptrs(C.byref(cfg), wsp, wsn, fptr, C.c_void_p(loss5.data_ptr()), gptr,
+                                                 stream), "focal_b200_set_ptrs")
 
     # -- row-sharded path over NVLink peer memory ------------------------------------------------------
     @staticmethod
@@ -155,10 +217,10 @@ class CudaBackend:
 
     def peer_setup(self, cfg: _cabi.FocalCfg, group, dev: torch.device):
         """Collective over ``group``: allocate this rank's workspace, exchange IPC handles, map the peers'.
-        Returns (FocalPeers, total_bytes) or None when any rank could not (then every rank gets None)."""
+        Returns (FocalPeers, total_bytes, opened, own) or None when any rank could not (then every rank gets None)."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        key = (cfg.B, cfg.S, cfg.M, cfg.D, cfg.no_private, cfg.terms, world, dev.index)
+        key = (cfg.B, cfg.S, cfg.M, cfg.D, cfg.no_private, cfg.terms, cfg.precision, world, dev.index)
         if key in self._peers:
             return self._peers[key]
         lib = self.lib
@@ -196,6 +258,24 @@ class CudaBackend:
         self._peers[key] = (peers, int(info.total_bytes), opened, own)
         return self._peers[key]
 
+    def close(self) -> None:
+        """Release the peer-memory resources (IPC mappings, the cudaMalloc'ed workspaces) and the cached workspaces.
+        Every rank must have finished its last step (callers barrier first): peers may still be storing into a
+        workspace otherwise."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for ent in self._peers.values():
+            if ent is None:
+                continue
+            _, _, opened, own = ent
+            for p in opened:
+                self.lib.focal_b200_peer_close(p)
+            if own.value:
+                self.lib.focal_b200_peer_free(own)
+        self._peers.clear()
+        self._plans.clear()
+        self._ws.clear()
+
     def run_sharded(self, hp: FocalHyper, local: Sequence[torch.Tensor], B: int, seq: Tuple[int, int], need_grad: bool,
                     peer) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
         """local: 2M fp32 CUDA tensors holding the owned rows.  Returns (GLOBAL loss5, grads of the owned rows)."""
@@ -217,23 +297,29 @@ class CudaBackend:
 
 
 class FocalEngine:
-    """Validates inputs, shards rows over the process group, drives a backend."""
+    """Validates inputs, shards rows over the process group, drives a backend.
+
+    CUDA graphs: the launch sequence of one (shape, need_grad) is captured ONCE with ``indirect_ptrs`` -- the kernels take
+    the caller's feature / gradient / loss pointers from a table in the workspace -- and every later step is
+    ``set_ptrs`` + ``graph.replay()``.  Inputs may live at a new address every step (activations of a training loop
+    do) and the outputs are freshly allocated tensors every step, so nothing a caller holds (autograd's saved gradients,
+    ``last_parts``) is ever overwritten by a later replay, and no caller storage is pinned by the cache.
+    """
 
     def __init__(self, hp: FocalHyper, process_group=None, backend=None, use_cuda_graph: bool = True):
         self.hp = hp
         self.group = process_group
         self.backend = backend if backend is not None else CudaBackend()
-        # CUDA graphs: the whole step (9 kernel launches, plus the collectives when row-sharded) is replayed as one
-        # graph when the same input buffers are seen again -- the launch-bound tail of the step disappears.
         import os
-        self.use_cuda_graph = (use_cuda_graph and getattr(self.backend, "name", "") == "cuda"
+        is_cuda = getattr(self.backend, "name", "") == "cuda"
+        self.use_cuda_graph = (use_cuda_graph and is_cuda and hasattr(self.backend, "launch_indirect")
                                and os.environ.get("FOCAL_B200_CUDA_GRAPH", "1") != "0")
         # row-sharded jobs: exchange over NVLink peer memory instead of collectives (one box, <= 8 ranks, CUDA backend)
-        self.use_peer = (getattr(self.backend, "name", "") == "cuda" and hasattr(self.backend, "run_sharded")
+        self.use_peer = (is_cuda and hasattr(self.backend, "run_sharded")
                          and os.environ.get("FOCAL_B200_PEER", "1") != "0")
-        self._graphs: Dict[tuple, tuple] = {}
-        self._seen: Dict[tuple, int] = {}
+        self._steps: Dict[tuple, object] = {}     # (rows, D, need_grad, device, world) -> "warm" | CUDAGraph
         self.graph_replays = 0
+        self.graph_captures = 0
 
     # ---------------------------------------------------------------------------------------------
     def _world(self) -> Tuple[int, int]:
@@ -263,43 +349,77 @@ class FocalEngine:
             raise ValueError(f"batch of {x0.shape[0]} rows is not a multiple of seq_len={hp.seq_len}")
         if getattr(self.backend, "name", "") == "cuda" and not x0.is_cuda:
             raise RuntimeError("focal_b200 runs on CUDA tensors only (no CPU fallback); move the features to the GPU")
-        return [t.detach().contiguous() for t in feats]
+        out = []
+        for t in feats:
+            t = t.detach().contiguous()
+            if t.data_ptr() % 16:             # a view into the middle of a larger buffer: the kernels use 16-byte vectors
+                t = t.clone()
+            out.append(t)
+        return out
 
     # ---------------------------------------------------------------------------------------------
     def loss_and_grads(self, f1: Dict[str, torch.Tensor], f2: Dict[str, torch.Tensor], need_grad: bool):
         """Returns (loss5, grads): loss5 = [total, shared, private, orth, temporal] of the GLOBAL batch,
-        grads = 2M tensors shaped like the (local) inputs, or None.
-
-        With CUDA graphs enabled the returned tensors are the graph's static outputs: they stay valid until the next
-        call that passes the SAME input buffers (same data pointers), which replays the graph and overwrites them.
-        """
+        grads = 2M tensors shaped like the (local) inputs, or None.  Both are fresh tensors owned by the caller."""
         local = self._check(f1, f2)
-        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+        dev = local[0].device
+        if not local[0].is_cuda:
             return self._run(local, need_grad)
-        key = (tuple(t.data_ptr() for t in local), tuple(local[0].shape), need_grad, local[0].device.index)
-        hit = self._graphs.get(key)
-        if hit is not None:
-            hit[0].replay()
-            self.graph_replays += 1
-            return hit[1], hit[2]
-        seen = self._seen.get(key, 0) + 1
-        self._seen[key] = seen
-        if seen < 2:
-            # first sighting: run eagerly (also warms up workspace, kernel attributes and communicators); buffers that
-            # never come back (fresh allocations every step) therefore never pay for a capture
-            if len(self._seen) > 256:
-                self._seen.clear()
+        with torch.cuda.device(dev):       # kernels, attributes and SM queries act on the CURRENT device
+            if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+                return self._step(local, need_grad)
             return self._run(local, need_grad)
-        if len(self._graphs) >= 32:
-            self._graphs.pop(next(iter(self._graphs)))
-        torch.cuda.synchronize(local[0].device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss5, grads = self._run(local, need_grad)
-        self._graphs[key] = (graph, loss5, grads, local)      # keep the inputs alive: their addresses are baked in
-        graph.replay()
+
+    def _peer_of(self, local: List[torch.Tensor], need_grad: bool):
+        """(B, seq, peer) of the row-sharded peer path, or None when this call does not take it."""
+        world, rank = self._world()
+        Bl, D = local[0].shape
+        if world == 1 or not (self.use_peer and self.backend.peer_eligible(self.hp, D, world)):
+            return None
+        B = world * Bl
+        seq = shard_sequences(B // self.hp.seq_len, world, rank)
+        peer = self.backend.peer_setup(self.backend._cfg(self.hp, B, D, need_grad, seq), self.group, local[0].device)
+        return None if peer is None else (B, seq, peer)
+
+    def _step(self, local: List[torch.Tensor], need_grad: bool):
+        hp, be = self.hp, self.backend
+        world, _ = self._world()
+        Bl, D = local[0].shape
+        dev = local[0].device
+        key = (Bl, D, need_grad, dev.index, world)
+        st = self._steps.get(key)
+        if st is None:
+            # first sighting: run eagerly (loads the kernels, sets their attributes, builds workspaces and, when
+            # row-sharded, runs the peer-memory handshake -- none of which may happen under stream capture)
+            self._steps[key] = "warm"
+            return self._run(local, need_grad)
+        if st == "none":
+            return self._run(local, need_grad)
+        if world == 1:
+            B, seq, peer = Bl, (0, Bl // hp.seq_len), None
+        else:
+            sh = self._peer_of(local, need_grad)
+            if sh is None:                     # collective path: its all-gathers read caller memory directly
+                self._steps[key] = "none"
+                return self._run(local, need_grad)
+            B, seq, peer = sh
+        if st == "warm":
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                be.launch_indirect(hp, B, D, need_grad, seq, dev, peer)
+            self._steps[key] = st = graph
+            self.graph_captures += 1
+        loss5 = torch.empty(5, dtype=torch.float32, device=dev)
+        grads = [torch.empty_like(t) for t in local] if need_grad else None
+        be.set_ptrs(hp, B, D, need_grad, seq, dev, local, loss5, grads, peer)
+        st.replay()
         self.graph_replays += 1
         return loss5, grads
+
+    def close(self) -> None:
+        self._steps.clear()
+        if hasattr(self.backend, "close"):
+            self.backend.close()
 
     def _run(self, local: List[torch.Tensor], need_grad: bool):
         hp = self.hp
@@ -311,12 +431,9 @@ class FocalEngine:
         import torch.distributed as dist
         Bl, D = local[0].shape
         nT = len(local)
-        if self.use_peer and self.backend.peer_eligible(hp, D, world):
-            B = world * Bl
-            seq = shard_sequences(B // hp.seq_len, world, rank)
-            peer = self.backend.peer_setup(self.backend._cfg(hp, B, D, need_grad, seq), self.group, local[0].device)
-            if peer is not None:
-                return self.backend.run_sharded(hp, local, B, seq, need_grad, peer)
+        sh = self._peer_of(local, need_grad)
+        if sh is not None:
+            return self.backend.run_sharded(hp, local, sh[0], sh[1], need_grad, sh[2])
         # (1) all-gather the raw features: per-rank [2M, Bl, D] -> [R, 2M, Bl, D]
         mine = torch.stack(local, dim=0)
         gathered = torch.empty((world * nT, Bl, D), dtype=mine.dtype, device=mine.device)

@@ -8,7 +8,12 @@ C ABI of ``libfocal_b200.so``; the gradients w.r.t. every feature tensor are pro
 as the loss and handed to autograd by a ``torch.autograd.Function``.
 
 Build-side options (never required): ``args.focal_process_group`` -- a ``torch.distributed`` process group over
-which the batch is row-sharded (each rank passes its own rows).
+which the batch is row-sharded (each rank passes its own rows); ``args.focal_precision`` -- ``"tf32"`` (north_star's
+fp32 mode: TF32 tiles, gradients within 2e-3 of the fp32 reference), ``"bf16"`` (bf16 tiles, 1e-2) or ``"auto"``
+(default: TF32 for batches up to ``engine.AUTO_TF32_MAX_ROWS`` rows, bf16 above; env ``FOCAL_B200_PRECISION``).
+
+Limits the reference does not have (they raise ``ValueError`` / ``TypeError`` before any launch): see INTEGRATION.md.
+Features that are not fp32 (autocast) are upcast, and their gradients cast back by autograd.
 """
 from __future__ import annotations
 
@@ -72,11 +77,15 @@ class FOCALLoss(nn.Module):
                 w_shared=float(cfg["shared_contrastive_loss_weight"]),
                 w_private=float(cfg["private_contrastive_loss_weight"]),
                 w_orth=float(cfg["orthogonal_loss_weight"]), w_rank=float(cfg["rank_loss_weight"]),
-                no_private=(getattr(self.args, "tag", None) == "noPrivate"))
+                no_private=(getattr(self.args, "tag", None) == "noPrivate"),
+                precision=str(getattr(self.args, "focal_precision", "auto")).lower())
             self._engine = FocalEngine(hp, process_group=getattr(self.args, "focal_process_group", None))
         return self._engine
 
     def forward(self, mod_features1: Dict[str, torch.Tensor], mod_features2: Dict[str, torch.Tensor], index=None):
         """loss = w_s * shared InfoNCE + w_p * private InfoNCE + w_o * orthogonality + w_r * temporal ranking."""
         feats = [mod_features1[m] for m in self.modalities] + [mod_features2[m] for m in self.modalities]
+        # the reference computes in fp32 (loss.py:74,117); lower-precision activations (autocast) are upcast here so
+        # that autograd casts their gradients back
+        feats = [f if f.dtype == torch.float32 or not f.is_floating_point() else f.float() for f in feats]
         return _FocalLossFn.apply(self, len(self.modalities), *feats)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FOCAL_B200_ABI_VERSION 2
+#define FOCAL_B200_ABI_VERSION 3
 #define FOCAL_MAX_MODALITIES 4
 
 enum {
@@ -63,6 +63,10 @@ typedef struct FocalCfg {
   /* local_rows != 0 (only with focal_b200_loss_sharded): feats[t] / grads[t] hold just the owned rows
    * [seq_begin*S, seq_end*S) of the B-row tensors, i.e. what a rank of a row-sharded job has in hand. */
   int32_t local_rows;
+  /* indirect_ptrs != 0: the feats / grads / loss5 arguments of the stage functions are ignored; the kernels read them
+   * from a table in the workspace that focal_b200_set_ptrs fills.  This is what makes the launch sequence replayable
+   * from a CUDA graph with different (freshly allocated) inputs and outputs every step. */
+  int32_t indirect_ptrs;
 } FocalCfg;
 
 /* Byte offsets (from the workspace base) and extents of the buffers a host may need to look at:
@@ -117,6 +121,11 @@ int focal_b200_temporal(const FocalCfg* cfg, void* ws, size_t ws_bytes, void* st
 int focal_b200_finalize(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,
                         float* const* grads, void* stream);
 
+/* Indirect mode (cfg->indirect_ptrs): store this step's caller pointers in the workspace table (one tiny launch on
+ * `stream`).  grads may be NULL when !cfg->need_grad.  Call it before every replay of a captured launch sequence. */
+int focal_b200_set_ptrs(const FocalCfg* cfg, void* ws, size_t ws_bytes, const float* const* feats, float* loss5,
+                        float* const* grads, void* stream);
+
 /* All stages in order on one stream (single-GPU call of FOCALLoss.forward + backward). */
 int focal_b200_loss(const FocalCfg* cfg, const float* const* feats, void* ws, size_t ws_bytes, float* loss5,
                     float* const* grads, void* stream);
@@ -149,20 +158,6 @@ int focal_b200_peer_free(void* ptr);
  * of 32, S in {1, 2, 4}, no noPrivate) -- callers then use the staged functions with a collective library. */
 int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, const FocalPeers* peers, size_t ws_bytes,
                             float* loss5, float* const* grads, void* stream);
-
-/* Bring-up probe: runs `ksteps` tcgen05.mma (M=128) on caller-provided shared-memory images and returns
- * the 128 x ncols fp32 accumulator.  Used by tests to pin the descriptor encodings on real hardware. */
-int focal_b200_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t idesc,
-                          uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep_bytes, uint32_t b_lbo, uint32_t b_sbo,
-                          uint32_t b_kstep_bytes, uint32_t ksteps, uint32_t ncols, uint32_t a_via_st, float* d_out,
-                          void* stream);
-
-/* Bring-up micro-benchmarks (tools/umma_rate.py, tools/tma_rate.py): cycles per tcgen05.mma for a given N / operand
- * placement / per-tile barrier traffic, and per-SM throughput of linear TMA bulk copies. */
-int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t iters, uint32_t sync_mode, uint32_t grid,
-                               long long* cycles, void* stream);
-int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, uint32_t copy_bytes, uint32_t copies_per_stage,
-                              uint32_t stages, uint32_t iters, uint32_t grid, long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ def idesc(M, N, a_mn=0, b_mn=0, fmt=1):
 
 def run_probe(a_img, b_img, idsc, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, ksteps, ncols, a_via_st=0):
     from focal_b200 import _cabi
-    lib = _cabi.load()
+    lib = _cabi.load_bringup()
     out = torch.full((128, ncols), float("nan"), device="cuda", dtype=torch.float32)
     rc = lib.focal_b200_debug_umma(C.c_void_p(a_img.data_ptr()), a_img.numel(), C.c_void_p(b_img.data_ptr()),
                                    b_img.numel(), idsc, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, ksteps, ncols,

@@ -45,8 +45,11 @@ def test_input_validation_raises_before_any_launch():
     with pytest.raises(KeyError):
         m({"seismic": ok["seismic"]}, ok)
     half = {k: v.half() for k, v in ok.items()}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(half, half)                                               # fp16 / bf16 activations are upcast, not refused
+    ints = {k: v.long() for k, v in ok.items()}
     with pytest.raises(TypeError):
-        m(half, half)
+        m(ints, ints)
     mixed = {"seismic": torch.randn(32, 16), "audio": torch.randn(32, 8)}
     with pytest.raises(ValueError):
         m(mixed, mixed)

@@ -3,8 +3,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from focal_b200 import _cabi
-lib = C.CDLL(_cabi.LIB_PATH)
-lib.focal_b200_debug_tma_rate.argtypes = [C.c_void_p] + [C.c_uint32] * 6 + [C.c_void_p, C.c_void_p]
+lib = _cabi.load_bringup()
 span = 32 << 20                                   # 32 MiB source: L2 resident
 src = torch.zeros(span + (1 << 20), dtype=torch.uint8, device="cuda")
 for grid in (1, 148):

@@ -3,8 +3,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from focal_b200 import _cabi
-lib = C.CDLL(_cabi.LIB_PATH)
-lib.focal_b200_debug_umma_rate.argtypes = [C.c_uint32] * 5 + [C.c_void_p, C.c_void_p]
+lib = _cabi.load_bringup()
 grid = 148
 for sync_mode in (0, 1, 3):
     for a_tmem, b_mn, N in ((0, 0, 64), (0, 0, 128), (0, 0, 256), (1, 1, 128)):
