@@ -13,9 +13,14 @@ memory, NCCL carries only the set-up handshake and the timing reductions).
 same step through ``FOCALLoss.forward/backward`` with pinned HOST inputs: the H2D copy of every step and the D2H read of
 every step's loss are inside the timed region (copy of step k+1 and read-back of step k-1 overlap the kernels of step k).
 
-``--impl reference`` times the reference's CPU implementation of the path on the host cores.  The reference is a
-pure-Python/PyTorch module that cannot travel to the GPU box, so its op-for-op port ``oracle/focal_ref_port.py``
-is timed (same ATen operators in the same order, autograd backward) on a bounded sample of the workload.
+``--impl reference`` times the reference's CPU implementation of the path on the host cores: the UNMODIFIED reference
+``FOCALLoss`` from ``oracle/_ref`` (placed there by ``python -m oracle.build_ref``, travels to the GPU box like a built
+``.so``; kind = "reference"), or -- only when that is absent -- its op-for-op port ``oracle/focal_ref_port.py``
+(kind = "port"), on a bounded sample of the workload.
+
+Roofline fractions are quoted against the measured peak that matches the clock sampled DURING the timed region: the burst
+figure of ``MEASURED_PEAKS.json`` when the SM clock stayed near its maximum (short runs), the sustained figure when
+the sampler saw the power-capped clock.  ``sustained`` is a second, >= 2 s timed pass with >= 50 clock samples.
 """
 from __future__ import annotations
 
@@ -37,6 +42,8 @@ UNIT = "samples/s"
 WORKLOADS = {
     # BASELINE.json metric configuration (configs[1] dims at the headline batch): the default and the only bench line
     "headline": dict(B=8192, S=4, M=2, D=256, T=0.5, mods=("seismic", "audio"), terms=7),
+    # configs[0]: the reference's own CPU-runnable case
+    "cfg1": dict(B=128, S=4, M=2, D=128, T=0.5, mods=("seismic", "audio"), terms=7),
     # the other BASELINE.json configs, for profiles/ (python bench.py --workload cfg3 ...)
     "cfg2": dict(B=1024, S=4, M=2, D=256, T=0.5, mods=("seismic", "audio"), terms=7),
     "cfg3": dict(B=4096, S=4, M=3, D=256, T=0.07, mods=("acc", "gyr", "mag"), terms=7),
@@ -62,10 +69,26 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as fh:
             p = json.load(fh)
-        return dict(tflops=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1413.7))),
+        cl = p.get("clocks_under_load", {})
+        return dict(tflops_sustained=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1413.7))),
                     tflops_burst=float(p.get("bf16_tflops", 1662.8)), hbm=float(p.get("hbm_gbs", 6541.1)),
+                    sustained_mhz=float(cl.get("sm_mhz_median", 1350.0)), max_mhz=float(p.get("sm_max_mhz", 1965.0)),
                     source="measured")
-    return dict(tflops=1590.0, tflops_burst=1590.0, hbm=6650.0, source="fallback")
+    # /opt/skills/guides/B200_PROFILING.md fallback: 1.59 PFLOP/s burst, ~1.4 sustained, 6.65 TB/s
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm=6650.0, sustained_mhz=1300.0, max_mhz=1965.0,
+                source="fallback")
+
+
+def tensor_peak_for(peaks, clocks, tf32=False):
+    """The measured dense peak that matches the clock seen DURING the timed region: burst when the SM clock stayed within
+    10 % of its maximum, sustained (the power-capped figure) otherwise.  TF32 runs at half the bf16 rate."""
+    mhz = (clocks or {}).get("sm_mhz")
+    burst = mhz is None or mhz >= 0.9 * peaks["max_mhz"]
+    val = peaks["tflops_burst"] if burst else peaks["tflops_sustained"]
+    if tf32:
+        val *= 0.5
+    kind = ("burst" if burst else "sustained") + (" bf16 x 0.5 (tf32)" if tf32 else " bf16")
+    return val, f"{peaks['source']} ({kind}; sampled SM clock {mhz} MHz)"
 
 
 # -------------------------------------------------------------------------------------------------
@@ -163,12 +186,38 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port of the reference) -- bounded sample of the workload
 # -------------------------------------------------------------------------------------------------
-def cpu_reference_time(B_sample: int, steps: int, warmup: int):
-    import torch
-    from oracle.focal_oracle import FocalConfig, make_iid
+def _reference_callable(w):
+    """(kind, fn(f1, f2) -> loss): the unmodified reference module from oracle/_ref, else the op-for-op port."""
+    import types
+
+    from oracle.focal_oracle import FocalConfig
+    try:
+        from oracle.build_ref import import_reference_loss, ref_available
+        if ref_available():
+            cls = import_reference_loss()
+            args_ns = types.SimpleNamespace(
+                device="cpu", model="DeepSense", tag=None,
+                dataset_config={"modality_names": list(w["mods"]), "seq_len": w["S"],
+                                "FOCAL": {"temperature": {"DeepSense": w["T"], "SW_Transformer": 0.07},
+                                          "inter_rank_margin": w["margin"],
+                                          "shared_contrastive_loss_weight": w["weights"][0],
+                                          "private_contrastive_loss_weight": w["weights"][1],
+                                          "orthogonal_loss_weight": w["weights"][2],
+                                          "rank_loss_weight": w["weights"][3]}})
+            mod = cls(args_ns)
+            return "reference", (lambda f1, f2: mod(f1, f2))
+    except Exception as exc:                                  # noqa: BLE001 -- fall back to the port, but say so
+        print(f"bench.py: oracle/_ref unusable ({exc!r}); timing the port", file=sys.stderr)
     from oracle.focal_ref_port import focal_loss_port
-    w = WORKLOAD
     cfg = FocalConfig(modalities=list(w["mods"]), seq_len=w["S"], temperature=w["T"], margin=w["margin"])
+    return "port", (lambda f1, f2: focal_loss_port(f1, f2, cfg))
+
+
+def cpu_reference_time(B_sample: int, steps: int, warmup: int, w=None):
+    """Seconds per fwd+bwd of the reference's CPU implementation on B_sample rows of workload w.  Returns (kind, times)."""
+    from oracle.focal_oracle import make_iid
+    w = w or WORKLOAD
+    kind, fn = _reference_callable(w)
     f1, f2 = make_iid(0, w["mods"], B_sample, w["D"])
     f1 = {m: v.requires_grad_(True) for m, v in f1.items()}
     f2 = {m: v.requires_grad_(True) for m, v in f2.items()}
@@ -177,47 +226,69 @@ def cpu_reference_time(B_sample: int, steps: int, warmup: int):
         for v in list(f1.values()) + list(f2.values()):
             v.grad = None
         t0 = time.perf_counter()
-        loss = focal_loss_port(f1, f2, cfg)
+        loss = fn(f1, f2)
         loss.backward()
         float(loss.detach())
         t1 = time.perf_counter()
         if it >= warmup:
             times.append(t1 - t0)
-    return times
+    return kind, times
 
 
 def pick_cpu_sample(budget_s: float, steps: int, warmup: int) -> int:
-    """Largest B in {128, 256, 512} whose (steps + warmup) run fits the budget; cost grows ~ B^2."""
-    t128 = min(cpu_reference_time(128, 2, 1))
-    best = 128
+    """Largest B in {128, 256, 512} (capped at the workload's batch) whose (steps + warmup) run fits the budget; the
+    reference's cost grows ~ B^2."""
+    cap = WORKLOAD["B"]
+    t128 = min(cpu_reference_time(min(128, cap), 2, 1)[1])
+    best = min(128, cap)
     for B in (256, 512):
-        if (steps + warmup) * t128 * (B / 128) ** 2 * 1.3 < budget_s:
+        if B <= cap and (steps + warmup) * t128 * (B / 128) ** 2 * 1.3 < budget_s:
             best = B
     return best
 
 
-def run_reference(args):
+def cfg1_reference(iters=30, warmup=5):
+    """the reference at configs[0] (B=128, M=2, S=4, D=128), 5 warm-up + 30 timed, median."""
+    w = WORKLOADS["cfg1"]
+    kind, ts = cpu_reference_time(w["B"], iters, warmup, w)
+    med = statistics.median(ts)
+    return {"workload": "cfg1: B=128, M=2, S=4, D=128, T=0.5 (BASELINE.json configs[0])", "kind": kind,
+            "ms_median": med * 1e3, "samples_per_s": w["B"] / med, "iters": iters, "warmup": warmup}
+
+
+def cpu_baseline_record(budget_s, steps, warmup):
     import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = WORKLOAD
+    Bs = pick_cpu_sample(budget_s, steps, warmup)
+    kind, ts = cpu_reference_time(Bs, steps, warmup)
+    what = ("unmodified reference FOCALLoss (oracle/_ref, /root/reference/src/models/loss.py)" if kind == "reference"
+            else "op-for-op port of the reference FOCALLoss (oracle/focal_ref_port.py)")
+    sample = (f"{what}, fwd+bwd on CPU, B={Bs} rows of the B={w['B']} workload (D={w['D']}, M={w['M']}, S={w['S']}); "
+              f"cost grows ~B^2 (the reference materialises [S,2b,2b,d]: 34 GB per call at B=8192, it cannot run there)")
+    rec = {"value": Bs / statistics.mean(ts), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+           "sample_batch": Bs, "ms_per_step": statistics.mean(ts) * 1e3}
+    return rec
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    Bs = pick_cpu_sample(150.0, args.steps, args.warmup)
-    times = cpu_reference_time(Bs, args.steps, args.warmup)
-    t = statistics.mean(times)
-    value = Bs / t
+    rec = cpu_baseline_record(150.0, args.steps, args.warmup)
+    try:
+        rec["cfg1"] = cfg1_reference()
+    except Exception as exc:                                  # noqa: BLE001
+        rec["cfg1"] = {"error": repr(exc)}
     w = WORKLOAD
-    sample = (f"op-for-op port of reference FOCALLoss (oracle/focal_ref_port.py), fwd+bwd on CPU, B={Bs} rows of the "
-              f"B={w['B']} workload (D={w['D']}, M={w['M']}, S={w['S']}); cost grows ~B^2 (the reference materialises "
-              f"[S,2b,2b,d]; at B=8192 that is 34 GB per call and cannot run)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "global_batch": w["B"], "cpu_sample_batch": Bs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(), "global_batch": w["B"], "cpu_sample_batch": rec["sample_batch"]},
+        "cpu_baseline": rec,
+        "e2e": {"value": rec["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))

@@ -1,6 +1,8 @@
 // C ABI of the B200-native FOCAL loss hot path (see include/focal_b200.h).
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <cuda_runtime.h>
 
 #include "../../include/focal_b200.h"
@@ -49,17 +51,22 @@ int make_plan(const FocalCfg* cfg, Plan& p) {
   return s.rc;
 }
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember what was set per device
-// ordinal and kernel, so a second GPU driven from the same process gets its own call.
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute of ONE kernel: remember what was
+// set per (kernel, device ordinal), so a second GPU driven from the same process gets its own call.  (Keyed on the
+// function address: all instantiations of a kernel template share one function-pointer TYPE.)
 template <class K>
 int ensure_dyn_smem(K kfn, size_t bytes, const char* what) {
   if (bytes <= 48 * 1024) return FOCAL_OK;
-  static size_t configured[64] = {0};
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, size_t> configured;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-  if (bytes > configured[dev]) {
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(reinterpret_cast<const void*>(kfn)) * 64u + (uint64_t)(dev & 63);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = configured[key];
+  if (bytes > have) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return cuda_ok(what);
-    configured[dev] = bytes;
+    have = bytes;
   }
   return FOCAL_OK;
 }
@@ -88,38 +95,46 @@ int lse_blocks(const Plan& p, int all_rows) {
   return (int)(((long)p.nProb * p.S * 2 * (p.seq1 - p.seq0) + 255) / 256);
 }
 
-template <int MODE, int KB, int SEQ>
+template <int MODE, int KB, int SEQ, int EL>
 int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int grid) {
-  using G = GramCfg<MODE, KB, SEQ>;
+  using G = GramCfg<MODE, KB, SEQ, EL>;
   static_assert(G::BN == tile_bn(KB), "plan.h and gram_kernel.cuh must agree on the column tile");
   using L = GramSmem<G::BN, KB, G::NB>;
-  auto kfn = gram_kernel<MODE, KB, SEQ>;
+  auto kfn = gram_kernel<MODE, KB, SEQ, EL>;
   if (int rc = ensure_dyn_smem(kfn, L::kDynamic, "cudaFuncSetAttribute(gram_kernel)")) return rc;
   if (grid <= 0) return FOCAL_OK;                                 // persistent: at most one CTA per SM (plan.h)
   kfn<<<grid, G::kThreads, L::kDynamic, st>>>(p, sel, ws);
   return cuda_ok("gram_kernel launch");
 }
 
-template <int MODE, int SEQ>
+// operand width in 128-byte K blocks: 1..4 (both precisions); temporal launches also 8 (bf16 "wide": 256 < D <= 512;
+// tf32: D = 256) and, tf32 only, 6 (D = 192)
+template <int MODE, int SEQ, int EL>
 int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int grid) {
   switch (kb) {
 #ifndef FB_FAST_BUILD
-    case 1: return launch_gram<MODE, 1, SEQ>(p, sel, ws, st, grid);
-    case 3: return launch_gram<MODE, 3, SEQ>(p, sel, ws, st, grid);
+    case 1: return launch_gram<MODE, 1, SEQ, EL>(p, sel, ws, st, grid);
+    case 3: return launch_gram<MODE, 3, SEQ, EL>(p, sel, ws, st, grid);
+    case 6:
+      if constexpr (EL == 1 && MODE >= 2) return launch_gram<MODE, 6, SEQ, EL>(p, sel, ws, st, grid);
+      break;
 #endif
-    case 2: return launch_gram<MODE, 2, SEQ>(p, sel, ws, st, grid);
-    case 4: return launch_gram<MODE, 4, SEQ>(p, sel, ws, st, grid);
+    case 2: return launch_gram<MODE, 2, SEQ, EL>(p, sel, ws, st, grid);
+    case 4: return launch_gram<MODE, 4, SEQ, EL>(p, sel, ws, st, grid);
+    case 8:
+#ifdef FB_FAST_BUILD
+      if constexpr (EL == 1 && MODE >= 2) return launch_gram<MODE, 8, SEQ, EL>(p, sel, ws, st, grid);
+#else
+      if constexpr (MODE >= 2) return launch_gram<MODE, 8, SEQ, EL>(p, sel, ws, st, grid);
+#endif
+      break;
   }
   return FOCAL_ESHAPE;
 }
-
-// temporal launches: operand width 1..4 K blocks, or 8 ("wide": 256 < D <= 512)
 template <int MODE, int SEQ>
-int launch_temporal_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int grid) {
-#ifndef FB_FAST_BUILD
-  if (p.kbFull == 8) return launch_gram<MODE, 8, SEQ>(p, sel, ws, st, grid);
-#endif
-  return launch_gram_kb<MODE, SEQ>(p, sel, ws, st, p.kbFull, grid);
+int launch_gram_prec(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int grid) {
+  return p.prec == FOCAL_PREC_TF32 ? launch_gram_kb<MODE, SEQ, 1>(p, sel, ws, st, kb, grid)
+                                   : launch_gram_kb<MODE, SEQ, 0>(p, sel, ws, st, kb, grid);
 }
 
 template <int MODE>
@@ -127,12 +142,12 @@ int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid, int p
   ProbSel sel{};
   sel.peer_wait = peer_wait;
   switch (p.S) {
-    case 4: return launch_temporal_kb<MODE, 4>(p, sel, ws, st, grid);
+    case 4: return launch_gram_prec<MODE, 4>(p, sel, ws, st, p.kbFull, grid);
 #ifndef FB_FAST_BUILD                 // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
-    case 2: return launch_temporal_kb<MODE, 2>(p, sel, ws, st, grid);
-    case 8: return launch_temporal_kb<MODE, 8>(p, sel, ws, st, grid);
-    case 16: return launch_temporal_kb<MODE, 16>(p, sel, ws, st, grid);
-    case 32: return launch_temporal_kb<MODE, 32>(p, sel, ws, st, grid);
+    case 2: return launch_gram_prec<MODE, 2>(p, sel, ws, st, p.kbFull, grid);
+    case 8: return launch_gram_prec<MODE, 8>(p, sel, ws, st, p.kbFull, grid);
+    case 16: return launch_gram_prec<MODE, 16>(p, sel, ws, st, p.kbFull, grid);
+    case 32: return launch_gram_prec<MODE, 32>(p, sel, ws, st, p.kbFull, grid);
 #endif
   }
   return FOCAL_ESHAPE;
@@ -148,7 +163,7 @@ int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st, int peer_wait = 0) {
     for (int q = 0; q < p.nProb; ++q)
       if (p.ops[p.probs[q].opA].kb == kb) sel.idx[sel.n++] = q;
     if (!sel.n) continue;
-    const int rc = launch_gram_kb<MODE, 0>(p, sel, ws, st, kb, p.grid_nce[kb]);
+    const int rc = launch_gram_prec<MODE, 0>(p, sel, ws, st, kb, p.grid_nce[kb]);
     if (rc) return rc;
   }
   return FOCAL_OK;
@@ -161,53 +176,72 @@ int fast_row_vw(const Plan& p, int no_private) {
   return (vw <= 4 || vw == 8) ? vw : 0;           // D = 64, 128, 192, 256, 512
 }
 
-template <int VW>
+template <int VW, int PREC>
 int launch_prologue_fast_vw(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, size_t smem, int grid, int fuse,
                             cudaStream_t st) {
-  if (int rc = ensure_dyn_smem(prologue_fast_kernel<VW>, smem, "cudaFuncSetAttribute(prologue_fast_kernel)")) return rc;
-  prologue_fast_kernel<VW><<<grid, 128, smem, st>>>(p, f, pw, w, fuse);
+  if (int rc = ensure_dyn_smem(prologue_fast_kernel<VW, PREC>, smem, "cudaFuncSetAttribute(prologue_fast_kernel)")) return rc;
+  prologue_fast_kernel<VW, PREC><<<grid, 128, smem, st>>>(p, f, pw, w, fuse);
   return cuda_ok("prologue_fast_kernel");
+}
+template <int PREC>
+int launch_prologue_fast_p(int vw, const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, size_t smem, int grid,
+                           int fuse, cudaStream_t st) {
+  switch (vw) {
+    case 1: return launch_prologue_fast_vw<1, PREC>(p, f, pw, w, smem, grid, fuse, st);
+    case 2: return launch_prologue_fast_vw<2, PREC>(p, f, pw, w, smem, grid, fuse, st);
+    case 3: return launch_prologue_fast_vw<3, PREC>(p, f, pw, w, smem, grid, fuse, st);
+    case 4: return launch_prologue_fast_vw<4, PREC>(p, f, pw, w, smem, grid, fuse, st);
+    case 8:
+      if constexpr (PREC == FOCAL_PREC_BF16) return launch_prologue_fast_vw<8, PREC>(p, f, pw, w, smem, grid, fuse, st);
+      break;                                      // tf32 tiles stop at D = 256
+  }
+  return FOCAL_ESHAPE;
 }
 int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, size_t smem, int grid,
                          int fuse, cudaStream_t st) {
-  switch (vw) {
-    case 1: return launch_prologue_fast_vw<1>(p, f, pw, w, smem, grid, fuse, st);
-    case 2: return launch_prologue_fast_vw<2>(p, f, pw, w, smem, grid, fuse, st);
-    case 3: return launch_prologue_fast_vw<3>(p, f, pw, w, smem, grid, fuse, st);
-    case 4: return launch_prologue_fast_vw<4>(p, f, pw, w, smem, grid, fuse, st);
-    case 8: return launch_prologue_fast_vw<8>(p, f, pw, w, smem, grid, fuse, st);
-  }
-  return FOCAL_ESHAPE;
+  return p.prec == FOCAL_PREC_TF32 ? launch_prologue_fast_p<FOCAL_PREC_TF32>(vw, p, f, pw, w, smem, grid, fuse, st)
+                                   : launch_prologue_fast_p<FOCAL_PREC_BF16>(vw, p, f, pw, w, smem, grid, fuse, st);
 }
 #ifndef FB_FINALIZE_RT
 #define FB_FINALIZE_RT 1          // 1: one warp per (row, tensor) when the launch is latency-bound; 0: always one warp per row
 #endif
-template <int VW, int MAXT>
+template <int VW, int MAXT, int PREC>
 int launch_finalize_rt_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
   const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT) * sizeof(float);
-  if (int rc = ensure_dyn_smem(finalize_rt_kernel<VW, MAXT>, smem, "cudaFuncSetAttribute(finalize_rt_kernel)")) return rc;
-  finalize_rt_kernel<VW, MAXT><<<grid, MAXT > 0 ? 128 * p.nT : 128, smem, st>>>(p, f, g, w);
+  if (int rc = ensure_dyn_smem(finalize_rt_kernel<VW, MAXT, PREC>, smem, "cudaFuncSetAttribute(finalize_rt_kernel)")) return rc;
+  finalize_rt_kernel<VW, MAXT, PREC><<<grid, MAXT > 0 ? 128 * p.nT : 128, smem, st>>>(p, f, g, w);
   return cuda_ok("finalize_rt_kernel");
 }
-template <int VW>
-int launch_finalize_rt_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
+template <int VW, int PREC>
+int launch_finalize_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st,
+                       bool rt) {
+  if (!rt) return launch_finalize_rt_t<VW, 0, PREC>(p, f, g, w, grid, st);
   // <= 4 tensors (M <= 2): 512-thread blocks, 128 registers per thread available; else 1024-thread blocks
-  return p.nT <= 4 ? launch_finalize_rt_t<VW, 4>(p, f, g, w, grid, st) : launch_finalize_rt_t<VW, 8>(p, f, g, w, grid, st);
+  return p.nT <= 4 ? launch_finalize_rt_t<VW, 4, PREC>(p, f, g, w, grid, st)
+                   : launch_finalize_rt_t<VW, 8, PREC>(p, f, g, w, grid, st);
 }
-int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid,
-                         cudaStream_t st) {
+template <int PREC>
+int launch_finalize_fast_p(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid,
+                           cudaStream_t st) {
   // Few rows (a row shard): the launch is one wave of blocks and its time is the dependent chain of one warp -> one warp
   // per (row, tensor) (measured 1024 rows: 41 -> 32 us).  Many rows: one warp per row walking the tensors, compiled for
   // 8 resident blocks per SM (measured 8192 rows: 79 us; (row, tensor) warps 116 us).  (VW 8, 1024 threads) would spill.
   const bool rt = FB_FINALIZE_RT && p.nT <= 8 && grid <= 2 * p.num_sms && !(vw == 8 && p.nT > 4);
   switch (vw) {
-    case 1: return rt ? launch_finalize_rt_vw<1>(p, f, g, w, grid, st) : launch_finalize_rt_t<1, 0>(p, f, g, w, grid, st);
-    case 2: return rt ? launch_finalize_rt_vw<2>(p, f, g, w, grid, st) : launch_finalize_rt_t<2, 0>(p, f, g, w, grid, st);
-    case 3: return rt ? launch_finalize_rt_vw<3>(p, f, g, w, grid, st) : launch_finalize_rt_t<3, 0>(p, f, g, w, grid, st);
-    case 4: return rt ? launch_finalize_rt_vw<4>(p, f, g, w, grid, st) : launch_finalize_rt_t<4, 0>(p, f, g, w, grid, st);
-    case 8: return rt ? launch_finalize_rt_vw<8>(p, f, g, w, grid, st) : launch_finalize_rt_t<8, 0>(p, f, g, w, grid, st);
+    case 1: return launch_finalize_vw<1, PREC>(p, f, g, w, grid, st, rt);
+    case 2: return launch_finalize_vw<2, PREC>(p, f, g, w, grid, st, rt);
+    case 3: return launch_finalize_vw<3, PREC>(p, f, g, w, grid, st, rt);
+    case 4: return launch_finalize_vw<4, PREC>(p, f, g, w, grid, st, rt);
+    case 8:
+      if constexpr (PREC == FOCAL_PREC_BF16) return launch_finalize_vw<8, PREC>(p, f, g, w, grid, st, rt);
+      break;
   }
   return FOCAL_ESHAPE;
+}
+int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid,
+                         cudaStream_t st) {
+  return p.prec == FOCAL_PREC_TF32 ? launch_finalize_fast_p<FOCAL_PREC_TF32>(vw, p, f, g, w, grid, st)
+                                   : launch_finalize_fast_p<FOCAL_PREC_BF16>(vw, p, f, g, w, grid, st);
 }
 
 // local_rows: the caller's tensors start at the first owned row; the kernels index rows globally, so hand them the

@@ -64,13 +64,20 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_KB8_NW               // the temporal launch of B = 4096, M = 4, D = 512 from 1118 to 899 us)
 #define FB_KB8_NW 2
 #endif
+#ifndef FB_TF32_SBO
+#define FB_TF32_SBO 512         // stride between the 4-row atoms of a 32-byte-atom SWIZZLE_128B tile (tools/tf32_probe.py)
+#endif
 constexpr int kTmemCols = 512;
 
 // Tile configuration as a function of the mode and the operand width in 64-element K blocks (see header comment).
-template <int MODE, int KB, int SEQ>
+// EL: element type of the tiles, 0 = bf16 (64 per 128-byte K block), 1 = tf32 (32 per K block).  KB counts 128-byte K
+// blocks, so the shared-memory / TMA side of a configuration depends on KB alone and the two precisions share it.
+template <int MODE, int KB, int SEQ, int EL = 0>
 struct GramCfg {
   static constexpr bool kBwd = (MODE == 1 || MODE == 3);
   static constexpr bool kTmp = (MODE >= 2);
+  static constexpr int kEPB = EL ? 32 : 64;                                      // elements per K block
+  static constexpr bool kWide = (EL == 0 && KB > 4);                             // bf16, 256 < D <= 512: O in two passes
   static constexpr int BN = tile_bn(KB);                                         // column tile
   static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : (KB == 8 ? FB_KB8_NS : 4));  // S stages
   static constexpr int NB = KB <= 3 ? 5 : (KB == 4 ? FB_KB4_NB : 1);             // B-tile ring stages (smem budget)
@@ -79,8 +86,10 @@ struct GramCfg {
   static constexpr int CW = (NG == 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
   static constexpr int kThreads = 64 + 128 * NG;
   static_assert(NG <= 4, "partial-sum arrays and register budget are sized for <= 4 epilogue warpgroups");
-  static constexpr int kOKB = KB > 4 ? 4 : KB;       // K blocks of the O accumulator (wide mode: one half per pass)
-  static_assert((kBwd ? kOKB * 64 : 0) + NS * BN <= kTmemCols, "TMEM budget");
+  static constexpr int kOKB = kWide ? 4 : KB;        // K blocks of the O accumulator (wide mode: one half per pass)
+  static constexpr int kON = kOKB * kEPB;            // columns of the O accumulator = UMMA #2 N
+  static_assert(kON <= 256, "UMMA N");
+  static_assert((kBwd ? kON : 0) + NS * BN <= kTmemCols, "TMEM budget");
 };
 
 template <int BN, int KB, int kNumBStages>
@@ -138,7 +147,7 @@ __device__ __forceinline__ int gram_num_items(const Plan& p, const ProbSel& sel)
     return sel.n * p.S * 2 * (t1 - t0);
   } else {
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
-    return p.nT * (t1 - t0) * ((MODE == TMP_BWD && p.kbFull > 4) ? 2 : 1);     // wide mode: one item per output half
+    return p.nT * (t1 - t0) * ((MODE == TMP_BWD && p.wide) ? 2 : 1);           // wide mode: one item per output half
   }
 }
 
@@ -167,7 +176,7 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
   } else {
     const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM, nrt = t1 - t0;
     int r = it, half = 0;
-    if (MODE == TMP_BWD && p.kbFull > 4) { half = r & 1; r >>= 1; }
+    if (MODE == TMP_BWD && p.wide) { half = r & 1; r >>= 1; }
     const int rt = t0 + r % nrt;
     const int c = r / nrt;
     x.kstride = (uint64_t)p.Bpad * 128;
@@ -208,22 +217,25 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int MODE, int KB, int SEQ>
-__global__ void __launch_bounds__((GramCfg<MODE, KB, SEQ>::kThreads), 1)
+template <int MODE, int KB, int SEQ, int EL>
+__global__ void __launch_bounds__((GramCfg<MODE, KB, SEQ, EL>::kThreads), 1)
 gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel, uint8_t* __restrict__ ws) {
-  using G = GramCfg<MODE, KB, SEQ>;
+  using G = GramCfg<MODE, KB, SEQ, EL>;
   constexpr int BN = G::BN, NS = G::NS, NB = G::NB, CW = G::CW, NW = G::NW, NG = G::NG;
   using L = GramSmem<BN, KB, NB>;
   constexpr bool kIsNce = (MODE == NCE_FWD || MODE == NCE_BWD);
   constexpr bool kBwd = (MODE == NCE_BWD || MODE == TMP_BWD);
   constexpr bool kColVec = (MODE != NCE_FWD);
   constexpr int kEpiThreads = 128 * NG;
-  // TMEM columns between the W of consecutive UMMA #2 K steps (16 bf16 = 8 packed columns).  When two warpgroups share a
-  // stage each W chunk stays inside the 16 S columns its own warpgroup consumed, so nobody overwrites columns the
-  // other warpgroup may not have read yet.
-  constexpr int kWStep = (NW > 1) ? 16 : 8;
+  // TMEM columns between the W of consecutive UMMA #2 K steps.  bf16: 16 elements = 8 packed columns; when two
+  // warpgroups share a stage each W chunk stays inside the 16 S columns its own warpgroup consumed, so nobody overwrites
+  // columns the other warpgroup may not have read yet.  tf32: W (one column per element, 8 per K step) replaces S in place.
+  constexpr bool kTf32 = (EL == 1);
+  constexpr bool kWide = G::kWide;
+  constexpr int kWStep = kTf32 ? 8 : ((NW > 1) ? 16 : 8);
   static_assert(NW == 1 || CW == 16, "shared stages use 16-column chunks");
-  constexpr int kON = G::kOKB * 64;                  // UMMA #2 N = padded operand width (wide mode: one half of it)
+  constexpr int kON = G::kON;                        // UMMA #2 N = padded operand width (wide mode: one half of it)
+  constexpr int kK2 = kTf32 ? 8 : 16;                // rows of the B tile one UMMA #2 K step consumes
   constexpr int kKSteps = KB * 4;                    // UMMA #1 K steps (K padded to 64 with zeros)
   constexpr uint32_t kOCol = 0;                      // TMEM: O accumulator at [0, kON) (backward modes only)
   constexpr uint32_t kSCol = kBwd ? kON : 0;         // TMEM: S stage w at kSCol + w * BN
@@ -317,11 +329,15 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   } else if (warp == 1) {
     // =============================== UMMA issuer ===============================
     {
-      constexpr uint32_t idesc1 = umma_idesc(UMMA_BF16, 128, BN, 0, 0);     // S = A(K-major) * B(K-major)^T
-      constexpr uint32_t idesc2 = umma_idesc(UMMA_BF16, 128, kON, 0, 1);    // O += W(TMEM) * B(MN-major)
-      const uint64_t da0 = umma_smem_desc(smem_u32(smem + L::kAOff), 16, 1024);
-      const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
-      const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
+      constexpr uint32_t kFmt = kTf32 ? UMMA_TF32 : UMMA_BF16;
+      constexpr uint32_t idesc1 = umma_idesc(kFmt, 128, BN, 0, 0);          // S = A(K-major) * B(K-major)^T
+      constexpr uint32_t idesc2 = umma_idesc(kFmt, 128, kON, 0, 1);         // O += W(TMEM) * B(MN-major)
+      // bf16: SWIZZLE_128B (8-row atoms, SBO 1024); tf32: SWIZZLE_128B with 32-byte atoms (4-row atoms, SBO 512)
+      constexpr uint32_t kLay = kTf32 ? UMMA_LAYOUT_SW128_B32 : UMMA_LAYOUT_SW128;
+      constexpr uint32_t kSbo = kTf32 ? FB_TF32_SBO : 1024;
+      const uint64_t da0 = umma_smem_desc(smem_u32(smem + L::kAOff), 16, kSbo, kLay);
+      const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, kSbo, kLay);            // K-major view
+      const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, kSbo, kLay);      // MN-major view
       uint32_t nb = 0, ni = 0;
       PieceIter pieces((int)blockIdx.x, (int)gridDim.x, n_items, gram_tiles_per_item<MODE, BN>(p),
                        (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
@@ -343,8 +359,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               const uint32_t d = tmem + kSCol + ss * BN;
 #pragma unroll
               for (int k = 0; k < kKSteps; ++k)
-                umma_bf16(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
-                          db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
+                umma_ss<kTf32>(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                               db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
               umma_commit(&bars->s_full[ss]);
               umma_commit(&bars->b_empty[st]);
             }
@@ -366,12 +382,13 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                 if (elect_one()) {
                   // MN-major view of the B tile; wide mode: the K blocks of this item's output half
                   const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4)) +
-                                      (uint64_t)((KB > 4 ? x.q * 4 * (BN * 128) : 0) >> 4);
-                  const uint32_t a = tmem + kSCol + ss * BN;    // W: packed bf16 over the consumed S stage
+                                      (uint64_t)((kWide ? x.q * 4 * (BN * 128) : 0) >> 4);
+                  const uint32_t a = tmem + kSCol + ss * BN;    // W over the consumed S stage (bf16: packed pairs)
                   const uint32_t acc = (t2 > 0) ? 1u : 0u;
 #pragma unroll
-                  for (int k = 0; k < BN / 16; ++k)
-                    umma_bf16_ts(tmem + kOCol, a + k * kWStep, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
+                  for (int k = 0; k < BN / kK2; ++k)
+                    umma_ts<kTf32>(tmem + kOCol, a + k * kWStep, dm + (uint64_t)((k * kK2 * 128) >> 4), idesc2,
+                                   k > 0 ? 1u : acc);
                   umma_commit(&bars->b_empty[st]);
                 }
                 __syncwarp();
@@ -389,8 +406,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                   const uint32_t d = tmem + kSCol + ss * BN;
 #pragma unroll
                   for (int k = 0; k < kKSteps; ++k)
-                    umma_bf16(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
-                              db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
+                    umma_ss<kTf32>(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                                   db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
                   umma_commit(&bars->s_full[ss]);
                 }
                 __syncwarp();
@@ -530,11 +547,19 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             }
           }
           if (kBwd) {
-            // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed
-            uint32_t pk[CW / 2];
+            if (kTf32) {
+              // ---------------- W chunk, tf32: rounded to 10 mantissa bits, in place over the S columns it came from
+              uint32_t wv[CW];
 #pragma unroll
-            for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            tmem_st_packed<CW>(s_addr + ch * (NW > 1 ? CW : CW / 2), pk);
+              for (int j = 0; j < CW; ++j) wv[j] = cvt_tf32(v[j]);
+              tmem_st_full<CW>(s_addr + ch * CW, wv);
+            } else {
+              // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed
+              uint32_t pk[CW / 2];
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              tmem_st_packed<CW>(s_addr + ch * (NW > 1 ? CW : CW / 2), pk);
+            }
           }
         }
         if (kBwd) {
@@ -571,7 +596,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           } else {
 #pragma unroll
             for (int w = 0; w < NG - 1; ++w) { hinge_acc += bars->part_hinge[w][trow]; cnt_i += bars->part_cnt[w][trow]; }
-            const bool first_half = (KB <= 4) || x.q == 0;      // wide mode: scalars are published by the first pass only
+            const bool first_half = !kWide || x.q == 0;         // wide mode: scalars are published by the first pass only
             if (kBwd && row_ok && first_half)
               reinterpret_cast<float*>(ws + p.rho_off + (uint64_t)pk * p.rho2_delta)[(uint64_t)x.c * p.Bpad + row] = rowacc;
             if (row_ok && first_half && (lane & (SQ - 1)) == 0)
@@ -594,7 +619,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                                                             row0 / kTileM] = npi - 1;
         } else {
           out = reinterpret_cast<float*>(ws + p.dx_off + (uint64_t)pk * p.dx2_delta) +
-                ((uint64_t)x.c * p.Bpad + row) * (KB * 64) + (KB > 4 ? x.q * kON : 0);
+                ((uint64_t)x.c * p.Bpad + row) * (KB * G::kEPB) + (kWide ? x.q * kON : 0);
           if (!second && trow == 0)
             reinterpret_cast<int32_t*>(ws + p.flag_tmp_off)[(uint64_t)x.c * (p.Bpad / kTileM) + row0 / kTileM] = npi - 1;
         }
@@ -614,7 +639,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       }
       if (MODE != NCE_BWD) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // partial arrays / red[] may be reused now
-        if (!kIsNce && wgi == 0 && trow == 0 && (KB <= 4 || x.q == 0)) {
+        if (!kIsNce && wgi == 0 && trow == 0 && (!kWide || x.q == 0)) {
           const int t0 = (p.seq0 * p.S) / kTileM;
           const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
           const int slot = p.np_tmp * (x.c * nrt + (row0 / kTileM - t0));

@@ -21,11 +21,11 @@ constexpr int kMaxOps = 6 * kMaxM;                       // shared + private (+ 
 constexpr int kMaxProb = kMaxM * kMaxM;                  // M^2 InfoNCE problems
 constexpr int kMaxOrth = 2 * (kMaxM + kMaxM * (kMaxM - 1) / 2);
 constexpr int kTileM = 128;                              // rows of a Gram tile (UMMA M, TMEM lanes)
-constexpr int kKBlk = 64;                                // bf16 elements per 128-byte swizzle row
+constexpr int kKBlk = 64;                                // bf16 elements per 128-byte swizzle row (TF32 tiles: 32)
 
 struct OpDesc {          // one normalised InfoNCE operand = a column slice of one feature tensor
-  int32_t tensor, col0, width, kb;   // kb = ceil(width / 64) K blocks
-  uint64_t off;                      // bytes from ws base: bf16 [kb][S*bpad][64], position-major rows, swizzled
+  int32_t tensor, col0, width, kb;   // kb = K blocks of 128 bytes (64 bf16 / 32 tf32 elements), zero-padded
+  uint64_t off;                      // bytes from ws base: [kb][S*bpad][128 B], position-major rows, swizzled
   int32_t nuse;                      // problems this operand takes part in (<= M - 1 for shared, 1 for private)
   int32_t use_prob[kMaxM];           // ... their indices,
   int32_t use_side[kMaxM];           // ... which side of z the operand is on,
@@ -50,6 +50,13 @@ struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
 #endif
 constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : (kb == 4 ? FB_KB4_BN : (kb == 8 ? FB_KB8_BN : 64)); }
 
+// Shared-memory image of an operand row (128 bytes per K block), identical in HBM (the prologue writes it, TMA copies it
+// verbatim): bf16 tiles are SWIZZLE_128B (16-byte chunk c of row r at c ^ (r & 7)); TF32 tiles are SWIZZLE_128B with
+// 32-byte atoms (32-byte chunk c at c ^ (r & 3)), the only swizzle a 32-bit MN-major UMMA operand accepts.
+// Byte offset, within the row's 128 bytes of its K block, of element `e` (index within the block).
+FB_HD uint32_t tile_byte_bf16(uint32_t row, uint32_t e) { return ((((e >> 3) ^ (row & 7u)) << 4) | ((e & 7u) << 1)); }
+FB_HD uint32_t tile_byte_tf32(uint32_t row, uint32_t e) { return ((((e >> 3) ^ (row & 3u)) << 5) | ((e & 7u) << 2)); }
+
 // Problems handled by one InfoNCE launch (all with the same operand width / K-block count).
 struct ProbSel {
   int32_t n;
@@ -63,9 +70,11 @@ struct Plan {
   int32_t nsplit_fwd;                                   // row-sum slots per row (= np_nce)
   // stream-K split of the Gram launches (see PieceIter): grid sizes and the largest number of pieces one 128-row
   // block is cut into; piece k of a block accumulates into the k-th copy of the output buffers
-  int32_t sk_nce, sk_tmp, np_nce, np_tmp, grid_tmp, grid_nce[5];
+  int32_t sk_nce, sk_tmp, np_nce, np_tmp, grid_tmp, grid_nce[9];
   int32_t in_rb, in_bs;                                 // row-blocked inputs: rows per block, block stride (floats)
   int32_t local_rows;                                   // sharded path: the prologue handles the owned rows only
+  int32_t prec, epb;                                    // tile precision (FOCAL_PREC_*), elements per 128-byte K block
+  int32_t wide;                                         // bf16, 256 < D <= 512: O accumulator in two 256-column passes
   int32_t indirect;                                     // caller pointers come from the table at ptrs_off (CUDA graphs)
   float T, margin, w_shared, w_private, w_orth, w_rank;
   float alpha;                                          // sqrt(log2(e)/T): operand pre-scale, Gram = log2-domain logit
@@ -79,7 +88,7 @@ struct Plan {
   uint64_t rpart_off;   // fp32 [nsplit_fwd][nProb][S][2][bpad]
   uint64_t rsum_off;    // fp32 [nProb][S][2][bpad]
   uint64_t rinv_off;    // fp32 [nProb][S][2][bpad]
-  uint64_t dx_off;      // fp32 [2M][Bpad][kbFull*64]
+  uint64_t dx_off;      // fp32 [2M][Bpad][kbFull*epb]
   uint64_t rho_off;     // fp32 [2M][Bpad] sum_j r_ij
   uint64_t cnt_off;     // int32 [2M][bpad]  active hinges per sequence
   uint64_t part1_off;   // fp32 [nblk1][4]  prologue partials: orth, pos_shared, pos_private
@@ -207,19 +216,33 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   if (c.S > 32 || (c.S & (c.S - 1))) return FOCAL_ESHAPE;  // sequence = power-of-two rows of one warp
   if (c.D < 2 || c.D > 512) return FOCAL_ESHAPE;
   if (!(c.temperature > 0.f)) return FOCAL_EINVAL;
-  if (c.precision != FOCAL_PREC_BF16) return FOCAL_EINVAL;
+  if (c.precision != FOCAL_PREC_BF16 && c.precision != FOCAL_PREC_TF32) return FOCAL_EINVAL;
+  p.prec = c.precision;
+  p.epb = c.precision == FOCAL_PREC_TF32 ? 32 : kKBlk;
+  // TF32 tiles are 4 bytes per element: a 128-row A tile of more than 256 columns does not fit shared memory
+  if (c.precision == FOCAL_PREC_TF32 && c.D > 256) return FOCAL_ESHAPE;
   p.B = c.B; p.S = c.S; p.M = c.M; p.D = c.D; p.d = c.D / 2;
   p.b = c.B / c.S;
   p.nT = 2 * c.M;
-  // temporal operand width in 64-column K blocks: 1..4, or 8 (zero-padded) for 256 < D <= 512, the "wide" Gram mode
-  p.kbFull = c.D <= 256 ? (c.D + kKBlk - 1) / kKBlk : 8;
+  // K blocks (128 bytes = 64 bf16 / 32 tf32 elements) of an operand of `w` columns, rounded up (zero padding) to a width
+  // the Gram kernels are instantiated for: 1, 2, 3, 4, 6, 8
+  auto kblocks = [&](int w) {
+    int kb = (w + p.epb - 1) / p.epb;
+    if (p.prec == FOCAL_PREC_BF16) return kb > 4 ? 8 : kb;       // bf16: 1..4, or the wide mode's 8
+    if (kb == 5) kb = 6;
+    if (kb == 7) kb = 8;
+    return kb;
+  };
+  // temporal operand: bf16 1..4 blocks, or 8 (zero-padded) for 256 < D <= 512, the "wide" Gram mode; tf32 1..8
+  p.kbFull = kblocks(c.D);
+  p.wide = (c.precision == FOCAL_PREC_BF16 && p.kbFull > 4) ? 1 : 0;
   {
     // rows are padded so that every 128-row A tile and every BN-row B tile stays inside the operand arrays
     auto pad_rows = [](int rows, int bn) {
       const int by_tile = (rows + bn - 1) / bn * bn;
       return (int32_t)align_up((uint64_t)(by_tile > rows ? by_tile : rows), kTileM);
     };
-    const int kbHalf = (p.d + kKBlk - 1) / kKBlk;
+    const int kbHalf = kblocks(p.d);
     p.bpad = pad_rows(p.b, tile_bn(kbHalf));
     if (c.no_private) { const int32_t alt = pad_rows(p.b, tile_bn(p.kbFull)); if (alt > p.bpad) p.bpad = alt; }
     p.Bpad = pad_rows(p.B, tile_bn(p.kbFull));
@@ -246,8 +269,8 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   auto op_private = [&](int t) { return 2 * t + 1; };
   auto op_full = [&](int t) { return 2 * p.nT + t; };
   for (int t = 0; t < p.nT; ++t) {
-    p.ops[op_shared(t)] = OpDesc{t, 0, d, (d + kKBlk - 1) / kKBlk, 0, 0, {0}, {0}, {0}};
-    p.ops[op_private(t)] = OpDesc{t, d, d, (d + kKBlk - 1) / kKBlk, 0, 0, {0}, {0}, {0}};
+    p.ops[op_shared(t)] = OpDesc{t, 0, d, kblocks(d), 0, 0, {0}, {0}, {0}};
+    p.ops[op_private(t)] = OpDesc{t, d, d, kblocks(d), 0, 0, {0}, {0}, {0}};
   }
   p.nOps = 2 * p.nT;
   if (c.no_private) {
@@ -287,9 +310,11 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   // ---- stream-K geometry of the Gram launches
   p.sk_nce = FB_STREAMK_NCE;
   p.np_nce = 2;
-  for (int kb = 1; kb <= 4; ++kb) {
+  for (int kb = 1; kb <= 8; ++kb) {
     int n = 0, np1 = 1;
     for (int q = 0; q < p.nProb; ++q) n += p.ops[p.probs[q].opA].kb == kb;
+    if (!n) continue;
+    if (kb > 4) return FOCAL_ESHAPE;         // InfoNCE operands wider than 4 K blocks (noPrivate: D > 256 bf16, > 128 tf32)
     const int bn = tile_bn(kb);
     p.grid_nce[kb] = piece_grid(n * p.S * 2 * nce_row_tiles(p), 2 * ((p.b + bn - 1) / bn), num_sms, p.sk_nce != 0, &np1);
     if (np1 > p.np_nce) p.np_nce = np1;
@@ -297,7 +322,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   {
     // wide mode (kbFull == 8): the O accumulator holds half of the columns, so the backward launch visits every row
     // block twice (one item per output half) and keeps whole row blocks per CTA (no stream-K pieces)
-    const bool wide = p.kbFull > 4;
+    const bool wide = p.wide != 0;
     const int items = p.nT * tmp_row_tiles(p) * ((wide && p.need_grad) ? 2 : 1), bn = tile_bn(p.kbFull);
     p.sk_tmp = !wide && ((FB_STREAMK_TMP > 0) || (FB_STREAMK_TMP == 0 && items < num_sms));
     p.np_tmp = 2;
@@ -321,7 +346,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.rinv_off = take(rs);
   p.dz_off = off;
   for (int q = 0; q < p.nProb; ++q)
-    p.probs[q].dz_off = take((uint64_t)2 * rowsNce * p.ops[p.probs[q].opA].kb * kKBlk * 4);
+    p.probs[q].dz_off = take((uint64_t)2 * rowsNce * p.ops[p.probs[q].opA].kb * p.epb * 4);
   p.dz_bytes = off - p.dz_off;
   p.dz2_delta = p.dz_bytes;
   for (int k = 1; k < p.np_nce; ++k) take(p.dz_bytes);               // dz accumulators of the secondary pieces
@@ -331,7 +356,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     for (int k = 1; k < n; ++k) take(bytes);
     return o;
   };
-  p.dx_bytes = (uint64_t)p.nT * p.Bpad * p.kbFull * kKBlk * 4;
+  p.dx_bytes = (uint64_t)p.nT * p.Bpad * p.kbFull * p.epb * 4;
   p.dx_off = take_n(p.dx_bytes, p.np_tmp, &p.dx2_delta);
   p.rho_off = take_n((uint64_t)p.nT * p.Bpad * 4, p.np_tmp, &p.rho2_delta);
   p.cnt_off = take_n((uint64_t)p.nT * p.bpad * 4, p.np_tmp, &p.cnt2_delta);

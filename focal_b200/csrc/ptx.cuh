@@ -192,6 +192,10 @@ template <int CW>
 __device__ __forceinline__ void tmem_st_packed(uint32_t taddr, const uint32_t (&r)[CW / 2]) {
   if constexpr (CW == 32) tmem_st16(taddr, r); else tmem_st8(taddr, r);
 }
+template <int CW>
+__device__ __forceinline__ void tmem_st_full(uint32_t taddr, const uint32_t (&r)[CW]) {
+  if constexpr (CW == 32) tmem_st32(taddr, r); else tmem_st16(taddr, r);
+}
 
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B operand tiles.
@@ -264,6 +268,18 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (TF32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
+  else umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+template <bool TF32>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (TF32) umma_tf32_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+  else umma_bf16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+}
 // All previously issued UMMAs of this thread complete -> one arrival on the mbarrier.
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -299,6 +315,12 @@ __device__ __forceinline__ float lg2_approx(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// fp32 -> tf32 (round to nearest, ties away: 10 mantissa bits kept, low 13 bits zero) as raw bits
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

@@ -55,6 +55,12 @@ __device__ __forceinline__ float bf16_round(float v) {
   return __uint_as_float(pack_bf16x2(v, 0.f) << 16);
 }
 
+__device__ __forceinline__ float tf32_round(float v) { return __uint_as_float(cvt_tf32(v)); }
+// the value the tensor core sees for an operand element in the given tile precision (FOCAL_PREC_*)
+__device__ __forceinline__ float op_round(int prec, float v) { return prec ? tf32_round(v) : bf16_round(v); }
+template <int PREC>
+__device__ __forceinline__ float op_round_t(float v) { return PREC ? tf32_round(v) : bf16_round(v); }
+
 __device__ __forceinline__ float warp_dot(const float* a, const float* b, int n, int lane) {
   float s = 0.f;
   for (int c = lane; c < n; c += 32) s = fmaf(a[c], b[c], s);
@@ -154,12 +160,17 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
         const float scale = p.alpha / fmaxf(sqrtf(ss), kNceEps);
         const float* x = xs + op.tensor * D + op.col0;
         for (int kb = 0; kb < op.kb; ++kb) {
-          const int e = kb * 64 + 2 * lane;
-          const float v0 = (e < op.width) ? x[e] * scale : 0.f;
-          const float v1 = (e + 1 < op.width) ? x[e + 1] * scale : 0.f;
           uint8_t* dst = ws + op.off + ((uint64_t)kb * rowsNce + rowN) * 128;
-          const uint32_t ch = lane >> 2;                       // 16-byte chunk of the 128-byte row
-          *reinterpret_cast<uint32_t*>(dst + ((ch ^ (uint32_t)(rowN & 7)) << 4) + (lane & 3) * 4) = pack_bf16x2(v0, v1);
+          if (p.prec == FOCAL_PREC_TF32) {                     // 32 elements per K block: one per lane
+            const int e = kb * 32 + lane;
+            const float v0 = (e < op.width) ? x[e] * scale : 0.f;
+            *reinterpret_cast<uint32_t*>(dst + tile_byte_tf32((uint32_t)rowN, lane)) = cvt_tf32(v0);
+          } else {                                             // 64 elements per K block: a pair per lane
+            const int e = kb * 64 + 2 * lane;
+            const float v0 = (e < op.width) ? x[e] * scale : 0.f;
+            const float v1 = (e + 1 < op.width) ? x[e + 1] * scale : 0.f;
+            *reinterpret_cast<uint32_t*>(dst + tile_byte_bf16((uint32_t)rowN, 2 * lane)) = pack_bf16x2(v0, v1);
+          }
         }
       }
     }
@@ -169,15 +180,22 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
         const float* x = xs + t * D;
         float sq = 0.f;
         for (int kb = 0; kb < p.kbFull; ++kb) {
-          const int e = kb * 64 + 2 * lane;
-          const float v0 = (e < D) ? x[e] : 0.f;
-          const float v1 = (e + 1 < D) ? x[e + 1] : 0.f;
-          const uint32_t pk = pack_bf16x2(v0, v1);
-          const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
-          sq = fmaf(r0, r0, fmaf(r1, r1, sq));
           uint8_t* dst = ws + p.xt_off + (((uint64_t)t * p.kbFull + kb) * p.Bpad + i) * 128;
-          const uint32_t ch = lane >> 2;
-          *reinterpret_cast<uint32_t*>(dst + ((ch ^ (uint32_t)(i & 7)) << 4) + (lane & 3) * 4) = pk;
+          if (p.prec == FOCAL_PREC_TF32) {
+            const int e = kb * 32 + lane;
+            const uint32_t rv = cvt_tf32((e < D) ? x[e] : 0.f);
+            const float r0 = __uint_as_float(rv);
+            sq = fmaf(r0, r0, sq);
+            *reinterpret_cast<uint32_t*>(dst + tile_byte_tf32((uint32_t)i, lane)) = rv;
+          } else {
+            const int e = kb * 64 + 2 * lane;
+            const float v0 = (e < D) ? x[e] : 0.f;
+            const float v1 = (e + 1 < D) ? x[e + 1] : 0.f;
+            const uint32_t pk = pack_bf16x2(v0, v1);
+            const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+            sq = fmaf(r0, r0, fmaf(r1, r1, sq));
+            *reinterpret_cast<uint32_t*>(dst + tile_byte_bf16((uint32_t)i, 2 * lane)) = pk;
+          }
         }
         sq = warp_sum(sq);
         if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
@@ -198,7 +216,8 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
           const float* xa = xs + a.tensor * D + a.col0;
           const float* xb = xs + b.tensor * D + b.col0;
           float dot = 0.f;
-          for (int c = lane; c < a.width; c += 32) dot = fmaf(bf16_round(xa[c] * fa), bf16_round(xb[c] * fb2), dot);
+          for (int c = lane; c < a.width; c += 32)
+            dot = fmaf(op_round(p.prec, xa[c] * fa), op_round(p.prec, xb[c] * fb2), dot);
           dot = warp_sum(dot);
           if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
         }
@@ -244,7 +263,7 @@ __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan
     for (int b2 = a + 1; b2 < S; ++b2) {
       float d2 = 0.f;
       for (int c = lane; c < D; c += 32) {
-        const float df = bf16_round(__ldg(x + a * D + c)) - bf16_round(__ldg(x + b2 * D + c));
+        const float df = op_round(p.prec, __ldg(x + a * D + c)) - op_round(p.prec, __ldg(x + b2 * D + c));
         d2 = fmaf(df, df, d2);
       }
       d2 = warp_sum(d2);
@@ -339,7 +358,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
   // ---- temporal
   if ((p.terms & FOCAL_TERM_TEMPORAL) && p.b > 1 && S > 1) {
     const float bb = (float)p.b * (float)(p.b - 1);
-    const int Dp = p.kbFull * 64;
+    const int Dp = p.kbFull * p.epb;
     for (int t = 0; t < p.nT; ++t) {
       const float* x = xs + t * D;
       // a row block whose column tiles were split over several CTAs (stream-K) has one set of accumulators per piece
@@ -355,7 +374,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
         float yc = y[c];
         for (int k = 1; k <= extra; ++k)
           yc += (reinterpret_cast<const float*>(ws + p.dx_off + k * p.dx2_delta) + ((uint64_t)t * p.Bpad + i) * Dp)[c];
-        gs[t * D + c] = p.w_rank * (bf16_round(x[c]) * rho - yc);
+        gs[t * D + c] = p.w_rank * (op_round(p.prec, x[c]) * rho - yc);
       }
       // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
       const float coef = p.w_rank * 2.f * (float)cnt / (bb * (float)(S * S - S));
@@ -365,14 +384,14 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
           if (j == s) continue;
           float d2 = 0.f;
           for (int c = lane; c < D; c += 32) {
-            const float df = bf16_round(x[c]) - bf16_round(__ldg(base + (size_t)j * D + c));
+            const float df = op_round(p.prec, x[c]) - op_round(p.prec, __ldg(base + (size_t)j * D + c));
             d2 = fmaf(df, df, d2);
           }
           d2 = warp_sum(d2);
           if (d2 > 0.f) {
             const float r = coef * rsqrtf(d2);
             for (int c = lane; c < D; c += 32)
-              gs[t * D + c] += r * (bf16_round(x[c]) - bf16_round(__ldg(base + (size_t)j * D + c)));
+              gs[t * D + c] += r * (op_round(p.prec, x[c]) - op_round(p.prec, __ldg(base + (size_t)j * D + c)));
           }
         }
       }
@@ -386,7 +405,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
     const float inv_alpha = 1.f / p.alpha;
     for (int o = 0; o < p.nOps; ++o) {
       const OpDesc& op = p.ops[o];
-      const int w = op.width, wp = op.kb * 64;
+      const int w = op.width, wp = op.kb * p.epb;
       const float ss = (w == D) ? sfull[op.tensor] : (op.col0 == 0 ? ssh[op.tensor] : spr[op.tensor]);
       const float nrm = fmaxf(sqrtf(ss), kNceEps);
       const float* x = xs + op.tensor * D + op.col0;
@@ -411,7 +430,8 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
         // dominates the row (small T, aligned views) W_kp - 2 is a tiny difference that bf16 W would destroy.
         const float fk = p.alpha / nrm;
         float gpos = 0.f;
-        for (int c = lane; c < w; c += 32) gpos = fmaf(bf16_round(x[c] * fk), bf16_round(px[c] * pinv), gpos);
+        for (int c = lane; c < w; c += 32)
+          gpos = fmaf(op_round(p.prec, x[c] * fk), op_round(p.prec, px[c] * pinv), gpos);
         gpos = warp_sum(gpos);
         const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
         const float wkp = exp2f(gpos) * (1.f / rs[(uint64_t)side * p.bpad + I] + 1.f / rs[(uint64_t)(1 - side) * p.bpad + I]);
@@ -419,7 +439,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
           float ac = acc[c];
           for (int k = 1; k <= extra; ++k)
             ac += (reinterpret_cast<const float*>(ws + pr.dz_off + k * p.dz2_delta) + ((uint64_t)side * S * p.bpad + rowN) * wp)[c];
-          tmp[c] += wq * inv_alpha * (ac + (wkp - 2.f) * bf16_round(px[c] * pinv));
+          tmp[c] += wq * inv_alpha * (ac + (wkp - 2.f) * op_round(p.prec, px[c] * pinv));
         }
       }
       if (!used) continue;

@@ -46,9 +46,30 @@ __device__ __forceinline__ void st_frag(float* p, const float (&v)[VW]) {
 
 // Store VW consecutive bf16 operand elements starting at element e0 (multiple of VW) of a swizzled 128-byte-row
 // operand array: K block e0/64, 16-byte chunk ((e0 % 64) / 8) ^ (row & 7).
-template <int VW>
+template <int VW, int PREC = 0>
 __device__ __forceinline__ void st_operand(uint8_t* op_base, uint64_t kstride_rows, uint64_t row, int e0,
                                            const float (&v)[VW]) {
+  if (PREC == FOCAL_PREC_TF32) {
+    // 32 tf32 elements per K block, 32-byte atoms: VW consecutive elements (e0 % VW == 0) stay inside one atom
+    uint8_t* dst = op_base + ((uint64_t)(e0 >> 5) * kstride_rows + row) * 128 + tile_byte_tf32((uint32_t)row, e0 & 31);
+    if (VW == 8) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(cvt_tf32(v[0]), cvt_tf32(v[1 % VW]), cvt_tf32(v[2 % VW]), cvt_tf32(v[3 % VW]));
+      *reinterpret_cast<uint4*>(dst + 16) =
+          make_uint4(cvt_tf32(v[4 % VW]), cvt_tf32(v[5 % VW]), cvt_tf32(v[6 % VW]), cvt_tf32(v[7 % VW]));
+    } else if (VW == 4) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(cvt_tf32(v[0]), cvt_tf32(v[1 % VW]), cvt_tf32(v[2 % VW]), cvt_tf32(v[3 % VW]));
+    } else if (VW == 2) {
+      *reinterpret_cast<uint2*>(dst) = make_uint2(cvt_tf32(v[0]), cvt_tf32(v[1 % VW]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        const int el = e0 + e;
+        *reinterpret_cast<uint32_t*>(op_base + ((uint64_t)(el >> 5) * kstride_rows + row) * 128 +
+                                     tile_byte_tf32((uint32_t)row, el & 31)) = cvt_tf32(v[e]);
+      }
+    }
+    return;
+  }
   uint8_t* dst = op_base + ((uint64_t)(e0 >> 6) * kstride_rows + row) * 128 +
                  ((((uint32_t)(e0 & 63) >> 3) ^ (uint32_t)(row & 7)) << 4) + (e0 & 7) * 2;
   if (VW == 8) {
@@ -82,7 +103,7 @@ __device__ __forceinline__ void stage_rows(const Plan& p, const FeatPtrs& f, con
 // ---------------------------------------------------------------------------------------------------------
 // fast prologue (+ fused intra-sequence means when S divides 4)
 // ---------------------------------------------------------------------------------------------------------
-template <int VW>
+template <int VW, int PREC>
 __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constant__ Plan p,
                                                             const __grid_constant__ FeatPtrs f,
                                                             const __grid_constant__ PeerWs pw,
@@ -123,9 +144,9 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
         for (int e = 0; e < VW; ++e) { zs[e] = sh[e] * fa; zp[e] = pr[e] * fb2; }
         for (int r = 0; r < pw.world; ++r) {
           uint8_t* w = pw.ws[r];
-          st_operand<VW>(w + p.ops[2 * t].off, rowsNce, rowN, c0, zs);
-          st_operand<VW>(w + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp);
-          if (VW & 1) {
+          st_operand<VW, PREC>(w + p.ops[2 * t].off, rowsNce, rowN, c0, zs);
+          st_operand<VW, PREC>(w + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp);
+          if (PREC == FOCAL_PREC_BF16 && (VW & 1)) {
             // d = 32 or 96: the last K block is half full -- its 32 padding columns must read as zeros
             const float z1[1] = {0.f};
             st_operand<1>(w + p.ops[2 * t].off, rowsNce, rowN, d + lane, z1);
@@ -136,13 +157,13 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
       if (p.terms & FOCAL_TERM_TEMPORAL) {
         for (int r = 0; r < pw.world; ++r) {
           uint8_t* xt = pw.ws[r] + p.xt_off + (uint64_t)t * p.kbFull * p.Bpad * 128;
-          st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, c0, sh);
-          st_operand<VW>(xt, (uint64_t)p.Bpad, (uint64_t)i, d + c0, pr);
+          st_operand<VW, PREC>(xt, (uint64_t)p.Bpad, (uint64_t)i, c0, sh);
+          st_operand<VW, PREC>(xt, (uint64_t)p.Bpad, (uint64_t)i, d + c0, pr);
         }
         float sq = 0.f;
 #pragma unroll
         for (int e = 0; e < VW; ++e) {
-          const float r0 = bf16_round(sh[e]), r1 = bf16_round(pr[e]);
+          const float r0 = op_round_t<PREC>(sh[e]), r1 = op_round_t<PREC>(pr[e]);
           sq = fmaf(r0, r0, fmaf(r1, r1, sq));
         }
         sq = warp_sum(sq);
@@ -164,7 +185,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
           ld_frag<VW>(xs + b.tensor * D + b.col0 + c0, xb);
           float dot = 0.f;
 #pragma unroll
-          for (int e = 0; e < VW; ++e) dot = fmaf(bf16_round(xa[e] * fa), bf16_round(xb[e] * fb2), dot);
+          for (int e = 0; e < VW; ++e) dot = fmaf(op_round_t<PREC>(xa[e] * fa), op_round_t<PREC>(xb[e] * fb2), dot);
           dot = warp_sum(dot);
           if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
         }
@@ -205,7 +226,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
           float d2 = 0.f;
 #pragma unroll
           for (int e = 0; e < VW; ++e) {
-            const float a = bf16_round(sh[e]) - bf16_round(osh[e]), b = bf16_round(pr[e]) - bf16_round(opr[e]);
+            const float a = op_round_t<PREC>(sh[e]) - op_round_t<PREC>(osh[e]), b = op_round_t<PREC>(pr[e]) - op_round_t<PREC>(opr[e]);
             d2 = fmaf(a, a, fmaf(b, b, d2));
           }
           sum += sqrtf(warp_sum(d2));
@@ -245,7 +266,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
 #ifndef FB_FIN_MINB
 #define FB_FIN_MINB 8            // resident blocks per SM the row-walk variant is compiled for (measured: 4 / 6 / 8 / 10
 #endif                           // blocks -> 107 / 94 / 79 / 92 us at 8192 rows; 8 = 64 registers, small spill)
-template <int VW, int MAXT>
+template <int VW, int MAXT, int PREC>
 __global__ void __launch_bounds__(MAXT > 0 ? 128 * MAXT : 128, MAXT > 0 ? 1 : (VW > 4 ? 4 : FB_FIN_MINB))
 finalize_rt_kernel(const __grid_constant__ Plan p,
                                                            const __grid_constant__ FeatPtrs f,
@@ -293,7 +314,7 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
   // ---- temporal part
   if ((p.terms & FOCAL_TERM_TEMPORAL) && p.b > 1 && S > 1) {
     const float bb = (float)p.b * (float)(p.b - 1);
-    const int Dp = p.kbFull * 64;
+    const int Dp = p.kbFull * p.epb;
     const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off) + (uint64_t)t * (p.Bpad / kTileM) + i / kTileM);
     float rho = __ldg(reinterpret_cast<const float*>(ws + p.rho_off) + (uint64_t)t * p.Bpad + i);
     const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
@@ -314,7 +335,7 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
     float rsh[VW], rpr[VW];
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
-      rsh[e] = bf16_round(sh[e]); rpr[e] = bf16_round(pr[e]);
+      rsh[e] = op_round_t<PREC>(sh[e]); rpr[e] = op_round_t<PREC>(pr[e]);
       gsh[e] = p.w_rank * (rsh[e] * rho - ysh[e]);
       gpr[e] = p.w_rank * (rpr[e] * rho - ypr[e]);
     }
@@ -331,7 +352,7 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
         float d2 = 0.f;
 #pragma unroll
         for (int e = 0; e < VW; ++e) {
-          osh[e] = rsh[e] - bf16_round(osh[e]); opr[e] = rpr[e] - bf16_round(opr[e]);
+          osh[e] = rsh[e] - op_round_t<PREC>(osh[e]); opr[e] = rpr[e] - op_round_t<PREC>(opr[e]);
           d2 = fmaf(osh[e], osh[e], fmaf(opr[e], opr[e], d2));
         }
         d2 = warp_sum(d2);
@@ -352,7 +373,7 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
     for (int half = 0; half < 2; ++half) {
       const OpDesc& op = p.ops[2 * t + half];
       if (op.nuse == 0) continue;
-      const int wp = op.kb * 64;
+      const int wp = op.kb * p.epb;
       const float inv_nk = fminf(rsqrtf(nrm[2 * t + half]), 1.f / kNceEps);        // 1 / max(|z|, eps)
       const float fk = p.alpha * inv_nk;
       float x[VW], tmp[VW];
@@ -379,7 +400,7 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
         // positive column in fp32 (masked out of the tiles): W_kp - 2 is a tiny difference when the positive dominates
         float gpos = 0.f;
 #pragma unroll
-        for (int e = 0; e < VW; ++e) { px[e] = bf16_round(px[e] * fp); gpos = fmaf(bf16_round(x[e] * fk), px[e], gpos); }
+        for (int e = 0; e < VW; ++e) { px[e] = op_round_t<PREC>(px[e] * fp); gpos = fmaf(op_round_t<PREC>(x[e] * fk), px[e], gpos); }
         gpos = warp_sum(gpos);
         const float wkp = ex2_approx(gpos) * (__frcp_rn(r_k) + __frcp_rn(r_p));
         const float wq = prb.weight * inv_tsn * inv_alpha;

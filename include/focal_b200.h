@@ -33,8 +33,10 @@ enum {
 
 /* terms bit mask: which parts of loss.py:139-218 to evaluate */
 enum { FOCAL_TERM_NCE = 1, FOCAL_TERM_ORTH = 2, FOCAL_TERM_TEMPORAL = 4, FOCAL_TERM_ALL = 7 };
-/* precision of the Gram tiles (everything outside the tiles is fp32) */
-enum { FOCAL_PREC_BF16 = 0 };
+/* precision of the Gram tiles (everything outside the tiles is fp32, accumulation is fp32):
+ *   FOCAL_PREC_BF16  bf16 operands, tcgen05 kind::f16  ("bf16 mode": gradients within 1e-2 of the fp32 reference)
+ *   FOCAL_PREC_TF32  tf32 operands, tcgen05 kind::tf32 ("fp32 mode": gradients within 2e-3); D <= 256 */
+enum { FOCAL_PREC_BF16 = 0, FOCAL_PREC_TF32 = 1 };
 
 /*
  * The values FOCALLoss reads from `args` (loss.py:11-23, 149, 163, 211-215) plus build-side options.

@@ -72,76 +72,107 @@ def lay(a, b):
     return ((a + 1) << 12) | ((b + 1) << 16)
 
 
-def report(name, out, ref):
-    if out is None:
-        print(f"{name:75s} launch refused")
-        return
-    err = float((out.double() - ref).abs().max())
-    nz = float((out != 0).float().mean())
-    print(f"{name:75s} max|err| = {err:9.3e}   nonzero = {nz:.2f}   {'OK' if err < 1e-3 else '--'}")
+def build_cases():
+    """List of (name, thunk -> (out, ref)); every case is independent so that a faulting one can be skipped."""
+    from focal_b200 import _cabi
+    lib = _cabi.load_bringup()
+    cases = []
+    K = 32
+
+    def mk(seed, *shape):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        return tf32_round(torch.randn(*shape, device="cuda", generator=g))
+
+    def add(name, fn):
+        cases.append((name, fn))
+
+    for N in (64, 128):
+        def u1(N=N, a_atom=16, b_img=None, a_lay=2, b_lay=2, a_par=(16, 1024, 32), b_par=(16, 1024, 32), a_inter=False):
+            A, Bm = mk(1, 128, K), mk(2, N, K)
+            ai = img_interleaved(A) if a_inter else img_rows(A, a_atom)
+            bi = b_img(Bm)
+            return run(lib, ai, bi, idesc(128, N), *a_par, *b_par, 4, N, TF32 | lay(a_lay, b_lay)), A.double() @ Bm.double().T
+        add(f"U1 N={N} B K-major layout2 (16B atoms) sbo1024", lambda u1=u1: u1(b_img=lambda m: img_rows(m, 16)))
+        for sbo in (512, 1024):
+            add(f"U1 N={N} B K-major layout1 (32B atoms) sbo{sbo}",
+                lambda u1=u1, sbo=sbo: u1(b_img=lambda m: img_rows(m, 32), b_lay=1, b_par=(16, sbo, 32)))
+            add(f"U1 N={N} A+B K-major layout1 (32B atoms) sbo{sbo}",
+                lambda u1=u1, sbo=sbo: u1(a_atom=32, a_lay=1, a_par=(16, sbo, 32), b_img=lambda m: img_rows(m, 32), b_lay=1,
+                                          b_par=(16, sbo, 32)))
+        g8 = K // 4 * 128
+        add(f"U1 N={N} B K-major layout0 interleaved lbo128 sbo{g8}",
+            lambda u1=u1, g8=g8: u1(b_img=img_interleaved, b_lay=0, b_par=(128, g8, 256)))
+        add(f"U1 N={N} B K-major layout0 interleaved lbo{g8} sbo128",
+            lambda u1=u1, g8=g8: u1(b_img=img_interleaved, b_lay=0, b_par=(g8, 128, 256)))
+        add(f"U1 N={N} A+B K-major layout0 interleaved",
+            lambda u1=u1, g8=g8: u1(a_inter=True, a_lay=0, a_par=(128, g8, 256), b_img=img_interleaved, b_lay=0,
+                                    b_par=(128, g8, 256)))
+
+    Kj = 32
+    for Nd in (64, 256):
+        for a_mode, a_tag in ((0, "A smem"), (2, "A tmem")):
+            def u2(Nd=Nd, a_mode=a_mode, z_img=None, b_lay=2, b_par=None):
+                W, Z = mk(3, 128, Kj), mk(4, Kj, Nd)
+                ai = img_rows(W, 16) if a_mode == 0 else W.contiguous().view(torch.uint8).reshape(-1)
+                ap = (16, 1024, 32) if a_mode == 0 else (0, 0, 0)
+                out = run(lib, ai, z_img(Z), idesc(128, Nd, 0, 1), *ap, *b_par, Kj // 8, Nd, a_mode | TF32 | lay(2, b_lay))
+                return out, W.double() @ Z.double()
+            add(f"U2 Nd={Nd} {a_tag} Z MN layout2 (16B atoms) lbo=Kj*128 sbo1024 kstep1024",
+                lambda u2=u2: u2(z_img=lambda m: img_rows(m, 16), b_lay=2, b_par=(Kj * 128, 1024, 1024)))
+            for sbo in (512, 1024):
+                add(f"U2 Nd={Nd} {a_tag} Z MN layout1 (32B atoms) lbo=Kj*128 sbo{sbo} kstep1024",
+                    lambda u2=u2, sbo=sbo: u2(z_img=lambda m: img_rows(m, 32), b_lay=1, b_par=(Kj * 128, sbo, 1024)))
+            add(f"U2 Nd={Nd} {a_tag} Z MN layout1 (32B atoms) lbo512 sbo=Kj*128 (swapped)",
+                lambda u2=u2: u2(z_img=lambda m: img_rows(m, 32), b_lay=1, b_par=(512, Kj * 128, 1024)))
+            grp = Nd // 4 * 128
+            add(f"U2 Nd={Nd} {a_tag} Z MN layout0 interleaved sbo128 lbo{grp}",
+                lambda u2=u2, grp=grp: u2(z_img=img_interleaved, b_lay=0, b_par=(grp, 128, grp)))
+            add(f"U2 Nd={Nd} {a_tag} Z MN layout0 interleaved lbo128 sbo{grp}",
+                lambda u2=u2, grp=grp: u2(z_img=img_interleaved, b_lay=0, b_par=(128, grp, grp)))
+            add(f"U2 Nd={Nd} {a_tag} Z MN layout0 plain rows lbo=Kj*128 sbo1024",
+                lambda u2=u2: u2(z_img=lambda m: img_rows(m, 0), b_lay=0, b_par=(Kj * 128, 1024, 1024)))
+    return cases
+
+
+def child(start):
+    cases = build_cases()
+    for i in range(start, len(cases)):
+        name, fn = cases[i]
+        print(f"BEGIN {i}", flush=True)
+        out, ref = fn()
+        if out is None:
+            print(f"CASE {i} {name:78s} launch refused", flush=True)
+            continue
+        err = float((out.double() - ref).abs().max())
+        nz = float((out != 0).float().mean())
+        print(f"CASE {i} {name:78s} max|err| = {err:9.3e} nonzero = {nz:.2f} {'OK' if err < 1e-3 else '--'}", flush=True)
+    print("DONE", flush=True)
 
 
 def main():
-    from focal_b200 import _cabi
-    lib = _cabi.load_bringup()
-    g = torch.Generator(device="cuda").manual_seed(7)
-    K = 32
-    A = tf32_round(torch.randn(128, K, device="cuda", generator=g))
-    a16 = img_rows(A, 16)
-    print("== UMMA #1: S = A B^T, both K-major (A: SWIZZLE_128B from smem unless stated)")
-    for N in (64, 128):
-        Bm = tf32_round(torch.randn(N, K, device="cuda", generator=g))
-        ref = A.double() @ Bm.double().T
-        report(f"N={N} B K-major layout2 (16B atoms) sbo1024", run(lib, a16, img_rows(Bm, 16), idesc(128, N), 16, 1024, 32, 16, 1024, 32, 4, N, TF32 | lay(2, 2)), ref)
-        for sbo in (512, 1024):
-            report(f"N={N} B K-major layout1 (32B atoms) sbo{sbo}", run(lib, a16, img_rows(Bm, 32), idesc(128, N), 16, 1024, 32, 16, sbo, 32, 4, N, TF32 | lay(2, 1)), ref)
-            report(f"N={N} A+B K-major layout1 (32B atoms) sbo{sbo}", run(lib, img_rows(A, 32), img_rows(Bm, 32), idesc(128, N), 16, sbo, 32, 16, sbo, 32, 4, N, TF32 | lay(1, 1)), ref)
-        # no swizzle: core matrices [row/8][k/4][8][16 B]: LBO = next K unit (128 B), SBO = next row group (K/4 * 128 B)
-        report(f"N={N} B K-major layout0 interleaved lbo128 sbo{K // 4 * 128}", run(lib, a16, img_interleaved(Bm), idesc(128, N), 16, 1024, 32, 128, K // 4 * 128, 256, 4, N, TF32 | lay(2, 0)), ref)
-        report(f"N={N} B K-major layout0 interleaved (lbo/sbo swapped)", run(lib, a16, img_interleaved(Bm), idesc(128, N), 16, 1024, 32, K // 4 * 128, 128, 256, 4, N, TF32 | lay(2, 0)), ref)
-        report(f"N={N} A+B K-major layout0 interleaved", run(lib, img_interleaved(A), img_interleaved(Bm), idesc(128, N), 128, K // 4 * 128, 256, 128, K // 4 * 128, 256, 4, N, TF32 | lay(0, 0)), ref)
-
-    print("== UMMA #2: O = W Z, W K-major (smem, SWIZZLE_128B) or in TMEM, Z [Kj, Nd] MN-major")
-    Kj = 32
-    W = tf32_round(torch.randn(128, Kj, device="cuda", generator=g))
-    w16 = img_rows(W, 16)
-    w_raw = W.contiguous().view(torch.uint8).reshape(-1)
-    for Nd in (64, 256):
-        Z = tf32_round(torch.randn(Kj, Nd, device="cuda", generator=g))
-        ref = W.double() @ Z.double()
-        for a_mode, a_img, a_tag in ((0, w16, "A smem"), (2, w_raw, "A tmem")):
-            ap = (16, 1024, 32) if a_mode == 0 else (0, 0, 0)
-            idn = idesc(128, Nd, 0, 1)
-            report(f"Nd={Nd} {a_tag} Z MN layout2 (16B atoms) lbo=Kj*128 sbo1024 kstep1024",
-                   run(lib, a_img, img_rows(Z, 16), idn, *ap, Kj * 128, 1024, 1024, Kj // 8, Nd, a_mode | TF32 | lay(2, 2)), ref)
-            for sbo in (512, 1024):
-                report(f"Nd={Nd} {a_tag} Z MN layout1 (32B atoms) lbo=Kj*128 sbo{sbo} kstep1024",
-                       run(lib, a_img, img_rows(Z, 32), idn, *ap, Kj * 128, sbo, 1024, Kj // 8, Nd, a_mode | TF32 | lay(2, 1)), ref)
-            report(f"Nd={Nd} {a_tag} Z MN layout1 (32B atoms) lbo/sbo swapped",
-                   run(lib, a_img, img_rows(Z, 32), idn, *ap, 512, Kj * 128, 1024, Kj // 8, Nd, a_mode | TF32 | lay(2, 1)), ref)
-            # no swizzle: [j/8][n/4][8][16 B]: MN units 128 B apart, 8-row K groups (Nd/4)*128 B apart
-            grp = Nd // 4 * 128
-            report(f"Nd={Nd} {a_tag} Z MN layout0 interleaved sbo128 lbo{grp}",
-                   run(lib, a_img, img_interleaved(Z), idn, *ap, grp, 128, grp, Kj // 8, Nd, a_mode | TF32 | lay(2, 0)), ref)
-            report(f"Nd={Nd} {a_tag} Z MN layout0 interleaved lbo128 sbo{grp}",
-                   run(lib, a_img, img_interleaved(Z), idn, *ap, 128, grp, grp, Kj // 8, Nd, a_mode | TF32 | lay(2, 0)), ref)
-            report(f"Nd={Nd} {a_tag} Z MN layout0 plain rows [Nd/32][Kj][128B] lbo=Kj*128 sbo1024",
-                   run(lib, a_img, img_rows(Z, 0), idn, *ap, Kj * 128, 1024, 1024, Kj // 8, Nd, a_mode | TF32 | lay(2, 0)), ref)
-
-    print("== bf16 control: MN-major second GEMM with the shared SWIZZLE_128B tile (must be OK)")
-    Wb = torch.randn(128, 64, device="cuda", generator=g).to(torch.bfloat16)
-    Zb = torch.randn(64, 128, device="cuda", generator=g).to(torch.bfloat16)
-
-    def img16(mat):
-        R, Kc = mat.shape
-        kb = Kc // 64
-        x = mat.reshape(R, kb, 8, 8).permute(1, 0, 2, 3).contiguous()
-        r = torch.arange(R, device=mat.device)
-        c = torch.arange(8, device=mat.device)
-        src = c[None, :] ^ (r[:, None] & 7)
-        return torch.gather(x, 2, src[None, :, :, None].expand(kb, R, 8, 8)).contiguous().view(torch.uint8).reshape(-1)
-    out = run(lib, img16(Wb), img16(Zb), idesc(128, 128, 0, 1, fmt=1), 16, 1024, 32, 64 * 128, 1024, 2048, 4, 128, 1)
-    report("bf16 W smem, Z MN layout2", out, Wb.double() @ Zb.double())
+    import subprocess
+    if len(sys.argv) > 2 and sys.argv[1] == "--child":
+        return child(int(sys.argv[2]))
+    start, guard = 0, 0
+    while guard < 80:
+        guard += 1
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(start)], capture_output=True, text=True)
+        last_begin, done = None, False
+        for line in res.stdout.splitlines():
+            if line.startswith("CASE "):
+                print(line[5:])
+            elif line.startswith("BEGIN "):
+                last_begin = int(line.split()[1])
+            elif line == "DONE":
+                done = True
+        if done:
+            break
+        if last_begin is None:
+            print("child failed before the first case:", res.stderr[-400:])
+            break
+        err = [l for l in res.stderr.splitlines() if "CUDA error" in l or "rror" in l][-1:] or ["?"]
+        print(f"{last_begin} FAULT ({err[0].strip()[:90]})")
+        start = last_begin + 1
 
 
 if __name__ == "__main__":
