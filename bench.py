@@ -311,7 +311,7 @@ def run_ours(args):
 
     import focal_b200
     from focal_b200 import _cabi
-    from focal_b200.engine import FocalEngine, FocalHyper
+    from focal_b200.engine import FocalEngine, FocalHyper, resolve_precision
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -333,11 +333,12 @@ def run_ours(args):
     if B % (S * world):
         raise SystemExit("global batch does not shard over the ranks")
     Bl = B // world
-    hp = FocalHyper(tuple(mods), S, w["T"], w["margin"], *w["weights"], False, w["terms"])
+    hp = FocalHyper(tuple(mods), S, w["T"], w["margin"], *w["weights"], False, w["terms"], args.precision)
     engine = FocalEngine(hp, process_group=group)
+    fp32_mode = resolve_precision(hp, B, D) == _cabi.FOCAL_PREC_FP32
 
     # synthetic inputs: NSETS different batches so that consecutive steps read their inputs from HBM, not L2
-    nsets = min(16, max(2, math.ceil(2 * L2_BYTES / (2 * M * B * D * 4))))     # <= graph cache size of the engine
+    nsets = min(16, max(2, math.ceil(2 * L2_BYTES / (2 * M * B * D * 4))))
     gen = torch.Generator(device="cpu").manual_seed(1234)
     host_sets, dev_sets = [], []
     for s_ in range(nsets):
@@ -358,8 +359,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (every input set is seen at least three times so that its CUDA graph is captured and replayed)
-    n_warm = max(args.warmup, 3 * nsets)
+    # ---- warm-up: W >= 3 steps (the engine runs the first one eagerly, captures the launch sequence on the second and
+    # replays it from then on; the captured graph serves every input set -- pointers travel through the workspace table)
+    n_warm = max(args.warmup, 3)
     for k in range(n_warm):
         step(k)
     sync_all()
@@ -385,9 +387,26 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = B / (ms_step * 1e-3)
+    clocks = sampler.summary() if sampler else None
+
+    # ---- sustained pass: >= 2 s of back-to-back steps with the clocks sampled throughout (what the step costs once the
+    # power cap has pulled the SM clock down); reported beside the K-step figure, never instead of it
+    sustained = None
+    if world == 1 and args.sustain_seconds > 0:
+        n_sus = max(50, int(args.sustain_seconds * 1e3 / max(ms_step, 1e-3)) + 1)
+        with ClockSampler(local_rank) as s2:
+            torch.cuda.synchronize()
+            ev0.record()
+            for k in range(n_sus):
+                step(k)
+            ev1.record()
+            torch.cuda.synchronize()
+        sus_ms = ev0.elapsed_time(ev1) / n_sus
+        sustained = {"steps": n_sus, "seconds": sus_ms * n_sus * 1e-3, "ms_per_step": sus_ms,
+                     "value": B / (sus_ms * 1e-3), "unit": UNIT, "clocks": s2.summary()}
 
     # ---- end-to-end: pinned host inputs -> H2D -> loss + grads -> D2H of the loss, through the module API
-    args_ns = make_args(mods, S, w, group)
+    args_ns = make_args(mods, S, w, group, args.precision)
     module = focal_b200.FOCALLoss(args_ns).to(dev)
     if w["terms"] != 7:
         module._engine = FocalEngine(hp, process_group=group)      # sub-set of the terms (cfg4: InfoNCE only)
@@ -434,7 +453,7 @@ def run_ours(args):
     for ev in consumed:
         ev.record()
     prefetch(0)
-    n_e2e_warm = 3 * nsets
+    n_e2e_warm = max(args.warmup, 3)
     for k in range(n_e2e_warm):
         e2e_step(k, collect_prev=k > 0)
     collect(n_e2e_warm - 1)
@@ -459,6 +478,7 @@ def run_ours(args):
     if rank == 0:
         peaks = measured_peaks()
         F = f_alg(B, M, D, S, w["terms"])
+        peak_tf, peak_src = tensor_peak_for(peaks, clocks, tf32=False)
         roof = None
         if stages is not None:
             # dominant launch: the fused temporal distance/ranking pass (2M calls, fwd+bwd in one launch); for the
@@ -468,30 +488,38 @@ def run_ours(args):
             else:
                 kname, F_k, t_k = "gram_kernel<NCE_BWD> (InfoNCE backward)", 8.0 * M * M * B * B * D / S, stages["nce_grad"]
             traffic = ncu_tensor = None
-            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-            if args.workload == "headline" and os.path.exists(tpath):
-                with open(tpath) as fh:
-                    tj = json.load(fh)
-                traffic = tj.get("gram_kernel_tmp_bwd_dram_bytes_per_launch")
-                ncu_tensor = tj.get("gram_kernel_tmp_bwd_tensor_pipe_active_pct_elapsed")
+            for tname in ("r2_traffic.json", "r1_traffic.json"):
+                tpath = os.path.join(ROOT, "profiles", tname)
+                if args.workload == "headline" and not fp32_mode and os.path.exists(tpath):
+                    with open(tpath) as fh:
+                        tj = json.load(fh)
+                    traffic = tj.get("gram_kernel_tmp_bwd_dram_bytes_per_launch")
+                    ncu_tensor = tj.get("gram_kernel_tmp_bwd_tensor_pipe_active_pct_elapsed")
+                    break
             t_s = max(t_k, 1e-6) * 1e-3
             # SURVEY 8d counts 3 GEMM-equivalents per contraction; the fused temporal pass executes 2 of them (the
-            # symmetric column-side gradient comes for free), the InfoNCE backward pass executes what it counts
-            executed = (2.0 / 3.0) if (w["terms"] & 4) else 1.0
-            roof = {"bound": "tensor", "kernel": kname, "achieved": F_k / t_s / 1e12, "peak": peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": F_k / t_s / 1e12 / peaks["tflops"],
-                    "peak_source": peaks["source"] + " (sustained bf16)", "traffic": traffic,
+            # symmetric column-side gradient comes for free), the InfoNCE backward pass executes what it counts.
+            # fp32 mode: every executed GEMM is three bf16 passes (hi*hi + hi*lo + lo*hi).
+            executed = ((2.0 / 3.0) if (w["terms"] & 4) else 1.0) * (3.0 if fp32_mode else 1.0)
+            roof = {"bound": "tensor", "kernel": kname, "achieved": F_k / t_s / 1e12, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": F_k / t_s / 1e12 / peak_tf,
+                    "peak_source": peak_src, "traffic": traffic,
                     "alg_flops_per_launch": F_k, "launch_ms": t_k,
-                    "executed_frac": executed * F_k / t_s / 1e12 / peaks["tflops"],
+                    "executed_frac": executed * F_k / t_s / 1e12 / peak_tf,
+                    "frac_vs_sustained_peak": F_k / t_s / 1e12 / peaks["tflops_sustained"],
+                    "frac_vs_burst_peak": F_k / t_s / 1e12 / peaks["tflops_burst"],
                     "ncu_tensor_pipe_active_pct": ncu_tensor,
                     "note": "achieved = ALGORITHMIC FLOPs (SURVEY 8d: 3 GEMM-equivalents per contraction) / measured "
-                            "launch time; executed_frac counts the FLOPs the kernel really issues; ncu's "
-                            "sm__pipe_tensor_cycles_active (profiles/r1_ncu_summary.md) is quoted beside it"}
+                            "launch time; frac = achieved / the measured dense bf16 peak that matches the SM clock sampled "
+                            "during the timed region (burst at ~max clock, sustained under the power cap); executed_frac "
+                            "counts the tensor-core FLOPs the kernel really issues; ncu's sm__pipe_tensor_cycles_active "
+                            "(profiles/) is quoted beside it"}
         row_kernels = None
         if stages is not None:
             # the O(B D) kernels against the HBM roofline: algorithmic bytes = what must cross HBM once
+            opb = 4.0 if fp32_mode else 2.0                                    # operand bytes per element (hi + lo images)
             feat_bytes = 2.0 * M * B * D * 4                                   # 2M fp32 [B, D] tensors
-            pro_bytes = feat_bytes + 2 * (2.0 * M * B * D * 2)                 # read features, write both bf16 operand sets
+            pro_bytes = feat_bytes + 2 * (2.0 * M * B * D * opb)               # read features, write both operand sets
             fin_bytes = feat_bytes + feat_bytes                                # read features, write gradients
             if w["terms"] & 1:
                 fin_bytes += 2.0 * M * B * D * 4                               # + the InfoNCE accumulators (dz)
@@ -504,17 +532,21 @@ def run_ours(args):
                                      "frac_hbm": nbytes / t_s / 1e9 / peaks["hbm"]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            Bs = pick_cpu_sample(20.0, 3, 1)
-            ts = cpu_reference_time(Bs, 3, 1)
-            cpu = {"value": Bs / statistics.mean(ts), "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"op-for-op port of the reference loss on CPU, fwd+bwd, B={Bs} of the B={B} workload "
-                             f"(D={D}, M={M}, S={S}); the reference cannot run B=8192 (34 GB per InfoNCE call)"}
+            cpu = cpu_baseline_record(12.0, 3, 1)
+            try:
+                cpu["cfg1"] = cfg1_reference(iters=30, warmup=5)
+            except Exception as exc:                              # noqa: BLE001
+                cpu["cfg1"] = {"error": repr(exc)}
+        sus_frac = None
+        if sustained is not None:
+            pk, src = tensor_peak_for(peaks, sustained["clocks"])
+            sustained["tensor_roofline_frac"] = F / (sustained["ms_per_step"] * 1e-3) / 1e12 / pk
+            sustained["peak"] = pk
+            sustained["peak_source"] = src
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16x3 (fp32 mode)" if fp32_mode else "bf16", "data": "synthetic",
             "config": {"workload": workload_name(), "global_batch": B, "rows_per_gpu": Bl,
                        "parallelism": (f"row-sharded x{world}, "
                                        + ("exchange by kernel stores into NVLink peer memory + device barriers"
@@ -523,14 +555,17 @@ def run_ours(args):
                        if world > 1 else "single GPU",
                        "l2": f"inputs rotate over {nsets} batches ({nsets * 2 * M * B * D * 4 / 2 ** 20:.0f} MiB"
                              + (" > 126 MiB L2)" if nsets * 2 * M * B * D * 4 > L2_BYTES else ", fits L2: small side workload)"),
-                       "tiles": "bf16 operands, fp32 accumulation (tcgen05 kind::f16)"},
-            "tensor_roofline_frac": F / (ms_step * 1e-3) / 1e12 / (peaks["tflops"] * world),   # of the N GPUs' peak
-            "alg_tflops": F / (ms_step * 1e-3) / 1e12,
+                       "tiles": ("split-bf16 operands (hi + lo, 16 significant bits), three tcgen05 kind::f16 passes per "
+                                 "product, fp32 accumulation" if fp32_mode
+                                 else "bf16 operands, fp32 accumulation (tcgen05 kind::f16)")},
+            "tensor_roofline_frac": F / (ms_step * 1e-3) / 1e12 / (peak_tf * world),   # of the N GPUs' peak
+            "tensor_roofline_peak": {"tflops_per_gpu": peak_tf, "source": peak_src},
+            "alg_tflops": F / (ms_step * 1e-3) / 1e12, "sustained": sustained,
             "roofline": roof, "row_kernels_hbm": row_kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": args.steps * launches_per_step(engine, B, D, world),
             "stages_ms": stages, "host_enqueue_ms_per_step": host_ms,
-            "cuda_graph_replays": engine.graph_replays,
-            "clocks": sampler.summary() if sampler else None,
+            "cuda_graph_replays": engine.graph_replays, "cuda_graph_captures": engine.graph_captures,
+            "clocks": clocks,
             "loss": float(loss5[0].item()),
         }
         print(json.dumps(out))
@@ -543,10 +578,14 @@ def run_ours(args):
         wd = threading.Timer(30.0, _bail)
         wd.daemon = True
         wd.start()
-        engine._graphs.clear()
+        engine._steps.clear()
         if module._engine is not None:
-            module._engine._graphs.clear()
+            module._engine._steps.clear()
         torch.cuda.synchronize()
+        dist.barrier()
+        engine.backend.close()
+        if module._engine is not None and module._engine.backend is not engine.backend:
+            module._engine.backend.close()
         dist.barrier()
         dist.destroy_process_group()
         wd.cancel()
@@ -577,13 +616,14 @@ def launches_per_step(engine, B, D, world):
     if (hp.terms & 4) and hp.seq_len > 1:
         n += 1                                                      # temporal
     n += 2                                                          # finalize, loss_reduce
+    n += 1 if engine.use_cuda_graph else 0                          # set_ptrs before every graph replay
     return n
 
 
-def make_args(mods, S, w, group):
+def make_args(mods, S, w, group, precision="auto"):
     import types
     return types.SimpleNamespace(
-        device="cuda", model="DeepSense", tag=None, focal_process_group=group,
+        device="cuda", model="DeepSense", tag=None, focal_process_group=group, focal_precision=precision,
         dataset_config={"modality_names": list(mods), "seq_len": S,
                         "FOCAL": {"temperature": {"DeepSense": w["T"], "SW_Transformer": 0.07},
                                   "inter_rank_margin": w["margin"],
@@ -637,6 +677,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", choices=["bf16", "fp32", "auto"], default="bf16",
+                    help="tile precision of the Gram kernels (north_star's bf16 / fp32 modes)")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0,
+                    help="length of the second, clock-sampled timed pass (0 disables it)")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="headline",
                     help="other BASELINE.json configurations (for profiles/); the bench line is the default")
     args = ap.parse_args()

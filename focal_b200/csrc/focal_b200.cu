@@ -107,14 +107,18 @@ int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st,
   return cuda_ok("gram_kernel launch");
 }
 
-// operand width in 128-byte K blocks: 1..4 (both precisions); temporal launches also 8 (bf16 "wide": 256 < D <= 512;
-// tf32: D = 256) and, tf32 only, 6 (D = 192)
+// operand width in 128-byte K blocks.  bf16 tiles: 1..4, temporal launches also 8 ("wide": 256 < D <= 512).
+// Split tiles (hi + lo images): 2, 4, temporal launches also 6 (D = 192) and 8 (D = 256).
 template <int MODE, int SEQ, int EL>
 int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int grid) {
   switch (kb) {
 #ifndef FB_FAST_BUILD
-    case 1: return launch_gram<MODE, 1, SEQ, EL>(p, sel, ws, st, grid);
-    case 3: return launch_gram<MODE, 3, SEQ, EL>(p, sel, ws, st, grid);
+    case 1:
+      if constexpr (EL == 0) return launch_gram<MODE, 1, SEQ, EL>(p, sel, ws, st, grid);
+      break;
+    case 3:
+      if constexpr (EL == 0) return launch_gram<MODE, 3, SEQ, EL>(p, sel, ws, st, grid);
+      break;
     case 6:
       if constexpr (EL == 1 && MODE >= 2) return launch_gram<MODE, 6, SEQ, EL>(p, sel, ws, st, grid);
       break;
@@ -133,7 +137,7 @@ int launch_gram_kb(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t 
 }
 template <int MODE, int SEQ>
 int launch_gram_prec(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int kb, int grid) {
-  return p.prec == FOCAL_PREC_TF32 ? launch_gram_kb<MODE, SEQ, 1>(p, sel, ws, st, kb, grid)
+  return p.prec == FOCAL_PREC_FP32 ? launch_gram_kb<MODE, SEQ, 1>(p, sel, ws, st, kb, grid)
                                    : launch_gram_kb<MODE, SEQ, 0>(p, sel, ws, st, kb, grid);
 }
 
@@ -193,13 +197,13 @@ int launch_prologue_fast_p(int vw, const Plan& p, const FeatPtrs& f, const PeerW
     case 4: return launch_prologue_fast_vw<4, PREC>(p, f, pw, w, smem, grid, fuse, st);
     case 8:
       if constexpr (PREC == FOCAL_PREC_BF16) return launch_prologue_fast_vw<8, PREC>(p, f, pw, w, smem, grid, fuse, st);
-      break;                                      // tf32 tiles stop at D = 256
+      break;                                      // split tiles stop at D = 256
   }
   return FOCAL_ESHAPE;
 }
 int launch_prologue_fast(int vw, const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, size_t smem, int grid,
                          int fuse, cudaStream_t st) {
-  return p.prec == FOCAL_PREC_TF32 ? launch_prologue_fast_p<FOCAL_PREC_TF32>(vw, p, f, pw, w, smem, grid, fuse, st)
+  return p.prec == FOCAL_PREC_FP32 ? launch_prologue_fast_p<FOCAL_PREC_FP32>(vw, p, f, pw, w, smem, grid, fuse, st)
                                    : launch_prologue_fast_p<FOCAL_PREC_BF16>(vw, p, f, pw, w, smem, grid, fuse, st);
 }
 #ifndef FB_FINALIZE_RT
@@ -240,7 +244,7 @@ int launch_finalize_fast_p(int vw, const Plan& p, const FeatPtrs& f, const GradP
 }
 int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid,
                          cudaStream_t st) {
-  return p.prec == FOCAL_PREC_TF32 ? launch_finalize_fast_p<FOCAL_PREC_TF32>(vw, p, f, g, w, grid, st)
+  return p.prec == FOCAL_PREC_FP32 ? launch_finalize_fast_p<FOCAL_PREC_FP32>(vw, p, f, g, w, grid, st)
                                    : launch_finalize_fast_p<FOCAL_PREC_BF16>(vw, p, f, g, w, grid, st);
 }
 

@@ -64,19 +64,22 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_KB8_NW               // the temporal launch of B = 4096, M = 4, D = 512 from 1118 to 899 us)
 #define FB_KB8_NW 2
 #endif
-#ifndef FB_TF32_SBO
-#define FB_TF32_SBO 512         // stride between the 4-row atoms of a 32-byte-atom SWIZZLE_128B tile (tools/tf32_probe.py)
-#endif
 constexpr int kTmemCols = 512;
 
 // Tile configuration as a function of the mode and the operand width in 64-element K blocks (see header comment).
-// EL: element type of the tiles, 0 = bf16 (64 per 128-byte K block), 1 = tf32 (32 per K block).  KB counts 128-byte K
-// blocks, so the shared-memory / TMA side of a configuration depends on KB alone and the two precisions share it.
+// EL: tile precision.  0 = bf16 tiles (north_star's bf16 mode).  1 = split-bf16 tiles (the fp32 mode): every operand
+// element x travels as hi = bf16(x) and lo = bf16(x - hi) -- 16 significant bits -- in two images (K blocks [0, KB/2) =
+// hi, [KB/2, KB) = lo), and every product is three tensor-core passes hi*hi + hi*lo + lo*hi with fp32 accumulation.
+// Why not kind::tf32: a 32-bit MN-major operand (UMMA #2's view of the B tile) is only accepted in the 32-byte-atom
+// swizzle, in which a K-major operand (UMMA #1's view) faults, so no single shared-memory image can feed both GEMMs
+// (tools/tf32_probe.py, profiles/r2_tf32_probe.txt), and two images of a D = 256 tile do not fit beside the 128 KB A tile.
+// KB counts 128-byte K blocks, so the shared-memory / TMA side of a configuration depends on KB alone.
 template <int MODE, int KB, int SEQ, int EL = 0>
 struct GramCfg {
   static constexpr bool kBwd = (MODE == 1 || MODE == 3);
   static constexpr bool kTmp = (MODE >= 2);
-  static constexpr int kEPB = EL ? 32 : 64;                                      // elements per K block
+  static constexpr int kEPB = EL ? 32 : 64;                                      // operand columns per K block (split: hi + lo)
+  static_assert(EL == 0 || KB % 2 == 0, "split tiles: as many lo blocks as hi blocks");
   static constexpr bool kWide = (EL == 0 && KB > 4);                             // bf16, 256 < D <= 512: O in two passes
   static constexpr int BN = tile_bn(KB);                                         // column tile
   static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : (KB == 8 ? FB_KB8_NS : 4));  // S stages
@@ -227,16 +230,15 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   constexpr bool kBwd = (MODE == NCE_BWD || MODE == TMP_BWD);
   constexpr bool kColVec = (MODE != NCE_FWD);
   constexpr int kEpiThreads = 128 * NG;
-  // TMEM columns between the W of consecutive UMMA #2 K steps.  bf16: 16 elements = 8 packed columns; when two
-  // warpgroups share a stage each W chunk stays inside the 16 S columns its own warpgroup consumed, so nobody overwrites
-  // columns the other warpgroup may not have read yet.  tf32: W (one column per element, 8 per K step) replaces S in place.
-  constexpr bool kTf32 = (EL == 1);
+  // TMEM columns between the W of consecutive UMMA #2 K steps (16 bf16 = 8 packed columns).  When two warpgroups share a
+  // stage each W chunk stays inside the 16 S columns its own warpgroup consumed, so nobody overwrites columns the
+  // other warpgroup may not have read yet.  Split tiles: chunk ch keeps its own CW columns: [hi pairs | lo pairs].
+  constexpr bool kSplit = (EL == 1);
   constexpr bool kWide = G::kWide;
-  constexpr int kWStep = kTf32 ? 8 : ((NW > 1) ? 16 : 8);
+  constexpr int kKH = kSplit ? KB / 2 : KB;          // K blocks of one image (split: hi and lo images of kKH blocks each)
+  constexpr int kWStep = (NW > 1) ? 16 : 8;
   static_assert(NW == 1 || CW == 16, "shared stages use 16-column chunks");
   constexpr int kON = G::kON;                        // UMMA #2 N = padded operand width (wide mode: one half of it)
-  constexpr int kK2 = kTf32 ? 8 : 16;                // rows of the B tile one UMMA #2 K step consumes
-  constexpr int kKSteps = KB * 4;                    // UMMA #1 K steps (K padded to 64 with zeros)
   constexpr uint32_t kOCol = 0;                      // TMEM: O accumulator at [0, kON) (backward modes only)
   constexpr uint32_t kSCol = kBwd ? kON : 0;         // TMEM: S stage w at kSCol + w * BN
   static_assert(BN % CW == 0 && (SEQ == 0 || CW % (SEQ > 0 ? SEQ : 1) == 0), "column tile / chunk / sequence");
@@ -329,15 +331,25 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   } else if (warp == 1) {
     // =============================== UMMA issuer ===============================
     {
-      constexpr uint32_t kFmt = kTf32 ? UMMA_TF32 : UMMA_BF16;
-      constexpr uint32_t idesc1 = umma_idesc(kFmt, 128, BN, 0, 0);          // S = A(K-major) * B(K-major)^T
-      constexpr uint32_t idesc2 = umma_idesc(kFmt, 128, kON, 0, 1);         // O += W(TMEM) * B(MN-major)
-      // bf16: SWIZZLE_128B (8-row atoms, SBO 1024); tf32: SWIZZLE_128B with 32-byte atoms (4-row atoms, SBO 512)
-      constexpr uint32_t kLay = kTf32 ? UMMA_LAYOUT_SW128_B32 : UMMA_LAYOUT_SW128;
-      constexpr uint32_t kSbo = kTf32 ? FB_TF32_SBO : 1024;
-      const uint64_t da0 = umma_smem_desc(smem_u32(smem + L::kAOff), 16, kSbo, kLay);
-      const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, kSbo, kLay);            // K-major view
-      const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, kSbo, kLay);      // MN-major view
+      constexpr uint32_t idesc1 = umma_idesc(UMMA_BF16, 128, BN, 0, 0);     // S = A(K-major) * B(K-major)^T
+      constexpr uint32_t idesc2 = umma_idesc(UMMA_BF16, 128, kON, 0, 1);    // O += W(TMEM) * B(MN-major)
+      const uint64_t da0 = umma_smem_desc(smem_u32(smem + L::kAOff), 16, 1024);
+      const uint64_t db0 = umma_smem_desc(smem_u32(smem + L::kBOff), 16, 1024);            // K-major view
+      const uint64_t dm0 = umma_smem_desc(smem_u32(smem + L::kBOff), BN * 128, 1024);      // MN-major view
+      // UMMA #1 of one column tile: K steps of 16 over the kKH blocks of an image; split tiles: three passes
+      // hi*hi + hi*lo + lo*hi (descriptor offsets of the lo images: kKH blocks further)
+      auto issue_gram = [&](uint32_t d, uint64_t db) {
+        constexpr int kPasses = kSplit ? 3 : 1;
+#pragma unroll
+        for (int ps = 0; ps < kPasses; ++ps) {
+          const uint64_t ao = (uint64_t)(((ps == 2) ? kKH * 16384 : 0) >> 4);
+          const uint64_t bo = (uint64_t)(((ps == 1) ? kKH * (BN * 128) : 0) >> 4);
+#pragma unroll
+          for (int k = 0; k < kKH * 4; ++k)
+            umma_bf16(d, da0 + ao + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
+                      db + bo + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, (ps | k) > 0);
+        }
+      };
       uint32_t nb = 0, ni = 0;
       PieceIter pieces((int)blockIdx.x, (int)gridDim.x, n_items, gram_tiles_per_item<MODE, BN>(p),
                        (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
@@ -355,12 +367,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             mbar_wait_warp(&bars->s_empty[ss], ((n / NS) & 1) ^ 1);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
-              const uint32_t d = tmem + kSCol + ss * BN;
-#pragma unroll
-              for (int k = 0; k < kKSteps; ++k)
-                umma_ss<kTf32>(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
-                               db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
+              issue_gram(tmem + kSCol + ss * BN, db0 + (uint64_t)(st * (L::kBStage >> 4)));
               umma_commit(&bars->s_full[ss]);
               umma_commit(&bars->b_empty[st]);
             }
@@ -383,12 +390,24 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                   // MN-major view of the B tile; wide mode: the K blocks of this item's output half
                   const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4)) +
                                       (uint64_t)((kWide ? x.q * 4 * (BN * 128) : 0) >> 4);
-                  const uint32_t a = tmem + kSCol + ss * BN;    // W over the consumed S stage (bf16: packed pairs)
+                  const uint32_t a = tmem + kSCol + ss * BN;    // W: packed bf16 over the consumed S stage
                   const uint32_t acc = (t2 > 0) ? 1u : 0u;
+                  if constexpr (!kSplit) {
 #pragma unroll
-                  for (int k = 0; k < BN / kK2; ++k)
-                    umma_ts<kTf32>(tmem + kOCol, a + k * kWStep, dm + (uint64_t)((k * kK2 * 128) >> 4), idesc2,
-                                   k > 0 ? 1u : acc);
+                    for (int k = 0; k < BN / 16; ++k)
+                      umma_bf16_ts(tmem + kOCol, a + k * kWStep, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
+                  } else {
+                    // split tiles: chunk c of CW columns holds [W_hi pairs | W_lo pairs]; O += Wh Xh + Wh Xl + Wl Xh
+                    constexpr uint64_t lo_img = (uint64_t)((kKH * (BN * 128)) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BN / 16; ++k) {
+                      const uint32_t ah = a + (k * 16 / CW) * CW + (k % (CW / 16)) * 8, al = ah + CW / 2;
+                      const uint64_t dk = dm + (uint64_t)((k * 2048) >> 4);
+                      umma_bf16_ts(tmem + kOCol, ah, dk, idesc2, k > 0 ? 1u : acc);
+                      umma_bf16_ts(tmem + kOCol, ah, dk + lo_img, idesc2, 1u);
+                      umma_bf16_ts(tmem + kOCol, al, dk, idesc2, 1u);
+                    }
+                  }
                   umma_commit(&bars->b_empty[st]);
                 }
                 __syncwarp();
@@ -402,12 +421,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               if (ready) {
                 tc_fence_after();
                 if (elect_one()) {
-                  const uint64_t db = db0 + (uint64_t)(st * (L::kBStage >> 4));
-                  const uint32_t d = tmem + kSCol + ss * BN;
-#pragma unroll
-                  for (int k = 0; k < kKSteps; ++k)
-                    umma_ss<kTf32>(d, da0 + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4),
-                                   db + (uint64_t)(((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4), idesc1, k > 0);
+                  issue_gram(tmem + kSCol + ss * BN, db0 + (uint64_t)(st * (L::kBStage >> 4)));
                   umma_commit(&bars->s_full[ss]);
                 }
                 __syncwarp();
@@ -547,11 +561,15 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             }
           }
           if (kBwd) {
-            if (kTf32) {
-              // ---------------- W chunk, tf32: rounded to 10 mantissa bits, in place over the S columns it came from
+            if (kSplit) {
+              // ---------------- W chunk, split: [hi pairs | lo pairs] over the CW columns this chunk came from
               uint32_t wv[CW];
 #pragma unroll
-              for (int j = 0; j < CW; ++j) wv[j] = cvt_tf32(v[j]);
+              for (int j = 0; j < CW / 2; ++j) {
+                const uint32_t hi = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                wv[j] = hi;
+                wv[CW / 2 + j] = pack_bf16x2(v[2 * j] - __uint_as_float(hi << 16), v[2 * j + 1] - __uint_as_float(hi & 0xffff0000u));
+              }
               tmem_st_full<CW>(s_addr + ch * CW, wv);
             } else {
               // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed

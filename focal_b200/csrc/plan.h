@@ -21,10 +21,10 @@ constexpr int kMaxOps = 6 * kMaxM;                       // shared + private (+ 
 constexpr int kMaxProb = kMaxM * kMaxM;                  // M^2 InfoNCE problems
 constexpr int kMaxOrth = 2 * (kMaxM + kMaxM * (kMaxM - 1) / 2);
 constexpr int kTileM = 128;                              // rows of a Gram tile (UMMA M, TMEM lanes)
-constexpr int kKBlk = 64;                                // bf16 elements per 128-byte swizzle row (TF32 tiles: 32)
+constexpr int kKBlk = 64;                                // bf16 elements per 128-byte swizzle row
 
 struct OpDesc {          // one normalised InfoNCE operand = a column slice of one feature tensor
-  int32_t tensor, col0, width, kb;   // kb = K blocks of 128 bytes (64 bf16 / 32 tf32 elements), zero-padded
+  int32_t tensor, col0, width, kb;   // kb = K blocks of 128 bytes (64 bf16; split tiles: hi blocks then lo blocks)
   uint64_t off;                      // bytes from ws base: [kb][S*bpad][128 B], position-major rows, swizzled
   int32_t nuse;                      // problems this operand takes part in (<= M - 1 for shared, 1 for private)
   int32_t use_prob[kMaxM];           // ... their indices,
@@ -50,12 +50,10 @@ struct OrthDesc {        // one orthogonality pair (loss.py:195-209)
 #endif
 constexpr int tile_bn(int kb) { return kb <= 2 ? 128 : (kb == 4 ? FB_KB4_BN : (kb == 8 ? FB_KB8_BN : 64)); }
 
-// Shared-memory image of an operand row (128 bytes per K block), identical in HBM (the prologue writes it, TMA copies it
-// verbatim): bf16 tiles are SWIZZLE_128B (16-byte chunk c of row r at c ^ (r & 7)); TF32 tiles are SWIZZLE_128B with
-// 32-byte atoms (32-byte chunk c at c ^ (r & 3)), the only swizzle a 32-bit MN-major UMMA operand accepts.
-// Byte offset, within the row's 128 bytes of its K block, of element `e` (index within the block).
+// Shared-memory image of an operand row (128 bytes = 64 bf16 per K block), identical in HBM (the prologue writes it, TMA
+// copies it verbatim): SWIZZLE_128B, 16-byte chunk c of row r at c ^ (r & 7).  Byte offset within the row's 128 bytes
+// of element `e` of the block.  Split tiles (fp32 mode) store a hi image (blocks [0, kb/2)) and a lo image ([kb/2, kb)).
 FB_HD uint32_t tile_byte_bf16(uint32_t row, uint32_t e) { return ((((e >> 3) ^ (row & 7u)) << 4) | ((e & 7u) << 1)); }
-FB_HD uint32_t tile_byte_tf32(uint32_t row, uint32_t e) { return ((((e >> 3) ^ (row & 3u)) << 5) | ((e & 7u) << 2)); }
 
 // Problems handled by one InfoNCE launch (all with the same operand width / K-block count).
 struct ProbSel {
@@ -73,7 +71,7 @@ struct Plan {
   int32_t sk_nce, sk_tmp, np_nce, np_tmp, grid_tmp, grid_nce[9];
   int32_t in_rb, in_bs;                                 // row-blocked inputs: rows per block, block stride (floats)
   int32_t local_rows;                                   // sharded path: the prologue handles the owned rows only
-  int32_t prec, epb;                                    // tile precision (FOCAL_PREC_*), elements per 128-byte K block
+  int32_t prec, epb;                                    // tile precision (FOCAL_PREC_*), operand COLUMNS per K block (64 / 32)
   int32_t wide;                                         // bf16, 256 < D <= 512: O accumulator in two 256-column passes
   int32_t indirect;                                     // caller pointers come from the table at ptrs_off (CUDA graphs)
   float T, margin, w_shared, w_private, w_orth, w_rank;
@@ -216,24 +214,22 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   if (c.S > 32 || (c.S & (c.S - 1))) return FOCAL_ESHAPE;  // sequence = power-of-two rows of one warp
   if (c.D < 2 || c.D > 512) return FOCAL_ESHAPE;
   if (!(c.temperature > 0.f)) return FOCAL_EINVAL;
-  if (c.precision != FOCAL_PREC_BF16 && c.precision != FOCAL_PREC_TF32) return FOCAL_EINVAL;
+  if (c.precision != FOCAL_PREC_BF16 && c.precision != FOCAL_PREC_FP32) return FOCAL_EINVAL;
   p.prec = c.precision;
-  p.epb = c.precision == FOCAL_PREC_TF32 ? 32 : kKBlk;
-  // TF32 tiles are 4 bytes per element: a 128-row A tile of more than 256 columns does not fit shared memory
-  if (c.precision == FOCAL_PREC_TF32 && c.D > 256) return FOCAL_ESHAPE;
+  p.epb = c.precision == FOCAL_PREC_FP32 ? 32 : kKBlk;
+  // split tiles are 4 bytes per element: a 128-row A tile of more than 256 columns does not fit shared memory
+  if (c.precision == FOCAL_PREC_FP32 && c.D > 256) return FOCAL_ESHAPE;
   p.B = c.B; p.S = c.S; p.M = c.M; p.D = c.D; p.d = c.D / 2;
   p.b = c.B / c.S;
   p.nT = 2 * c.M;
-  // K blocks (128 bytes = 64 bf16 / 32 tf32 elements) of an operand of `w` columns, rounded up (zero padding) to a width
-  // the Gram kernels are instantiated for: 1, 2, 3, 4, 6, 8
+  // K blocks (128 bytes = 64 bf16 elements, zero-padded) of an operand of `w` columns: bf16 1..4, or the wide mode's 8;
+  // split tiles: a hi and a lo image of ceil(w / 64) blocks each -> 2, 4, 6, 8
   auto kblocks = [&](int w) {
-    int kb = (w + p.epb - 1) / p.epb;
-    if (p.prec == FOCAL_PREC_BF16) return kb > 4 ? 8 : kb;       // bf16: 1..4, or the wide mode's 8
-    if (kb == 5) kb = 6;
-    if (kb == 7) kb = 8;
-    return kb;
+    const int kb = (w + kKBlk - 1) / kKBlk;
+    if (p.prec == FOCAL_PREC_BF16) return kb > 4 ? 8 : kb;
+    return 2 * kb;
   };
-  // temporal operand: bf16 1..4 blocks, or 8 (zero-padded) for 256 < D <= 512, the "wide" Gram mode; tf32 1..8
+  // temporal operand: bf16 1..4 blocks, or 8 (zero-padded) for 256 < D <= 512, the "wide" Gram mode; split 2..8
   p.kbFull = kblocks(c.D);
   p.wide = (c.precision == FOCAL_PREC_BF16 && p.kbFull > 4) ? 1 : 0;
   {
@@ -314,7 +310,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     int n = 0, np1 = 1;
     for (int q = 0; q < p.nProb; ++q) n += p.ops[p.probs[q].opA].kb == kb;
     if (!n) continue;
-    if (kb > 4) return FOCAL_ESHAPE;         // InfoNCE operands wider than 4 K blocks (noPrivate: D > 256 bf16, > 128 tf32)
+    if (kb > 4) return FOCAL_ESHAPE;         // InfoNCE operands wider than 4 K blocks (noPrivate: D > 256 bf16, > 128 split)
     const int bn = tile_bn(kb);
     p.grid_nce[kb] = piece_grid(n * p.S * 2 * nce_row_tiles(p), 2 * ((p.b + bn - 1) / bn), num_sms, p.sk_nce != 0, &np1);
     if (np1 > p.np_nce) p.np_nce = np1;

@@ -268,18 +268,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-template <bool TF32>
-__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                        uint32_t accumulate) {
-  if constexpr (TF32) umma_tf32(tmem_d, desc_a, desc_b, idesc, accumulate);
-  else umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
-}
-template <bool TF32>
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                        uint32_t accumulate) {
-  if constexpr (TF32) umma_tf32_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
-  else umma_bf16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
-}
 // All previously issued UMMAs of this thread complete -> one arrival on the mbarrier.
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

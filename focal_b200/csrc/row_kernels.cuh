@@ -55,11 +55,25 @@ __device__ __forceinline__ float bf16_round(float v) {
   return __uint_as_float(pack_bf16x2(v, 0.f) << 16);
 }
 
-__device__ __forceinline__ float tf32_round(float v) { return __uint_as_float(cvt_tf32(v)); }
+// split tiles (fp32 mode): hi = bf16(v), lo = bf16(v - hi); the tensor core sees hi + lo (exact in fp32: 16 bits)
+__device__ __forceinline__ float split_round(float v) {
+  const float hi = bf16_round(v);
+  return hi + bf16_round(v - hi);
+}
 // the value the tensor core sees for an operand element in the given tile precision (FOCAL_PREC_*)
-__device__ __forceinline__ float op_round(int prec, float v) { return prec ? tf32_round(v) : bf16_round(v); }
+__device__ __forceinline__ float op_round(int prec, float v) { return prec ? split_round(v) : bf16_round(v); }
 template <int PREC>
-__device__ __forceinline__ float op_round_t(float v) { return PREC ? tf32_round(v) : bf16_round(v); }
+__device__ __forceinline__ float op_round_t(float v) { return PREC ? split_round(v) : bf16_round(v); }
+// What the tiles compute for a product of two operand elements a, b: bf16 tiles hi_a * hi_b; split tiles the three passes
+// hi_a hi_b + hi_a lo_b + lo_a hi_b (the lo * lo term, <= 2^-18 relative, is not computed).  Everything that is
+// subtracted from a tile result (positive logits, squared norms) must be built from exactly this product, otherwise the
+// part of the rounding that is coherent between aligned rows does not cancel.
+__device__ __forceinline__ float tile_product(int prec, float a, float b) {
+  const float ha = bf16_round(a), hb = bf16_round(b);
+  if (!prec) return ha * hb;
+  const float la = bf16_round(a - ha), lb = bf16_round(b - hb);
+  return fmaf(ha, hb + lb, la * hb);
+}
 
 __device__ __forceinline__ float warp_dot(const float* a, const float* b, int n, int lane) {
   float s = 0.f;
@@ -159,18 +173,17 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
         const float ss = (op.width == D) ? sfull[op.tensor] : (op.col0 == 0 ? ssh[op.tensor] : spr[op.tensor]);
         const float scale = p.alpha / fmaxf(sqrtf(ss), kNceEps);
         const float* x = xs + op.tensor * D + op.col0;
-        for (int kb = 0; kb < op.kb; ++kb) {
-          uint8_t* dst = ws + op.off + ((uint64_t)kb * rowsNce + rowN) * 128;
-          if (p.prec == FOCAL_PREC_TF32) {                     // 32 elements per K block: one per lane
-            const int e = kb * 32 + lane;
-            const float v0 = (e < op.width) ? x[e] * scale : 0.f;
-            *reinterpret_cast<uint32_t*>(dst + tile_byte_tf32((uint32_t)rowN, lane)) = cvt_tf32(v0);
-          } else {                                             // 64 elements per K block: a pair per lane
-            const int e = kb * 64 + 2 * lane;
-            const float v0 = (e < op.width) ? x[e] * scale : 0.f;
-            const float v1 = (e + 1 < op.width) ? x[e + 1] * scale : 0.f;
-            *reinterpret_cast<uint32_t*>(dst + tile_byte_bf16((uint32_t)rowN, 2 * lane)) = pack_bf16x2(v0, v1);
-          }
+        const int kh = p.prec == FOCAL_PREC_FP32 ? op.kb / 2 : op.kb;       // blocks of one image
+        for (int kb = 0; kb < kh; ++kb) {                                      // 64 elements per K block: a pair per lane
+          uint8_t* dst = ws + op.off + ((uint64_t)kb * rowsNce + rowN) * 128 + tile_byte_bf16((uint32_t)rowN, 2 * lane);
+          const int e = kb * 64 + 2 * lane;
+          const float v0 = (e < op.width) ? x[e] * scale : 0.f;
+          const float v1 = (e + 1 < op.width) ? x[e + 1] * scale : 0.f;
+          const uint32_t hi = pack_bf16x2(v0, v1);
+          *reinterpret_cast<uint32_t*>(dst) = hi;
+          if (p.prec == FOCAL_PREC_FP32)                                       // lo image: kh blocks further
+            *reinterpret_cast<uint32_t*>(dst + (uint64_t)kh * rowsNce * 128) =
+                pack_bf16x2(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
         }
       }
     }
@@ -179,23 +192,22 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
       for (int t = 0; t < p.nT; ++t) {
         const float* x = xs + t * D;
         float sq = 0.f;
-        for (int kb = 0; kb < p.kbFull; ++kb) {
-          uint8_t* dst = ws + p.xt_off + (((uint64_t)t * p.kbFull + kb) * p.Bpad + i) * 128;
-          if (p.prec == FOCAL_PREC_TF32) {
-            const int e = kb * 32 + lane;
-            const uint32_t rv = cvt_tf32((e < D) ? x[e] : 0.f);
-            const float r0 = __uint_as_float(rv);
-            sq = fmaf(r0, r0, sq);
-            *reinterpret_cast<uint32_t*>(dst + tile_byte_tf32((uint32_t)i, lane)) = rv;
-          } else {
-            const int e = kb * 64 + 2 * lane;
-            const float v0 = (e < D) ? x[e] : 0.f;
-            const float v1 = (e + 1 < D) ? x[e + 1] : 0.f;
-            const uint32_t pk = pack_bf16x2(v0, v1);
-            const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
-            sq = fmaf(r0, r0, fmaf(r1, r1, sq));
-            *reinterpret_cast<uint32_t*>(dst + tile_byte_bf16((uint32_t)i, 2 * lane)) = pk;
+        const int kh = p.prec == FOCAL_PREC_FP32 ? p.kbFull / 2 : p.kbFull;
+        for (int kb = 0; kb < kh; ++kb) {
+          uint8_t* dst = ws + p.xt_off + (((uint64_t)t * p.kbFull + kb) * p.Bpad + i) * 128 + tile_byte_bf16((uint32_t)i, 2 * lane);
+          const int e = kb * 64 + 2 * lane;
+          const float v0 = (e < D) ? x[e] : 0.f;
+          const float v1 = (e + 1 < D) ? x[e + 1] : 0.f;
+          const uint32_t pk = pack_bf16x2(v0, v1);
+          const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+          *reinterpret_cast<uint32_t*>(dst) = pk;
+          float l0 = 0.f, l1 = 0.f;
+          if (p.prec == FOCAL_PREC_FP32) {
+            const uint32_t lo = pack_bf16x2(v0 - r0, v1 - r1);
+            *reinterpret_cast<uint32_t*>(dst + (uint64_t)kh * p.Bpad * 128) = lo;
+            l0 = __uint_as_float(lo << 16); l1 = __uint_as_float(lo & 0xffff0000u);
           }
+          sq = fmaf(r0, r0 + 2.f * l0, fmaf(r1, r1 + 2.f * l1, sq));      // = tile_product(x, x) (no lo * lo term)
         }
         sq = warp_sum(sq);
         if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
           const float* xb = xs + b.tensor * D + b.col0;
           float dot = 0.f;
           for (int c = lane; c < a.width; c += 32)
-            dot = fmaf(op_round(p.prec, xa[c] * fa), op_round(p.prec, xb[c] * fb2), dot);
+            dot += tile_product(p.prec, xa[c] * fa, xb[c] * fb2);
           dot = warp_sum(dot);
           if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
         }
@@ -431,7 +443,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
         const float fk = p.alpha / nrm;
         float gpos = 0.f;
         for (int c = lane; c < w; c += 32)
-          gpos = fmaf(op_round(p.prec, x[c] * fk), op_round(p.prec, px[c] * pinv), gpos);
+          gpos += tile_product(p.prec, x[c] * fk, px[c] * pinv);
         gpos = warp_sum(gpos);
         const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
         const float wkp = exp2f(gpos) * (1.f / rs[(uint64_t)side * p.bpad + I] + 1.f / rs[(uint64_t)(1 - side) * p.bpad + I]);

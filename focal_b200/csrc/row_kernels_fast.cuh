@@ -46,30 +46,9 @@ __device__ __forceinline__ void st_frag(float* p, const float (&v)[VW]) {
 
 // Store VW consecutive bf16 operand elements starting at element e0 (multiple of VW) of a swizzled 128-byte-row
 // operand array: K block e0/64, 16-byte chunk ((e0 % 64) / 8) ^ (row & 7).
-template <int VW, int PREC = 0>
+template <int VW>
 __device__ __forceinline__ void st_operand(uint8_t* op_base, uint64_t kstride_rows, uint64_t row, int e0,
                                            const float (&v)[VW]) {
-  if (PREC == FOCAL_PREC_TF32) {
-    // 32 tf32 elements per K block, 32-byte atoms: VW consecutive elements (e0 % VW == 0) stay inside one atom
-    uint8_t* dst = op_base + ((uint64_t)(e0 >> 5) * kstride_rows + row) * 128 + tile_byte_tf32((uint32_t)row, e0 & 31);
-    if (VW == 8) {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(cvt_tf32(v[0]), cvt_tf32(v[1 % VW]), cvt_tf32(v[2 % VW]), cvt_tf32(v[3 % VW]));
-      *reinterpret_cast<uint4*>(dst + 16) =
-          make_uint4(cvt_tf32(v[4 % VW]), cvt_tf32(v[5 % VW]), cvt_tf32(v[6 % VW]), cvt_tf32(v[7 % VW]));
-    } else if (VW == 4) {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(cvt_tf32(v[0]), cvt_tf32(v[1 % VW]), cvt_tf32(v[2 % VW]), cvt_tf32(v[3 % VW]));
-    } else if (VW == 2) {
-      *reinterpret_cast<uint2*>(dst) = make_uint2(cvt_tf32(v[0]), cvt_tf32(v[1 % VW]));
-    } else {
-#pragma unroll
-      for (int e = 0; e < VW; ++e) {
-        const int el = e0 + e;
-        *reinterpret_cast<uint32_t*>(op_base + ((uint64_t)(el >> 5) * kstride_rows + row) * 128 +
-                                     tile_byte_tf32((uint32_t)row, el & 31)) = cvt_tf32(v[e]);
-      }
-    }
-    return;
-  }
   uint8_t* dst = op_base + ((uint64_t)(e0 >> 6) * kstride_rows + row) * 128 +
                  ((((uint32_t)(e0 & 63) >> 3) ^ (uint32_t)(row & 7)) << 4) + (e0 & 7) * 2;
   if (VW == 8) {
@@ -87,6 +66,20 @@ __device__ __forceinline__ void st_operand(uint8_t* op_base, uint64_t kstride_ro
                     ((((uint32_t)(el & 63) >> 3) ^ (uint32_t)(row & 7)) << 4) + (el & 7) * 2;
       *reinterpret_cast<uint16_t*>(d1) = (uint16_t)(pack_bf16x2(v[e], 0.f) & 0xffffu);
     }
+  }
+}
+
+// Precision-aware operand store: bf16 tiles store bf16(v); split tiles (fp32 mode) store hi = bf16(v) into the hi image
+// and lo = bf16(v - hi) into the lo image, `kh` K blocks further.
+template <int VW, int PREC>
+__device__ __forceinline__ void st_operand_p(uint8_t* op_base, uint64_t kstride_rows, uint64_t row, int e0,
+                                             const float (&v)[VW], int kh) {
+  st_operand<VW>(op_base, kstride_rows, row, e0, v);
+  if (PREC == FOCAL_PREC_FP32) {
+    float lo[VW];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) lo[e] = v[e] - bf16_round(v[e]);
+    st_operand<VW>(op_base + (uint64_t)kh * kstride_rows * 128, kstride_rows, row, e0, lo);
   }
 }
 
@@ -144,27 +137,28 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
         for (int e = 0; e < VW; ++e) { zs[e] = sh[e] * fa; zp[e] = pr[e] * fb2; }
         for (int r = 0; r < pw.world; ++r) {
           uint8_t* w = pw.ws[r];
-          st_operand<VW, PREC>(w + p.ops[2 * t].off, rowsNce, rowN, c0, zs);
-          st_operand<VW, PREC>(w + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp);
-          if (PREC == FOCAL_PREC_BF16 && (VW & 1)) {
+          const int kh = (PREC == FOCAL_PREC_FP32) ? p.ops[2 * t].kb / 2 : p.ops[2 * t].kb;
+          st_operand_p<VW, PREC>(w + p.ops[2 * t].off, rowsNce, rowN, c0, zs, kh);
+          st_operand_p<VW, PREC>(w + p.ops[2 * t + 1].off, rowsNce, rowN, c0, zp, kh);
+          if (VW & 1) {
             // d = 32 or 96: the last K block is half full -- its 32 padding columns must read as zeros
             const float z1[1] = {0.f};
-            st_operand<1>(w + p.ops[2 * t].off, rowsNce, rowN, d + lane, z1);
-            st_operand<1>(w + p.ops[2 * t + 1].off, rowsNce, rowN, d + lane, z1);
+            st_operand_p<1, PREC>(w + p.ops[2 * t].off, rowsNce, rowN, d + lane, z1, kh);
+            st_operand_p<1, PREC>(w + p.ops[2 * t + 1].off, rowsNce, rowN, d + lane, z1, kh);
           }
         }
       }
       if (p.terms & FOCAL_TERM_TEMPORAL) {
         for (int r = 0; r < pw.world; ++r) {
           uint8_t* xt = pw.ws[r] + p.xt_off + (uint64_t)t * p.kbFull * p.Bpad * 128;
-          st_operand<VW, PREC>(xt, (uint64_t)p.Bpad, (uint64_t)i, c0, sh);
-          st_operand<VW, PREC>(xt, (uint64_t)p.Bpad, (uint64_t)i, d + c0, pr);
+          const int khf = (PREC == FOCAL_PREC_FP32) ? p.kbFull / 2 : p.kbFull;
+          st_operand_p<VW, PREC>(xt, (uint64_t)p.Bpad, (uint64_t)i, c0, sh, khf);
+          st_operand_p<VW, PREC>(xt, (uint64_t)p.Bpad, (uint64_t)i, d + c0, pr, khf);
         }
         float sq = 0.f;
 #pragma unroll
         for (int e = 0; e < VW; ++e) {
-          const float r0 = op_round_t<PREC>(sh[e]), r1 = op_round_t<PREC>(pr[e]);
-          sq = fmaf(r0, r0, fmaf(r1, r1, sq));
+          sq += tile_product(PREC, sh[e], sh[e]) + tile_product(PREC, pr[e], pr[e]);
         }
         sq = warp_sum(sq);
         if (lane < pw.world) reinterpret_cast<float*>(pw.ws[lane] + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
@@ -185,7 +179,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
           ld_frag<VW>(xs + b.tensor * D + b.col0 + c0, xb);
           float dot = 0.f;
 #pragma unroll
-          for (int e = 0; e < VW; ++e) dot = fmaf(op_round_t<PREC>(xa[e] * fa), op_round_t<PREC>(xb[e] * fb2), dot);
+          for (int e = 0; e < VW; ++e) dot += tile_product(PREC, xa[e] * fa, xb[e] * fb2);
           dot = warp_sum(dot);
           if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
         }
@@ -400,7 +394,10 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
         // positive column in fp32 (masked out of the tiles): W_kp - 2 is a tiny difference when the positive dominates
         float gpos = 0.f;
 #pragma unroll
-        for (int e = 0; e < VW; ++e) { px[e] = op_round_t<PREC>(px[e] * fp); gpos = fmaf(op_round_t<PREC>(x[e] * fk), px[e], gpos); }
+        for (int e = 0; e < VW; ++e) {
+          gpos += tile_product(PREC, x[e] * fk, px[e] * fp);
+          px[e] = op_round_t<PREC>(px[e] * fp);
+        }
         gpos = warp_sum(gpos);
         const float wkp = ex2_approx(gpos) * (__frcp_rn(r_k) + __frcp_rn(r_p));
         const float wq = prb.weight * inv_tsn * inv_alpha;

@@ -41,12 +41,13 @@ class FocalHyper:
     w_rank: float
     no_private: bool = False
     terms: int = _cabi.FOCAL_TERM_ALL
-    precision: str = "auto"        # "bf16" | "tf32" (north_star's fp32 mode) | "auto" (see resolve_precision)
+    precision: str = "auto"        # "bf16" | "fp32" (split-bf16 tiles, 16 significant bits) | "auto" (resolve_precision)
 
 
-# "auto": batches whose step is launch-latency-sized anyway run the fp32 mode (TF32 tiles); above that the Gram passes
-# are tensor-pipe-bound and run bf16 tiles (north_star's bf16 mode).  FOCAL_B200_PRECISION overrides "auto".
-AUTO_TF32_MAX_ROWS = 0      # TODO(tf32): 2048 once the TF32 tile mode is in
+# "auto": batches whose step is launch-latency-sized anyway run the fp32 mode (split-bf16 tiles, three tensor-core passes
+# per product); above that the Gram passes are tensor-pipe-bound and run bf16 tiles (north_star's bf16 mode).
+# FOCAL_B200_PRECISION overrides "auto".
+AUTO_FP32_MAX_ROWS = 2048
 
 
 def resolve_precision(hp: "FocalHyper", B: int, D: int) -> int:
@@ -55,12 +56,12 @@ def resolve_precision(hp: "FocalHyper", B: int, D: int) -> int:
     if want == "auto":
         want = os.environ.get("FOCAL_B200_PRECISION", "auto").lower()
     if want in ("fp32", "tf32"):
-        return _cabi.FOCAL_PREC_TF32
+        return _cabi.FOCAL_PREC_FP32
     if want == "bf16":
         return _cabi.FOCAL_PREC_BF16
     if want != "auto":
-        raise ValueError(f"unknown precision {want!r} (bf16 | tf32 | auto)")
-    return _cabi.FOCAL_PREC_TF32 if B <= AUTO_TF32_MAX_ROWS else _cabi.FOCAL_PREC_BF16
+        raise ValueError(f"unknown precision {want!r} (bf16 | fp32 | auto)")
+    return _cabi.FOCAL_PREC_FP32 if (B <= AUTO_FP32_MAX_ROWS and D <= 256) else _cabi.FOCAL_PREC_BF16
 
 
 def shard_sequences(b: int, world: int, rank: int) -> Tuple[int, int]:

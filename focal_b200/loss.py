@@ -8,9 +8,10 @@ C ABI of ``libfocal_b200.so``; the gradients w.r.t. every feature tensor are pro
 as the loss and handed to autograd by a ``torch.autograd.Function``.
 
 Build-side options (never required): ``args.focal_process_group`` -- a ``torch.distributed`` process group over
-which the batch is row-sharded (each rank passes its own rows); ``args.focal_precision`` -- ``"tf32"`` (north_star's
-fp32 mode: TF32 tiles, gradients within 2e-3 of the fp32 reference), ``"bf16"`` (bf16 tiles, 1e-2) or ``"auto"``
-(default: TF32 for batches up to ``engine.AUTO_TF32_MAX_ROWS`` rows, bf16 above; env ``FOCAL_B200_PRECISION``).
+which the batch is row-sharded (each rank passes its own rows); ``args.focal_precision`` -- ``"fp32"`` (north_star's
+fp32 mode: split-bf16 tiles with 16 significant bits, gradients within 2e-3 of the fp32 reference; ``"tf32"`` is accepted
+as an alias), ``"bf16"`` (bf16 tiles, 1e-2) or ``"auto"`` (default: fp32 mode for batches up to
+``engine.AUTO_FP32_MAX_ROWS`` rows, bf16 above; env ``FOCAL_B200_PRECISION``).
 
 Limits the reference does not have (they raise ``ValueError`` / ``TypeError`` before any launch): see INTEGRATION.md.
 Features that are not fp32 (autocast) are upcast, and their gradients cast back by autograd.

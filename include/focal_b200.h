@@ -33,10 +33,14 @@ enum {
 
 /* terms bit mask: which parts of loss.py:139-218 to evaluate */
 enum { FOCAL_TERM_NCE = 1, FOCAL_TERM_ORTH = 2, FOCAL_TERM_TEMPORAL = 4, FOCAL_TERM_ALL = 7 };
-/* precision of the Gram tiles (everything outside the tiles is fp32, accumulation is fp32):
- *   FOCAL_PREC_BF16  bf16 operands, tcgen05 kind::f16  ("bf16 mode": gradients within 1e-2 of the fp32 reference)
- *   FOCAL_PREC_TF32  tf32 operands, tcgen05 kind::tf32 ("fp32 mode": gradients within 2e-3); D <= 256 */
-enum { FOCAL_PREC_BF16 = 0, FOCAL_PREC_TF32 = 1 };
+/* precision of the Gram tiles (everything outside the tiles is fp32; accumulation is always fp32):
+ *   FOCAL_PREC_BF16  bf16 operands, one tcgen05 kind::f16 pass: north_star's "bf16 mode" (gradients within 1e-2)
+ *   FOCAL_PREC_FP32  north_star's "fp32 mode" (gradients within 2e-3): every operand element travels as a bf16 hi / lo
+ *                    pair (16 significant bits) and every product is three kind::f16 passes hi*hi + hi*lo + lo*hi.
+ *                    kind::tf32 cannot serve here: the B tile is the K-major operand of the Gram and the MN-major
+ *                    operand of the gradient GEMM, and no shared-memory layout is legal for both views of 32-bit
+ *                    elements (profiles/r2_tf32_probe.txt).  D <= 256. */
+enum { FOCAL_PREC_BF16 = 0, FOCAL_PREC_FP32 = 1 };
 
 /*
  * The values FOCALLoss reads from `args` (loss.py:11-23, 149, 163, 211-215) plus build-side options.
