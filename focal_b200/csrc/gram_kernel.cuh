@@ -469,6 +469,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const int row = row0 + trow;                    // row within side (NCE: sequence index k) / tensor (TMP: i)
       const bool row_ok = row < ncol_valid && row >= x.row_lo && row < x.row_hi;
       float rowacc = 0.f;                             // NCE_FWD: row sum; TMP: rho_i
+      float posg = 0.f;                               // NCE_FWD: G_{k,p(k)} as this row's tile computed it
+      bool pos_seen = false;
       float ck = 0.f, n_i = 0.f, mim = -1e30f, hinge_acc = 0.f;
       int cnt_i = 0;
       if (MODE == NCE_BWD && row_ok) ck = (side ? x.cv0_1 : x.cv0_0)[row];
@@ -491,6 +493,10 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         // same sequence index), whose contribution the finalize kernel adds in fp32
         const bool overlap = col0 < row0 + kTileM && col0 + BN > row0;
         const bool diag = kIsNce ? (overlap && (MODE == NCE_BWD || cs == side)) : overlap;
+        // the positive p(k): other side, same sequence index.  The row-sum pass hands the logit it saw to nce_lse /
+        // finalize, so that ln(sum_j e^{s_kj}) - s_{k,p(k)} cancels to the last bit where the positive dominates the row
+        // (tensor-core accumulation is not round-to-nearest: a separately computed fp32 dot product differs by ~1e-5)
+        const bool ptile = (MODE == NCE_FWD) && overlap && cs != side;
 #pragma unroll 1
         for (int ch = sub; ch < BN / CW; ch += NW) {
           float v[CW];
@@ -498,6 +504,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           tmem_ld_wait();
           const int cbase = col0 + ch * CW;           // column (within side) of v[0]
           if (kIsNce) {
+            if (ptile) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j)
+                if (cbase + j == row) { posg = v[j]; pos_seen = true; }
+            }
             // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
 #pragma unroll
             for (int j = 0; j < CW; ++j)
@@ -595,6 +606,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       }
       nb += ntiles;
 
+      if (MODE == NCE_FWD && pos_seen && row_ok)      // exactly one thread of one piece sees the positive of a row
+        reinterpret_cast<float*>(ws + p.pos_off)[(((uint64_t)x.q * p.S + x.s) * 2 + side) * p.bpad + row] = posg;
       // ---------------- item epilogue: fold the per-row partials of warpgroups 1.. into warpgroup 0
       if (MODE != NCE_BWD) {
         if (wgi > 0) {

@@ -86,10 +86,11 @@ struct Plan {
   uint64_t rpart_off;   // fp32 [nsplit_fwd][nProb][S][2][bpad]
   uint64_t rsum_off;    // fp32 [nProb][S][2][bpad]
   uint64_t rinv_off;    // fp32 [nProb][S][2][bpad]
+  uint64_t pos_off;     // fp32 [nProb][S][2][bpad] positive-pair logit G_{k,p(k)} (log2 domain) as the row-sum tile saw it
   uint64_t dx_off;      // fp32 [2M][Bpad][kbFull*epb]
   uint64_t rho_off;     // fp32 [2M][Bpad] sum_j r_ij
   uint64_t cnt_off;     // int32 [2M][bpad]  active hinges per sequence
-  uint64_t part1_off;   // fp32 [nblk1][4]  prologue partials: orth, pos_shared, pos_private
+  uint64_t part1_off;   // fp32 [nblk1][4]  prologue partials: orth
   uint64_t part2_off;   // fp32 [nblk2][2]  log-row-sum partials: shared, private
   uint64_t part3_off;   // fp32 [nitems3]   hinge partials
   uint64_t lossd_off;   // double [8]
@@ -340,6 +341,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.rpart_off = take(rs * p.nsplit_fwd);
   p.rsum_off = take(rs);
   p.rinv_off = take(rs);
+  p.pos_off = take(rs);
   p.dz_off = off;
   for (int q = 0; q < p.nProb; ++q)
     p.probs[q].dz_off = take((uint64_t)2 * rowsNce * p.ops[p.probs[q].opA].kb * p.epb * 4);

@@ -215,25 +215,6 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
     }
     // ---- loss terms of the owned rows
     if (I >= p.seq0 && I < p.seq1) {
-      if (p.terms & FOCAL_TERM_NCE) {
-        // s_{k,p(k)} is taken from the same bf16-rounded, pre-scaled operands the Gram tiles use, so that
-        // ln(sum_j exp s_kj) - s_{k,p(k)} cancels exactly where the positive dominates the row (small T)
-        const float sc = -2.f * 0.6931471805599453f / ((float)p.S * (float)(2 * p.b));   // -2 ln2 G~ / (S N)
-        for (int q = 0; q < p.nProb; ++q) {
-          const OpDesc& a = p.ops[p.probs[q].opA];
-          const OpDesc& b = p.ops[p.probs[q].opB];
-          const float sa = (a.width == D) ? sfull[a.tensor] : (a.col0 == 0 ? ssh[a.tensor] : spr[a.tensor]);
-          const float sb = (b.width == D) ? sfull[b.tensor] : (b.col0 == 0 ? ssh[b.tensor] : spr[b.tensor]);
-          const float fa = p.alpha / fmaxf(sqrtf(sa), kNceEps), fb2 = p.alpha / fmaxf(sqrtf(sb), kNceEps);
-          const float* xa = xs + a.tensor * D + a.col0;
-          const float* xb = xs + b.tensor * D + b.col0;
-          float dot = 0.f;
-          for (int c = lane; c < a.width; c += 32)
-            dot += tile_product(p.prec, xa[c] * fa, xb[c] * fb2);
-          dot = warp_sum(dot);
-          if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
-        }
-      }
       if (p.terms & FOCAL_TERM_ORTH) {
         for (int k = 0; k < p.nOrth; ++k) {
           const OrthDesc& od = p.orth[k];
@@ -316,7 +297,9 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
         reinterpret_cast<float*>(pw.ws[rk] + p.rsum_off)[e] = r;
         reinterpret_cast<float*>(pw.ws[rk] + p.rinv_off)[e] = 1.f / r;
       }
-      const float lg = logf(r) / ((float)p.S * (float)(2 * p.b));          // ln sum_{j != k} exp(s_kj) / (S N)
+      // row loss ln sum_{j != k} exp(s_kj) - s_{k,p(k)}, both from the tiles of THIS row (log2-domain logit G: s = ln2 G)
+      const float g_pos = reinterpret_cast<const float*>(ws + p.pos_off)[e];
+      const float lg = (logf(r) - 0.6931471805599453f * g_pos) / ((float)p.S * (float)(2 * p.b));
       if (p.probs[q].kind == 0) ls = lg; else lp = lg;
     }
   }
@@ -440,11 +423,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
         const float wq = pr.weight * inv_tsn;
         // The positive column p(k) is masked out of the tiles and handled here in fp32: where the positive
         // dominates the row (small T, aligned views) W_kp - 2 is a tiny difference that bf16 W would destroy.
-        const float fk = p.alpha / nrm;
-        float gpos = 0.f;
-        for (int c = lane; c < w; c += 32)
-          gpos += tile_product(p.prec, x[c] * fk, px[c] * pinv);
-        gpos = warp_sum(gpos);
+        const float gpos = reinterpret_cast<const float*>(ws + p.pos_off)[((uint64_t)(q * S + s) * 2 + side) * p.bpad + I];
         const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
         const float wkp = exp2f(gpos) * (1.f / rs[(uint64_t)side * p.bpad + I] + 1.f / rs[(uint64_t)(1 - side) * p.bpad + I]);
         for (int c = lane; c < w; c += 32) {

@@ -166,24 +166,6 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
     }
     __syncwarp();
     if (I >= p.seq0 && I < p.seq1) {
-      if (p.terms & FOCAL_TERM_NCE) {
-        const float sc = -2.f * 0.6931471805599453f / ((float)p.S * (float)(2 * p.b));   // -2 ln2 G~ / (S N)
-        for (int q = 0; q < p.nProb; ++q) {
-          const OpDesc& a = p.ops[p.probs[q].opA];
-          const OpDesc& b = p.ops[p.probs[q].opB];
-          const int ha = a.col0 ? 1 : 0, hb = b.col0 ? 1 : 0;
-          const float fa = p.alpha * fminf(rsqrtf(nrm[2 * a.tensor + ha]), 1.f / kNceEps);
-          const float fb2 = p.alpha * fminf(rsqrtf(nrm[2 * b.tensor + hb]), 1.f / kNceEps);
-          float xa[VW], xb[VW];
-          ld_frag<VW>(xs + a.tensor * D + a.col0 + c0, xa);
-          ld_frag<VW>(xs + b.tensor * D + b.col0 + c0, xb);
-          float dot = 0.f;
-#pragma unroll
-          for (int e = 0; e < VW; ++e) dot += tile_product(PREC, xa[e] * fa, xb[e] * fb2);
-          dot = warp_sum(dot);
-          if (p.probs[q].kind == 0) acc_ps += sc * dot; else acc_pp += sc * dot;
-        }
-      }
       if (p.terms & FOCAL_TERM_ORTH) {
         for (int k = 0; k < p.nOrth; ++k) {
           const OrthDesc& od = p.orth[k];
@@ -392,13 +374,9 @@ finalize_rt_kernel(const __grid_constant__ Plan p,
         const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(q * S + s) * 2) * p.bpad;
         const float r_k = __ldg(rs + (uint64_t)side * p.bpad + I), r_p = __ldg(rs + (uint64_t)(1 - side) * p.bpad + I);
         // positive column in fp32 (masked out of the tiles): W_kp - 2 is a tiny difference when the positive dominates
-        float gpos = 0.f;
+        const float gpos = __ldg(reinterpret_cast<const float*>(ws + p.pos_off) + ((uint64_t)(q * S + s) * 2 + side) * p.bpad + I);
 #pragma unroll
-        for (int e = 0; e < VW; ++e) {
-          gpos += tile_product(PREC, x[e] * fk, px[e] * fp);
-          px[e] = op_round_t<PREC>(px[e] * fp);
-        }
-        gpos = warp_sum(gpos);
+        for (int e = 0; e < VW; ++e) px[e] = op_round_t<PREC>(px[e] * fp);
         const float wkp = ex2_approx(gpos) * (__frcp_rn(r_k) + __frcp_rn(r_p));
         const float wq = prb.weight * inv_tsn * inv_alpha;
 #pragma unroll

@@ -64,6 +64,10 @@ def resolve_precision(hp: "FocalHyper", B: int, D: int) -> int:
     return _cabi.FOCAL_PREC_FP32 if (B <= AUTO_FP32_MAX_ROWS and D <= 256) else _cabi.FOCAL_PREC_BF16
 
 
+# calls served by this process, by kind (tests use it to prove that third-party code really went through the CUDA path)
+CALLS = {"grad": 0, "nograd": 0}
+
+
 def shard_sequences(b: int, world: int, rank: int) -> Tuple[int, int]:
     """Sequences owned by ``rank`` when b sequences are split rank-major into equal blocks."""
     if b % world:
@@ -364,6 +368,7 @@ class FocalEngine:
         grads = 2M tensors shaped like the (local) inputs, or None.  Both are fresh tensors owned by the caller."""
         local = self._check(f1, f2)
         dev = local[0].device
+        CALLS["grad" if need_grad else "nograd"] += 1
         if not local[0].is_cuda:
             return self._run(local, need_grad)
         with torch.cuda.device(dev):       # kernels, attributes and SM queries act on the CURRENT device
