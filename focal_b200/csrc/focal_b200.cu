@@ -1,5 +1,6 @@
 // C ABI of the B200-native FOCAL loss hot path (see include/focal_b200.h).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -10,6 +11,7 @@
 #include "plan.h"
 #include "row_kernels.cuh"
 #include "row_kernels_fast.cuh"
+#include "row_kernels_v2.cuh"
 
 using namespace fb;
 
@@ -248,6 +250,49 @@ int launch_finalize_fast(int vw, const Plan& p, const FeatPtrs& f, const GradPtr
                                    : launch_finalize_fast_p<FOCAL_PREC_BF16>(vw, p, f, g, w, grid, st);
 }
 
+// ---- second-generation row kernels (one warp per (row, tensor)): D <= 256 on the vectorised path
+bool use_row_v2(int vw) {
+  static const int forced_v1 = [] {
+    const char* e = std::getenv("FOCAL_B200_ROW_KERNELS");      // "v1": the first-generation kernels (A/B measurements)
+    return (e && std::strcmp(e, "v1") == 0) ? 1 : 0;
+  }();
+  return !forced_v1 && vw >= 1 && vw <= 4;
+}
+template <int VW, int PREC>
+int launch_prologue_v2_vw(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, int grid, int fuse, cudaStream_t st) {
+  const size_t smem = row_v2_smem_bytes(p.nT, p.D);
+  if (int rc = ensure_dyn_smem(prologue_v2_kernel<VW, PREC>, smem, "cudaFuncSetAttribute(prologue_v2_kernel)")) return rc;
+  prologue_v2_kernel<VW, PREC><<<grid, 128 * p.nT, smem, st>>>(p, f, pw, w, fuse);
+  return cuda_ok("prologue_v2_kernel");
+}
+template <int VW, int PREC>
+int launch_finalize_v2_vw(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid, cudaStream_t st) {
+  const size_t smem = row_v2_smem_bytes(p.nT, p.D);
+  if (int rc = ensure_dyn_smem(finalize_v2_kernel<VW, PREC>, smem, "cudaFuncSetAttribute(finalize_v2_kernel)")) return rc;
+  finalize_v2_kernel<VW, PREC><<<grid, 128 * p.nT, smem, st>>>(p, f, g, w);
+  return cuda_ok("finalize_v2_kernel");
+}
+#define FB_V2_DISPATCH(FN, ...)                                                                    \
+  do {                                                                                             \
+    const bool fp32 = p.prec == FOCAL_PREC_FP32;                                                   \
+    switch (vw) {                                                                                  \
+      case 1: return fp32 ? FN<1, FOCAL_PREC_FP32>(__VA_ARGS__) : FN<1, FOCAL_PREC_BF16>(__VA_ARGS__); \
+      case 2: return fp32 ? FN<2, FOCAL_PREC_FP32>(__VA_ARGS__) : FN<2, FOCAL_PREC_BF16>(__VA_ARGS__); \
+      case 3: return fp32 ? FN<3, FOCAL_PREC_FP32>(__VA_ARGS__) : FN<3, FOCAL_PREC_BF16>(__VA_ARGS__); \
+      case 4: return fp32 ? FN<4, FOCAL_PREC_FP32>(__VA_ARGS__) : FN<4, FOCAL_PREC_BF16>(__VA_ARGS__); \
+    }                                                                                              \
+    return FOCAL_ESHAPE;                                                                           \
+  } while (0)
+int launch_prologue_v2(int vw, const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, int grid, int fuse,
+                       cudaStream_t st) {
+  FB_V2_DISPATCH(launch_prologue_v2_vw, p, f, pw, w, grid, fuse, st);
+}
+int launch_finalize_v2(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, int grid,
+                       cudaStream_t st) {
+  FB_V2_DISPATCH(launch_finalize_v2_vw, p, f, g, w, grid, st);
+}
+#undef FB_V2_DISPATCH
+
 // local_rows: the caller's tensors start at the first owned row; the kernels index rows globally, so hand them the
 // (virtual) address of row 0 -- only owned rows are ever dereferenced.
 int fill_feats(const Plan& p, const float* const* feats, FeatPtrs& f) {
@@ -297,7 +342,10 @@ int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& 
   if (vw) {
     fused_intra = (p.S == 2 || p.S == 4);
     const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT + 4 * kMaxT) * sizeof(float);
-    if ((rc = launch_prologue_fast(vw, p, f, pw, w, smem, p.nblk1, fused_intra ? 1 : 0, st))) return rc;
+    // finalize_v2 reads the squared norms prologue_v2 stores, so the two generations are only used as a pair
+    if (use_row_v2(vw)) rc = launch_prologue_v2(vw, p, f, pw, w, p.nblk1, fused_intra ? 1 : 0, st);
+    else rc = launch_prologue_fast(vw, p, f, pw, w, smem, p.nblk1, fused_intra ? 1 : 0, st);
+    if (rc) return rc;
   } else {
     if (pw.world > 1 || p.local_rows) return FOCAL_ESHAPE;      // the generic row kernels have no peer path
     const size_t smem = (size_t)kRowsPerBlock * p.nT * p.D * sizeof(float);
@@ -325,7 +373,9 @@ int do_finalize(const Plan& p, int no_private, const float* const* feats, float*
     const int rows = (p.seq1 - p.seq0) * p.S;
     const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, no_private) : 0;
     if (vw) {
-      if ((rc = launch_finalize_fast(vw, p, f, g, w, (rows + 3) / 4, st))) return rc;
+      if (use_row_v2(vw)) rc = launch_finalize_v2(vw, p, f, g, w, (rows + 3) / 4, st);
+      else rc = launch_finalize_fast(vw, p, f, g, w, (rows + 3) / 4, st);
+      if (rc) return rc;
     } else {
       const size_t smem = (size_t)kRowsPerBlock * (2 * p.nT + 1) * p.D * sizeof(float);
       if ((rc = ensure_dyn_smem(finalize_kernel, smem, "cudaFuncSetAttribute(finalize_kernel)"))) return rc;
@@ -589,3 +639,18 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
 }
 
 }  // extern "C"
+
+#ifdef FB_TRACE
+// experiment builds only: copy the pipeline trace of the last Gram launch to the host (tools/trace_gram.py)
+extern "C" int focal_b200_debug_trace(long long* host_dst, size_t n) {
+  const size_t have = sizeof(fb::fb_trace_buf) / sizeof(long long);
+  if (!host_dst || n > have) return FOCAL_EINVAL;
+  if (cudaDeviceSynchronize() != cudaSuccess) return FOCAL_ECUDA;
+  return cudaMemcpyFromSymbol(host_dst, fb::fb_trace_buf, n * sizeof(long long)) == cudaSuccess ? FOCAL_OK : FOCAL_ECUDA;
+}
+extern "C" int focal_b200_debug_trace_clear(void) {
+  void* ptr = nullptr;
+  if (cudaGetSymbolAddress(&ptr, fb::fb_trace_buf) != cudaSuccess) return FOCAL_ECUDA;
+  return cudaMemset(ptr, 0, sizeof(fb::fb_trace_buf)) == cudaSuccess ? FOCAL_OK : FOCAL_ECUDA;
+}
+#endif

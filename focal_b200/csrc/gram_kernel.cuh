@@ -66,6 +66,20 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #endif
 constexpr int kTmemCols = 512;
 
+// Experiment builds only (tools/trace_gram.py, -DFB_TRACE=1): per-CTA clock64 stamps of the pipeline events of the first
+// kTraceTiles column tiles: role 0 = TMA producer, 1 = UMMA issuer, 2 + g = epilogue warpgroup g.
+#ifdef FB_TRACE
+constexpr int kTraceTiles = 96, kTraceRoles = 6, kTraceTags = 4, kTraceBlocks = 160;
+__device__ long long fb_trace_buf[kTraceBlocks * kTraceRoles * kTraceTiles * kTraceTags];
+#define FB_TRACE_EV(role, n, tag)                                                                                     \
+  do {                                                                                                                \
+    if ((threadIdx.x & 31) == 0 && (n) < (uint32_t)kTraceTiles && blockIdx.x < kTraceBlocks)                          \
+      fb_trace_buf[(((size_t)blockIdx.x * kTraceRoles + (role)) * kTraceTiles + (n)) * kTraceTags + (tag)] = clock64(); \
+  } while (0)
+#else
+#define FB_TRACE_EV(role, n, tag) do {} while (0)
+#endif
+
 // Tile configuration as a function of the mode and the operand width in 64-element K blocks (see header comment).
 // EL: tile precision.  0 = bf16 tiles (north_star's bf16 mode).  1 = split-bf16 tiles (the fp32 mode): every operand
 // element x travels as hi = bf16(x) and lo = bf16(x - hi) -- 16 significant bits -- in two images (K blocks [0, KB/2) =
@@ -312,6 +326,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           const int cs = ct >= x.ntc ? 1 : 0, tc = ct - cs * x.ntc;
           const uint8_t* src = (cs ? x.b_src1 : x.b_src0) + (uint64_t)tc * BN * 128;
           mbar_wait_warp(&bars->b_empty[st], ((nb / NB) & 1) ^ 1);
+          FB_TRACE_EV(0, nb, 0);
           if (elect_one()) {
             uint8_t* dst = smem + L::kBOff + st * L::kBStage;
             constexpr uint32_t bytes = L::kBTile + (kColVec ? (kIsNce ? 1 : 2) * BN * 4 : 0);
@@ -366,12 +381,14 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             mbar_wait_warp(&bars->b_full[st], (n / NB) & 1);
             mbar_wait_warp(&bars->s_empty[ss], ((n / NS) & 1) ^ 1);
             tc_fence_after();
+            FB_TRACE_EV(1, n, 0);
             if (elect_one()) {
               issue_gram(tmem + kSCol + ss * BN, db0 + (uint64_t)(st * (L::kBStage >> 4)));
               umma_commit(&bars->s_full[ss]);
               umma_commit(&bars->b_empty[st]);
             }
             __syncwarp();
+            FB_TRACE_EV(1, n, 1);
           }
         } else {
           // Out-of-order issue: UMMA #2 of the oldest tile whose W is ready, else UMMA #1 of the next tile whose B
@@ -386,6 +403,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               const bool ready = mbar_try_wait_warp(&bars->w_full[ss], (n / NS) & 1);
               if (ready) {
                 tc_fence_after();
+                FB_TRACE_EV(1, n, 2);
                 if (elect_one()) {
                   // MN-major view of the B tile; wide mode: the K blocks of this item's output half
                   const uint64_t dm = dm0 + (uint64_t)(st * (L::kBStage >> 4)) +
@@ -411,6 +429,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                   umma_commit(&bars->b_empty[st]);
                 }
                 __syncwarp();
+                FB_TRACE_EV(1, n, 3);
                 ++t2;
                 did = true;
               }
@@ -420,11 +439,13 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               const bool ready = mbar_try_wait_warp(&bars->b_full[st], (n / NB) & 1);
               if (ready) {
                 tc_fence_after();
+                FB_TRACE_EV(1, n, 0);
                 if (elect_one()) {
                   issue_gram(tmem + kSCol + ss * BN, db0 + (uint64_t)(st * (L::kBStage >> 4)));
                   umma_commit(&bars->s_full[ss]);
                 }
                 __syncwarp();
+                FB_TRACE_EV(1, n, 1);
                 ++t1;
                 did = true;
               }
@@ -485,9 +506,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         const int cs = ct >= ntc ? 1 : 0, tc = ct - cs * ntc;
         const int col0 = tc * BN;                     // first column (within side) of this tile
         const uint32_t cv = cv_base + st * L::kBStage;
+        FB_TRACE_EV(2 + wgi, n, 0);
         if (kColVec) mbar_wait(&bars->b_full[st], (n / NB) & 1);
         mbar_wait(&bars->s_full[wg], sphase);
         tc_fence_after();
+        FB_TRACE_EV(2 + wgi, n, 1);
         const bool tail = col0 + BN > ncol_valid;
         // columns to drop: j == k (same side) always; in the backward pass also the positive p(k) (other side,
         // same sequence index), whose contribution the finalize kernel adds in fp32
@@ -591,6 +614,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             }
           }
         }
+        FB_TRACE_EV(2 + wgi, n, 2);
         if (kBwd) {
           tmem_st_wait();
           tc_fence_before();

@@ -83,6 +83,7 @@ struct Plan {
   uint64_t xt_off;      // bf16 [2M][kbFull][Bpad][64] temporal operands (natural row order, swizzled)
   uint64_t sq_off;      // fp32 [2M][Bpad] squared norms of the rounded temporal operands
   uint64_t mintra_off;  // fp32 [2M][Bpad] m_II of the row's sequence (exact fp32)
+  uint64_t nrm_off;     // fp32 [2M][Bpad][2] squared norms of the shared / private half (prologue_v2 -> finalize_v2)
   uint64_t rpart_off;   // fp32 [nsplit_fwd][nProb][S][2][bpad]
   uint64_t rsum_off;    // fp32 [nProb][S][2][bpad]
   uint64_t rinv_off;    // fp32 [nProb][S][2][bpad]
@@ -337,6 +338,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.xt_off = take((uint64_t)p.nT * p.kbFull * p.Bpad * 128);
   p.sq_off = take((uint64_t)p.nT * p.Bpad * 4);
   p.mintra_off = take((uint64_t)p.nT * p.Bpad * 4);
+  p.nrm_off = take((uint64_t)p.nT * p.Bpad * 8);
   const uint64_t rs = (uint64_t)p.nProb * p.S * 2 * p.bpad * 4;
   p.rpart_off = take(rs * p.nsplit_fwd);
   p.rsum_off = take(rs);
