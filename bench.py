@@ -633,7 +633,8 @@ def make_args(mods, S, w, group, precision="auto"):
 
 
 def stage_breakdown(engine, dev_sets, mods, M, steps, world, group):
-    """Mean device time of each C-ABI stage over `steps` steps (events on the launching stream)."""
+    """Mean device time of each C-ABI stage over `steps` steps (events on the launching stream, launches pre-queued
+    behind a spin kernel so that host launch latency is not part of the figures)."""
     import ctypes as C
 
     import torch
@@ -656,6 +657,9 @@ def stage_breakdown(engine, dev_sets, mods, M, steps, world, group):
         grads = [torch.empty_like(t) for t in feats]
         gptr = _cabi.ptr_array([g.data_ptr() for g in grads])
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        # keep the GPU busy (~0.5 ms) while the host enqueues the whole sequence: the stages then run back to back and
+        # the events measure kernels, not the host's launch latency (which exceeds the short row kernels)
+        torch.cuda._sleep(1_000_000)
         evs[0].record()
         _cabi.check(lib.focal_b200_prologue(ref, fptr, wsp, wsn, stream), "prologue"); evs[1].record()
         _cabi.check(lib.focal_b200_nce_rowsum(ref, wsp, wsn, stream), "nce_rowsum"); evs[2].record()

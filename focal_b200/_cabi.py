@@ -12,8 +12,8 @@ LIB_PATH = os.path.join(_PKG, "libfocal_b200.so")
 
 FOCAL_TERM_NCE, FOCAL_TERM_ORTH, FOCAL_TERM_TEMPORAL, FOCAL_TERM_ALL = 1, 2, 4, 7
 FOCAL_PREC_BF16, FOCAL_PREC_FP32 = 0, 1
-FOCAL_MAX_MODALITIES = 4
-ABI_VERSION = 3
+FOCAL_MAX_MODALITIES = 8
+ABI_VERSION = 4
 FOCAL_OK, FOCAL_EINVAL, FOCAL_ESHAPE, FOCAL_ECUDA, FOCAL_EWORKSPACE = 0, -1, -2, -3, -4
 
 EXPORTS = (

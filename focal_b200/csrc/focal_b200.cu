@@ -147,7 +147,7 @@ template <int MODE>
 int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid, int peer_wait = 0) {
   ProbSel sel{};
   sel.peer_wait = peer_wait;
-  switch (p.S) {
+  switch (p.Sp) {                     // lanes per (padded) sequence; p.S itself may be any length up to 32
     case 4: return launch_gram_prec<MODE, 4>(p, sel, ws, st, p.kbFull, grid);
 #ifndef FB_FAST_BUILD                 // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
     case 2: return launch_gram_prec<MODE, 2>(p, sel, ws, st, p.kbFull, grid);
@@ -177,7 +177,7 @@ int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st, int peer_wait = 0) {
 
 // lanes own VW = d/32 consecutive columns per half on the vectorised row-kernel path (0 = use the generic kernels)
 int fast_row_vw(const Plan& p, int no_private) {
-  if (no_private || (p.D & 1) || p.d % 32 || p.d < 32) return 0;
+  if (no_private || (p.D & 1) || p.d % 32 || p.d < 32 || p.Sp != p.S) return 0;
   const int vw = p.d / 32;
   return (vw <= 4 || vw == 8) ? vw : 0;           // D = 64, 128, 192, 256, 512
 }
@@ -333,7 +333,7 @@ PeerWs solo(void* ws) {
 int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st,
                 bool zero_pads = true) {
   int rc;
-  if (zero_pads && (p.bpad != p.b || p.Bpad != p.B)) {
+  if (zero_pads && (p.bpad != p.b || p.Bpad != p.Bt || p.Sp != p.S)) {
     zero_pad_kernel<<<64, 256, 0, st>>>(p, w);
     if ((rc = cuda_ok("zero_pad_kernel"))) return rc;
   }
@@ -343,7 +343,7 @@ int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& 
     fused_intra = (p.S == 2 || p.S == 4);
     const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT + 4 * kMaxT) * sizeof(float);
     // finalize_v2 reads the squared norms prologue_v2 stores, so the two generations are only used as a pair
-    if (use_row_v2(vw)) rc = launch_prologue_v2(vw, p, f, pw, w, p.nblk1, fused_intra ? 1 : 0, st);
+    if (use_row_v2(vw) && p.nT <= 8) rc = launch_prologue_v2(vw, p, f, pw, w, p.nblk1, fused_intra ? 1 : 0, st);
     else rc = launch_prologue_fast(vw, p, f, pw, w, smem, p.nblk1, fused_intra ? 1 : 0, st);
     if (rc) return rc;
   } else {
@@ -373,7 +373,7 @@ int do_finalize(const Plan& p, int no_private, const float* const* feats, float*
     const int rows = (p.seq1 - p.seq0) * p.S;
     const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, no_private) : 0;
     if (vw) {
-      if (use_row_v2(vw)) rc = launch_finalize_v2(vw, p, f, g, w, (rows + 3) / 4, st);
+      if (use_row_v2(vw) && p.nT <= 8) rc = launch_finalize_v2(vw, p, f, g, w, (rows + 3) / 4, st);
       else rc = launch_finalize_fast(vw, p, f, g, w, (rows + 3) / 4, st);
       if (rc) return rc;
     } else {
@@ -398,7 +398,7 @@ const char* focal_b200_strerror(int code) {
     case FOCAL_OK: return "ok";
     case FOCAL_EINVAL: return "invalid argument";
     case FOCAL_ESHAPE:
-      return "unsupported shape: need B % S == 0, S a power of two <= 32, 2 <= D <= 512, 1 <= M <= 4, "
+      return "unsupported shape: need B % S == 0, S <= 32, 2 <= D <= 512 (fp32 mode: <= 256), 1 <= M <= 8, "
              "temperature >= 0.016";
     case FOCAL_ECUDA: return "CUDA error (see stderr)";
     case FOCAL_EWORKSPACE: return "workspace too small or not 1024-byte aligned";

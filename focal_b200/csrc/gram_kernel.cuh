@@ -51,6 +51,12 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_KB4_NW
 #define FB_KB4_NW 2             // epilogue warpgroups sharing one S stage (they split its 16-column chunks)
 #endif
+#ifndef FB_KB4_SHARE
+#define FB_KB4_SHARE 1          // 256-column operands: 1 = ALL epilogue warpgroups work on every tile (see GramCfg::kShareAll)
+#endif
+#ifndef FB_EPI_UNROLL
+#define FB_EPI_UNROLL 1         // chunks of one thread's share of a tile that are in flight together (shared-stage configs)
+#endif
 #ifndef FB_POLY_PER8
 #define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
 #endif
@@ -98,8 +104,13 @@ struct GramCfg {
   static constexpr int BN = tile_bn(KB);                                         // column tile
   static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : (KB == 8 ? FB_KB8_NS : 4));  // S stages
   static constexpr int NB = KB <= 3 ? 5 : (KB == 4 ? FB_KB4_NB : 1);             // B-tile ring stages (smem budget)
-  static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? FB_KB4_NW : (KB == 8 ? FB_KB8_NW : 1));   // warpgroups per S stage
-  static constexpr int NG = NS * NW;                                             // epilogue warpgroups in total
+  // kShareAll (256-column operands, two S stages): the pipeline trace (tools/trace_gram.py, profiles/r2_trace_temporal.txt)
+  // showed the two stages' epilogues running one after the other, never together (each stage's chain UMMA #1 -> epilogue
+  // -> UMMA #2 -> UMMA #1 is serial and the stages interleave), so warpgroups bound to a stage idle half of the time.
+  // With kShareAll every warpgroup takes a share of EVERY tile: half the epilogue latency per tile, same issue work.
+  static constexpr bool kShareAll = (KB == 4 && SEQ <= 16 && FB_KB4_SHARE != 0);
+  static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? (kShareAll ? 4 : FB_KB4_NW) : (KB == 8 ? FB_KB8_NW : 1));   // warpgroups per tile
+  static constexpr int NG = kShareAll ? NW : NS * NW;                            // epilogue warpgroups in total
   static constexpr int CW = (NG == 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
   static constexpr int kThreads = 64 + 128 * NG;
   static_assert(NG <= 4, "partial-sum arrays and register budget are sized for <= 4 epilogue warpgroups");
@@ -163,7 +174,7 @@ __device__ __forceinline__ int gram_num_items(const Plan& p, const ProbSel& sel)
     const int t0 = p.seq0 / kTileM, t1 = (p.seq1 + kTileM - 1) / kTileM;
     return sel.n * p.S * 2 * (t1 - t0);
   } else {
-    const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM;
+    const int t0 = (p.seq0 * p.Sp) / kTileM, t1 = (p.seq1 * p.Sp + kTileM - 1) / kTileM;
     return p.nT * (t1 - t0) * ((MODE == TMP_BWD && p.wide) ? 2 : 1);           // wide mode: one item per output half
   }
 }
@@ -191,7 +202,7 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
     x.row_lo = p.seq0; x.row_hi = p.seq1;
     x.q = q; x.s = s; x.c = 0;
   } else {
-    const int t0 = (p.seq0 * p.S) / kTileM, t1 = (p.seq1 * p.S + kTileM - 1) / kTileM, nrt = t1 - t0;
+    const int t0 = (p.seq0 * p.Sp) / kTileM, t1 = (p.seq1 * p.Sp + kTileM - 1) / kTileM, nrt = t1 - t0;
     int r = it, half = 0;
     if (MODE == TMP_BWD && p.wide) { half = r & 1; r >>= 1; }
     const int rt = t0 + r % nrt;
@@ -201,10 +212,10 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
     x.a_src = x.b_src0 + (uint64_t)rt * kTileM * 128;
     x.cv0_0 = x.cv0_1 = reinterpret_cast<const float*>(ws + p.sq_off) + (uint64_t)c * p.Bpad;
     x.cv1 = reinterpret_cast<const float*>(ws + p.mintra_off) + (uint64_t)c * p.Bpad;
-    x.ntc = (p.B + BN - 1) / BN;
+    x.ntc = (p.Bt + BN - 1) / BN;                    // rows and columns live in the temporal row space (plan.h: Sp, Bt)
     x.ct_begin = 0; x.ct_end = x.ntc;
-    x.row0 = rt * kTileM; x.side = 0; x.ncol_valid = p.B;
-    x.row_lo = p.seq0 * p.S; x.row_hi = p.seq1 * p.S;
+    x.row0 = rt * kTileM; x.side = 0; x.ncol_valid = p.Bt;
+    x.row_lo = p.seq0 * p.Sp; x.row_hi = p.seq1 * p.Sp;
     x.q = half; x.s = 0; x.c = c;                   // q: which 256-column half of dx this item accumulates (wide mode)
   }
 }
@@ -217,7 +228,7 @@ __device__ __forceinline__ void gram_decode(const Plan& p, const ProbSel& sel, c
 // (dz / dx / rho / cnt / row sums + k * delta) and finalize adds them in piece order, so the result is deterministic.
 template <int MODE, int BN>
 __device__ __forceinline__ int gram_tiles_per_item(const Plan& p) {
-  return (MODE == NCE_FWD || MODE == NCE_BWD) ? 2 * ((p.b + BN - 1) / BN) : (p.B + BN - 1) / BN;
+  return (MODE == NCE_FWD || MODE == NCE_BWD) ? 2 * ((p.b + BN - 1) / BN) : (p.Bt + BN - 1) / BN;
 }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -465,19 +476,22 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     }
   } else {
     // =============================== epilogue warps ===============================
+    constexpr bool kShareAll = G::kShareAll;          // every warpgroup works on every tile (stage = tile index % NS)
     const int wgi = (warp - 2) >> 2;                  // epilogue warpgroup index
-    const int wg = wgi / NW;                          // S stage this warpgroup works on
-    const int sub = wgi % NW;                         // which of the stage's chunks it takes (chunk % NW == sub)
+    const int wg0 = kShareAll ? 0 : wgi / NW;         // S stage this warpgroup is bound to (unless kShareAll)
+    const int sub = kShareAll ? wgi : wgi % NW;       // which of a tile's chunks it takes (chunk % NW == sub)
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int trow = quarter * 32 + lane;             // row within the tile == TMEM lane
     const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
-    constexpr int SQ = SEQ > 0 ? SEQ : 1;
-    const float inv_cnt = 1.f / (float)(SQ * SQ);
-    const float coef1 = -1.f / ((float)p.b * (float)(p.b - 1) * (float)(SQ * SQ));
+    constexpr int SQ = SEQ > 0 ? SEQ : 1;             // lanes / columns per (padded) sequence: plan.h Sp
+    const int Sr = kIsNce ? 1 : p.S;                  // real sequence length; positions >= Sr of a sequence are phantoms
+    const bool padseq = !kIsNce && Sr != SQ;
+    const float inv_cnt = 1.f / (float)(Sr * Sr);
+    const float coef1 = -1.f / ((float)p.b * (float)(p.b - 1) * (float)(Sr * Sr));
     const float coef2 = 2.f * coef1;
     const float margin = p.margin;
     const uint32_t cv_base = smem_u32(smem + L::kBOff + L::kBTile);
-    const uint32_t s_addr = tmem + tlane + kSCol + wg * BN;
+    const uint32_t s_addr0 = tmem + tlane + kSCol;
     uint32_t nb = 0, ni = 0;
     PieceIter pieces((int)blockIdx.x, (int)gridDim.x, n_items, gram_tiles_per_item<MODE, BN>(p),
                        (kIsNce ? p.sk_nce : p.sk_tmp) != 0);
@@ -488,7 +502,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const bool second = pk > 0;                     // secondary piece of a split row block
       const int row0 = x.row0, ncol_valid = x.ncol_valid, side = x.side, ntc = x.ntc, ct_begin = x.ct_begin;
       const int row = row0 + trow;                    // row within side (NCE: sequence index k) / tensor (TMP: i)
-      const bool row_ok = row < ncol_valid && row >= x.row_lo && row < x.row_hi;
+      const bool rowpad = padseq && (row & (SQ - 1)) >= Sr;            // phantom row of a padded sequence
+      const bool row_ok = row < ncol_valid && row >= x.row_lo && row < x.row_hi && !rowpad;
       float rowacc = 0.f;                             // NCE_FWD: row sum; TMP: rho_i
       float posg = 0.f;                               // NCE_FWD: G_{k,p(k)} as this row's tile computed it
       bool pos_seen = false;
@@ -498,10 +513,12 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       if (!kIsNce && row_ok) { n_i = x.cv0_0[row]; mim = x.cv1[row] + margin; }   // m_II + margin
       const int seq_i = row / SQ;
       const int ntiles = x.ct_end - ct_begin;
-      // first tile of this item that belongs to this warpgroup: (nb + t) % NS == wg
-      for (int t = (int)((wg + NS - nb % NS) % NS); t < ntiles; t += NS) {
+      // first tile of this item that belongs to this warpgroup: (nb + t) % NS == wg0; kShareAll: every tile
+      for (int t = kShareAll ? 0 : (int)((wg0 + NS - nb % NS) % NS); t < ntiles; t += (kShareAll ? 1 : NS)) {
         const uint32_t n = nb + t, st = n % NB;
         const uint32_t sphase = (n / NS) & 1;
+        const int wg = kShareAll ? (int)(n % NS) : wg0;     // S stage of this tile
+        const uint32_t s_addr = s_addr0 + wg * BN;
         const int ct = ct_begin + t;
         const int cs = ct >= ntc ? 1 : 0, tc = ct - cs * ntc;
         const int col0 = tc * BN;                     // first column (within side) of this tile
@@ -568,13 +585,26 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
             for (int g0 = 0; g0 < CW; g0 += SQ) {
               float gsum = 0.f;
+              if (!padseq) {
 #pragma unroll
-              for (int j = 0; j < SQ; ++j) {
-                // cdist mm form; the floor keeps 1/delta finite for coincident rows (their r_ij (x_i - x_j) is 0)
-                const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], nj[g0 + j]), 1e-12f);
-                const float rs = rsqrt_approx(d2);                    // 1 / delta
-                v[g0 + j] = rs;
-                gsum = fmaf(d2, rs, gsum);                            // delta = d2 / delta
+                for (int j = 0; j < SQ; ++j) {
+                  // cdist mm form; the floor keeps 1/delta finite for coincident rows (their r_ij (x_i - x_j) is 0)
+                  const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], nj[g0 + j]), 1e-12f);
+                  const float rs = rsqrt_approx(d2);                    // 1 / delta
+                  v[g0 + j] = rs;
+                  gsum = fmaf(d2, rs, gsum);                            // delta = d2 / delta
+                }
+              } else {
+                // sequence length not a power of two: columns at positions >= Sr are phantoms (no distance, no weight)
+#pragma unroll
+                for (int j = 0; j < SQ; ++j) {
+                  const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], nj[g0 + j]), 1e-12f);
+                  const float rs = rsqrt_approx(d2);
+                  const bool real = j < Sr;
+                  v[g0 + j] = real ? rs : 0.f;
+                  gsum = real ? fmaf(d2, rs, gsum) : gsum;
+                }
+                if (rowpad) gsum = 0.f;                                 // phantom rows add nothing to the block sums
               }
 #pragma unroll
               for (int o = 1; o < SQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
@@ -695,8 +725,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       if (MODE != NCE_BWD) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // partial arrays / red[] may be reused now
         if (!kIsNce && wgi == 0 && trow == 0 && (!kWide || x.q == 0)) {
-          const int t0 = (p.seq0 * p.S) / kTileM;
-          const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
+          const int t0 = (p.seq0 * p.Sp) / kTileM;
+          const int nrt = (p.seq1 * p.Sp + kTileM - 1) / kTileM - t0;
           const int slot = p.np_tmp * (x.c * nrt + (row0 / kTileM - t0));
           float* p3 = reinterpret_cast<float*>(ws + p.part3_off);
           p3[slot + pk] =

@@ -65,6 +65,10 @@ struct ProbSel {
 struct Plan {
   // dims
   int32_t B, S, M, D, d, b, bpad, Bpad, nT, nOps, nProb, nOrth, kbFull, seq0, seq1, need_grad, terms, num_sms;
+  // Temporal row space: the distance kernel reduces S x S blocks with shuffles over Sp = the next power of two >= S lanes,
+  // so every temporal per-row array (operands, squared norms, m_II, dx, rho) is indexed by tr(i) = (i / S) * Sp + i % S;
+  // rows with position >= S are phantoms (zero operands, masked everywhere).  Sp == S for the usual power-of-two S.
+  int32_t Sp, Bt;                                       // padded sequence length, rows of the temporal row space (b * Sp)
   int32_t nsplit_fwd;                                   // row-sum slots per row (= np_nce)
   // stream-K split of the Gram launches (see PieceIter): grid sizes and the largest number of pieces one 128-row
   // block is cut into; piece k of a block accumulates into the k-th copy of the output buffers
@@ -199,8 +203,10 @@ struct PieceIter {
 
 FB_HD int nce_row_tiles(const Plan& p) { return (p.seq1 + kTileM - 1) / kTileM - p.seq0 / kTileM; }
 FB_HD int tmp_row_tiles(const Plan& p) {
-  return (p.seq1 * p.S + kTileM - 1) / kTileM - (p.seq0 * p.S) / kTileM;
+  return (p.seq1 * p.Sp + kTileM - 1) / kTileM - (p.seq0 * p.Sp) / kTileM;
 }
+// row of the temporal row space that holds feature row i
+FB_HD int tmp_row(const Plan& p, int i) { return p.Sp == p.S ? i : (i / p.S) * p.Sp + i % p.S; }
 #ifndef FB_STREAMK_TMP
 #define FB_STREAMK_TMP 1        // 1: always; 0: only when the launch has fewer row blocks than SMs (row shards); -1: never
 #endif
@@ -213,7 +219,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   if (c.B <= 0 || c.S <= 0 || c.M <= 0 || c.D <= 0) return FOCAL_EINVAL;
   if (c.M < 1 || c.M > kMaxM) return FOCAL_ESHAPE;
   if (c.B % c.S) return FOCAL_ESHAPE;                    // loss.py:154 reshape(-1, S, D) would raise
-  if (c.S > 32 || (c.S & (c.S - 1))) return FOCAL_ESHAPE;  // sequence = power-of-two rows of one warp
+  if (c.S > 32) return FOCAL_ESHAPE;                     // a (padded) sequence = rows of one warp
   if (c.D < 2 || c.D > 512) return FOCAL_ESHAPE;
   if (!(c.temperature > 0.f)) return FOCAL_EINVAL;
   if (c.precision != FOCAL_PREC_BF16 && c.precision != FOCAL_PREC_FP32) return FOCAL_EINVAL;
@@ -223,6 +229,9 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   if (c.precision == FOCAL_PREC_FP32 && c.D > 256) return FOCAL_ESHAPE;
   p.B = c.B; p.S = c.S; p.M = c.M; p.D = c.D; p.d = c.D / 2;
   p.b = c.B / c.S;
+  p.Sp = 1;
+  while (p.Sp < c.S) p.Sp *= 2;
+  p.Bt = p.b * p.Sp;
   p.nT = 2 * c.M;
   // K blocks (128 bytes = 64 bf16 elements, zero-padded) of an operand of `w` columns: bf16 1..4, or the wide mode's 8;
   // split tiles: a hi and a lo image of ceil(w / 64) blocks each -> 2, 4, 6, 8
@@ -243,7 +252,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     const int kbHalf = kblocks(p.d);
     p.bpad = pad_rows(p.b, tile_bn(kbHalf));
     if (c.no_private) { const int32_t alt = pad_rows(p.b, tile_bn(p.kbFull)); if (alt > p.bpad) p.bpad = alt; }
-    p.Bpad = pad_rows(p.B, tile_bn(p.kbFull));
+    p.Bpad = pad_rows(p.Bt, tile_bn(p.kbFull));
   }
   p.seq0 = c.seq_begin; p.seq1 = c.seq_end;
   if (p.seq0 < 0 || p.seq1 > p.b || p.seq0 >= p.seq1) return FOCAL_EINVAL;
@@ -325,7 +334,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
     p.sk_tmp = !wide && ((FB_STREAMK_TMP > 0) || (FB_STREAMK_TMP == 0 && items < num_sms));
     p.np_tmp = 2;
     int np1 = 1;
-    p.grid_tmp = piece_grid(items, (p.B + bn - 1) / bn, num_sms, p.sk_tmp != 0, &np1);
+    p.grid_tmp = piece_grid(items, (p.Bt + bn - 1) / bn, num_sms, p.sk_tmp != 0, &np1);
     if (np1 > p.np_tmp) p.np_tmp = np1;
   }
   p.nsplit_fwd = p.np_nce;      // row-sum slots per row: one per stream-K piece

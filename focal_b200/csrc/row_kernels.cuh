@@ -86,7 +86,7 @@ __device__ __forceinline__ float warp_dot(const float* a, const float* b, int n,
 // ---------------------------------------------------------------------------------------------------------
 __global__ void zero_pad_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws) {
   const int padN = p.bpad - p.b;      // per (op, kb, s)
-  const int padT = p.Bpad - p.B;      // per (tensor, kb)
+  const int padT = p.Bpad - p.Bt;     // per (tensor, kb)
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long stride = (long)gridDim.x * blockDim.x;
   const uint4 z = make_uint4(0, 0, 0, 0);
@@ -113,22 +113,24 @@ __global__ void zero_pad_kernel(const __grid_constant__ Plan p, uint8_t* __restr
       rsum[grp * p.bpad + p.b + pr] = 1.f;
     }
   }
-  if (padT > 0) {
-    const long chunks = (long)p.nT * p.kbFull * padT * 8;
+  if (padT > 0 || p.Sp != p.S) {
+    // temporal row space: rows beyond the batch and the phantom rows of padded sequences (position >= S)
+    const long chunks = (long)p.nT * p.kbFull * p.Bpad * 8;
     for (long e = tid; e < chunks; e += stride) {
       const int c = e & 7;
       long r = e >> 3;
-      const int pr = r % padT; r /= padT;
+      const int row = r % p.Bpad; r /= p.Bpad;
+      if (row < p.Bt && (row % p.Sp) < p.S) continue;
       const uint64_t tk = r;      // t * kbFull + kb
-      *reinterpret_cast<uint4*>(ws + p.xt_off + (tk * p.Bpad + p.B + pr) * 128 + c * 16) = z;
+      *reinterpret_cast<uint4*>(ws + p.xt_off + (tk * p.Bpad + row) * 128 + c * 16) = z;
     }
     float* sq = reinterpret_cast<float*>(ws + p.sq_off);
     float* mi = reinterpret_cast<float*>(ws + p.mintra_off);
-    for (long e = tid; e < (long)p.nT * padT; e += stride) {
-      const long t = e / padT;
-      const int pr = e % padT;
-      sq[t * p.Bpad + p.B + pr] = 0.f;
-      mi[t * p.Bpad + p.B + pr] = 0.f;
+    for (long e = tid; e < (long)p.nT * p.Bpad; e += stride) {
+      const int row = e % p.Bpad;
+      if (row < p.Bt && (row % p.Sp) < p.S) continue;
+      sq[e] = 0.f;
+      mi[e] = 0.f;
     }
   }
 }
@@ -187,14 +189,15 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
         }
       }
     }
-    // ---- temporal operands
+    // ---- temporal operands (row tr(i) of the temporal row space)
     if (p.terms & FOCAL_TERM_TEMPORAL) {
+      const int it = tmp_row(p, i);
       for (int t = 0; t < p.nT; ++t) {
         const float* x = xs + t * D;
         float sq = 0.f;
         const int kh = p.prec == FOCAL_PREC_FP32 ? p.kbFull / 2 : p.kbFull;
         for (int kb = 0; kb < kh; ++kb) {
-          uint8_t* dst = ws + p.xt_off + (((uint64_t)t * p.kbFull + kb) * p.Bpad + i) * 128 + tile_byte_bf16((uint32_t)i, 2 * lane);
+          uint8_t* dst = ws + p.xt_off + (((uint64_t)t * p.kbFull + kb) * p.Bpad + it) * 128 + tile_byte_bf16((uint32_t)it, 2 * lane);
           const int e = kb * 64 + 2 * lane;
           const float v0 = (e < D) ? x[e] : 0.f;
           const float v1 = (e + 1 < D) ? x[e + 1] : 0.f;
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
           sq = fmaf(r0, r0 + 2.f * l0, fmaf(r1, r1 + 2.f * l1, sq));      // = tile_product(x, x) (no lo * lo term)
         }
         sq = warp_sum(sq);
-        if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;
+        if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + it] = sq;
       }
     }
     // ---- loss terms of the owned rows
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan
       tot += sqrtf(d2);
     }
   const float m = 2.f * tot / (float)(S * S - S);
-  float* mi = reinterpret_cast<float*>(ws + p.mintra_off) + (uint64_t)t * p.Bpad + (uint64_t)I * S;
+  float* mi = reinterpret_cast<float*>(ws + p.mintra_off) + (uint64_t)t * p.Bpad + (uint64_t)I * p.Sp;
   for (int a = lane; a < S; a += 32) mi[a] = m;
 }
 
@@ -357,18 +360,19 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
     for (int t = 0; t < p.nT; ++t) {
       const float* x = xs + t * D;
       // a row block whose column tiles were split over several CTAs (stream-K) has one set of accumulators per piece
-      const int extra = reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off)[(uint64_t)t * (p.Bpad / kTileM) + i / kTileM];
-      float rho = reinterpret_cast<const float*>(ws + p.rho_off)[(uint64_t)t * p.Bpad + i];
-      const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + i) * Dp;
+      const int it = tmp_row(p, i);
+      const int extra = reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off)[(uint64_t)t * (p.Bpad / kTileM) + it / kTileM];
+      float rho = reinterpret_cast<const float*>(ws + p.rho_off)[(uint64_t)t * p.Bpad + it];
+      const float* y = reinterpret_cast<const float*>(ws + p.dx_off) + ((uint64_t)t * p.Bpad + it) * Dp;
       int cnt = reinterpret_cast<const int32_t*>(ws + p.cnt_off)[(uint64_t)t * p.bpad + I];
       for (int k = 1; k <= extra; ++k) {
-        rho += reinterpret_cast<const float*>(ws + p.rho_off + k * p.rho2_delta)[(uint64_t)t * p.Bpad + i];
+        rho += reinterpret_cast<const float*>(ws + p.rho_off + k * p.rho2_delta)[(uint64_t)t * p.Bpad + it];
         cnt += reinterpret_cast<const int32_t*>(ws + p.cnt_off + k * p.cnt2_delta)[(uint64_t)t * p.bpad + I];
       }
       for (int c = lane; c < D; c += 32) {
         float yc = y[c];
         for (int k = 1; k <= extra; ++k)
-          yc += (reinterpret_cast<const float*>(ws + p.dx_off + k * p.dx2_delta) + ((uint64_t)t * p.Bpad + i) * Dp)[c];
+          yc += (reinterpret_cast<const float*>(ws + p.dx_off + k * p.dx2_delta) + ((uint64_t)t * p.Bpad + it) * Dp)[c];
         gs[t * D + c] = p.w_rank * (op_round(p.prec, x[c]) * rho - yc);
       }
       // intra-sequence pairs: dL/dm_II = cnt / (b(b-1)), spread over S^2 - S ordered pairs, both orders
@@ -505,8 +509,8 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant_
       acc[1] += p2[(size_t)k * 2 + 1];
     }
   if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_nan) {
-    const int t0 = (p.seq0 * p.S) / kTileM;
-    const int nrt = (p.seq1 * p.S + kTileM - 1) / kTileM - t0;
+    const int t0 = (p.seq0 * p.Sp) / kTileM;
+    const int nrt = (p.seq1 * p.Sp + kTileM - 1) / kTileM - t0;
     for (int k = threadIdx.x; k < p.np_tmp * p.nT * nrt; k += 256) acc[3] += p3[k];
   }
   double out[4];

@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(1024, 1) prologue_v2_kernel(const __grid_const
                                                               uint8_t* __restrict__ ws, int fuse_intra) {
   extern __shared__ float smem_f[];
   const int nT = p.nT, D = p.D, d = p.d, S = p.S;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so that every branch on (row, tensor) state below is uniform for
+  // the compiler too and the shuffle reductions inside them need no WARPSYNC / collective wrappers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int r = warp / nT, t = warp - r * nT;                 // row within the block, tensor
   const int row_lo = p.local_rows ? p.seq0 * S : 0, row_hi = p.local_rows ? p.seq1 * S : p.B;
   const int i = row_lo + blockIdx.x * 4 + r;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(1024, 1) finalize_v2_kernel(const __grid_const
                                                               const uint8_t* __restrict__ ws) {
   extern __shared__ float smem_f[];
   const int nT = p.nT, D = p.D, d = p.d, S = p.S;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;    // warp-uniform
   const int r = warp / nT, t = warp - r * nT;
   const int i = p.seq0 * S + blockIdx.x * 4 + r;
   const bool live = i < p.seq1 * S;

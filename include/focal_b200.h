@@ -20,8 +20,8 @@
 extern "C" {
 #endif
 
-#define FOCAL_B200_ABI_VERSION 3
-#define FOCAL_MAX_MODALITIES 4
+#define FOCAL_B200_ABI_VERSION 4
+#define FOCAL_MAX_MODALITIES 8
 
 enum {
   FOCAL_OK = 0,

@@ -55,6 +55,14 @@ CASES = [
     # cfg 5 embedding width (shared 256 + private 256): the wide temporal mode of the CUDA path
     dict(name="kat6_d512", gen="structured", seed=13, mods=["seismic", "audio"], B=128, D=512, model="DeepSense"),
     dict(name="kat7_d320_m3", gen="iid", seed=14, mods=["acc", "gyr", "mag"], B=4 * 21, D=320, model="DeepSense"),
+    # shapes the reference accepts and round 1 refused: more than 4 modalities, sequence lengths that are not powers of two
+    dict(name="kat8_m5", gen="iid", seed=15, mods=["m0", "m1", "m2", "m3", "m4"], B=64, D=64, model="DeepSense"),
+    dict(name="kat9_m8", gen="structured", seed=16, mods=[f"m{i}" for i in range(8)], B=32, D=64, model="DeepSense"),
+    dict(name="edge_seq3", gen="structured", seed=17, mods=["seismic", "audio"], B=3 * 40, D=128, model="DeepSense",
+         seq_len=3),
+    dict(name="edge_seq6", gen="iid", seed=18, mods=["seismic", "audio"], B=6 * 24, D=64, model="DeepSense", seq_len=6),
+    dict(name="edge_seq5_m3", gen="structured", seed=19, mods=["acc", "gyr", "mag"], B=5 * 32, D=96,
+         model="SW_Transformer", seq_len=5),
 ]
 
 

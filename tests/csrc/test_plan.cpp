@@ -98,13 +98,14 @@ static void check_plan(const FocalCfg& c, int sms) {
       CHECK(r[i].off + r[i].bytes <= r[j].off || r[j].off + r[j].bytes <= r[i].off, "%s overlaps %s (B=%d D=%d M=%d)",
             r[i].name, r[j].name, c.B, c.D, c.M);
   }
-  CHECK(p.bpad % kTileM == 0 && p.Bpad % kTileM == 0 && p.bpad >= p.b && p.Bpad >= p.B, "padding");
+  CHECK(p.bpad % kTileM == 0 && p.Bpad % kTileM == 0 && p.bpad >= p.b && p.Bpad >= p.Bt && p.Bt >= p.B, "padding");
+  CHECK(p.Sp >= p.S && (p.Sp & (p.Sp - 1)) == 0 && p.Sp < 2 * p.S + (p.S == 1) && p.Bt == p.b * p.Sp, "temporal row space");
   // the launch geometries the plan stores must be the ones PieceIter will see
   const int bnT = tile_bn(p.kbFull);
-  const int wide = (p.kbFull > 4 && p.need_grad) ? 2 : 1;
-  check_geometry(p.nT * tmp_row_tiles(p) * wide, (p.B + bnT - 1) / bnT, sms, p.sk_tmp != 0);
+  const int wide = (p.wide && p.need_grad) ? 2 : 1;
+  check_geometry(p.nT * tmp_row_tiles(p) * wide, (p.Bt + bnT - 1) / bnT, sms, p.sk_tmp != 0);
   int np = 0;
-  CHECK(piece_grid(p.nT * tmp_row_tiles(p) * wide, (p.B + bnT - 1) / bnT, sms, p.sk_tmp != 0, &np) == p.grid_tmp, "grid_tmp");
+  CHECK(piece_grid(p.nT * tmp_row_tiles(p) * wide, (p.Bt + bnT - 1) / bnT, sms, p.sk_tmp != 0, &np) == p.grid_tmp, "grid_tmp");
   CHECK(np <= p.np_tmp, "np_tmp %d < %d", p.np_tmp, np);
 }
 
@@ -127,12 +128,16 @@ int main() {
   check_plan(cfg(32, 4, 2, 33, 0, 8), 148);
   check_plan(cfg(4, 4, 2, 16, 0, 1), 148);
   check_plan(cfg(512, 32, 1, 64, 0, 16), 148);
+  check_plan(cfg(3 * 40, 3, 2, 128, 0, 40), 148);          // sequence lengths that are not powers of two
+  check_plan(cfg(6 * 24, 6, 2, 64, 0, 24), 148);
+  check_plan(cfg(5 * 2048, 5, 3, 256, 0, 2048), 148);
+  check_plan(cfg(2048, 4, 8, 128, 0, 512), 148);           // 8 modalities
   // documented limits
   Plan p;
   CHECK(build_plan(cfg(8190, 4, 2, 256, 0, 2047), p, 148) == FOCAL_ESHAPE, "B %% S");
-  CHECK(build_plan(cfg(8190, 3, 2, 256, 0, 2730), p, 148) == FOCAL_ESHAPE, "S not a power of two");
+  CHECK(build_plan(cfg(33 * 8, 33, 2, 256, 0, 8), p, 148) == FOCAL_ESHAPE, "S > 32");
   CHECK(build_plan(cfg(8192, 4, 2, 514, 0, 2048), p, 148) == FOCAL_ESHAPE, "D > 512");
-  CHECK(build_plan(cfg(8192, 4, 5, 256, 0, 2048), p, 148) == FOCAL_ESHAPE, "M > 4");
+  CHECK(build_plan(cfg(8192, 4, 9, 256, 0, 2048), p, 148) == FOCAL_ESHAPE, "M > 8");
   CHECK(build_plan(cfg(8192, 4, 2, 256, 5, 5), p, 148) == FOCAL_EINVAL, "empty shard");
   if (fails) {
     std::printf("%d failures\n", fails);

@@ -101,8 +101,13 @@ def test_workspace_info_and_error_codes_without_a_gpu(lib):
     c3 = cfg(M=3, B=4096, seq_end=1024)
     assert lib.focal_b200_workspace_info(C.byref(c3), C.byref(info)) == 0 and info.n_problems == 9 and info.n_ops == 12
     # shape errors the Python layer turns into ValueError
-    for bad in (cfg(B=8190), cfg(S=3, B=8190, seq_end=2730), cfg(D=514), cfg(M=5), cfg(temperature=0.01)):
+    for bad in (cfg(B=8190), cfg(S=33, B=8184, seq_end=248), cfg(D=514), cfg(M=9), cfg(temperature=0.01),
+                cfg(precision=1, D=320)):
         assert lib.focal_b200_workspace_info(C.byref(bad), C.byref(info)) == _cabi.FOCAL_ESHAPE
+    # shapes the reference accepts and round 1 refused: any seq_len up to 32 (padded to a power of two inside), M up to 8
+    assert lib.focal_b200_workspace_info(C.byref(cfg(S=3, B=8190, seq_end=2730)), C.byref(info)) == 0
+    assert info.Bpad >= 2730 * 4                                    # temporal row space: sequences padded to 4 rows
+    assert lib.focal_b200_workspace_info(C.byref(cfg(M=5)), C.byref(info)) == 0 and info.n_problems == 25
     for bad in (cfg(seq_begin=5, seq_end=5), cfg(seq_end=4096), cfg(temperature=0.0)):
         assert lib.focal_b200_workspace_info(C.byref(bad), C.byref(info)) == _cabi.FOCAL_EINVAL
     assert lib.focal_b200_workspace_info(None, C.byref(info)) == _cabi.FOCAL_EINVAL

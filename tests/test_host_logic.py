@@ -30,8 +30,9 @@ def test_module_mirrors_reference_constructor_contract():
     hp = m.engine.hp
     assert (hp.w_shared, hp.w_private, hp.w_orth, hp.w_rank, hp.margin) == (1.0, 1.0, 3.0, 5.0, 1.0)
     assert FOCALLoss(make_args(tag="noPrivate")).engine.hp.no_private is True
+    assert len(FOCALLoss(make_args(mods=("a", "b", "c", "d", "e"))).modalities) == 5     # up to 8 modalities
     with pytest.raises(ValueError):
-        FOCALLoss(make_args(mods=("a", "b", "c", "d", "e")))
+        FOCALLoss(make_args(mods=tuple("abcdefghi")))
 
 
 def test_input_validation_raises_before_any_launch():

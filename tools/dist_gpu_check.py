@@ -48,7 +48,9 @@ def main():
             ok = ok and good
             print(f"[rank {rank}/{world}] {mode:10s} B={B} D={D} M={len(mods)}: loss5 rel diff {lerr:.2e}, "
                   f"grad rel diff {gerr:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
-            sharded._graphs.clear()
+            dist.barrier()
+            sharded.close()
+            dist.barrier()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
