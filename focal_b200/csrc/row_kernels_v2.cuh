@@ -30,7 +30,7 @@ __device__ __forceinline__ void warp_sum_n(float (&v)[N]) {
   }
 }
 
-// shared memory of both kernels: the staged rows, then per-(row, tensor) scalars
+// shared memory of both kernels: per-(row, tensor) scalars first (fixed offsets), then the staged rows
 __host__ __device__ inline size_t row_v2_smem_bytes(int nT, int D) {
   return ((size_t)4 * nT * D + (size_t)4 * nT * 4) * sizeof(float);
 }
@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(1024, 1) prologue_v2_kernel(const __grid_const
   const int row_lo = p.local_rows ? p.seq0 * S : 0, row_hi = p.local_rows ? p.seq1 * S : p.B;
   const int i = row_lo + blockIdx.x * 4 + r;
   const bool live = i < row_hi;
-  float* xs = smem_f;                                         // [4][nT][D] raw rows
-  float* nrm2 = smem_f + (size_t)4 * nT * D;                  // [4][nT][2] squared norms (shared half, private half)
+  float* nrm2 = smem_f;                                       // [4][nT][2] squared norms (shared half, private half)
   float* part = nrm2 + 4 * nT * 2;                            // [4][nT] intra-sequence partial sums
   float* red = part + 4 * nT;                                 // [4][nT] orthogonality partial sums
+  float* xs = red + 4 * nT;                                   // [4][nT][D] raw rows (16 * nT floats in: 16-byte aligned)
   const int c0 = VW * lane;
   const int I = i / S, s = i - I * S;
   const bool owned = live && I >= p.seq0 && I < p.seq1;
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(1024, 1) finalize_v2_kernel(const __grid_const
   const int r = warp / nT, t = warp - r * nT;
   const int i = p.seq0 * S + blockIdx.x * 4 + r;
   const bool live = i < p.seq1 * S;
-  float* xs = smem_f;                                         // [4][nT][D]
-  float* nrm2 = smem_f + (size_t)4 * nT * D;                  // [4][nT][2]
+  float* nrm2 = smem_f;                                       // [4][nT][2]
+  float* xs = smem_f + 16 * nT;                               // [4][nT][D] (same layout as the prologue)
   const int c0 = VW * lane;
   float sh[VW], pr[VW];
   float na = 1.f, nb = 1.f;
