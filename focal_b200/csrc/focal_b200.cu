@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/focal_b200.h"
+#include "augment_kernels.cuh"
 #include "gram_kernel.cuh"
 #include "plan.h"
 #include "row_kernels.cuh"
@@ -639,6 +640,22 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// frequency-domain input stage
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int focal_b200_spectrum_rotate(const float* in, float* out, long long n_bc, int plane, int interleaved,
+                                          float cos_angle, float sin_angle, void* stream) {
+  if (!in || !out || n_bc <= 0 || plane <= 0 || (plane & 3)) return FOCAL_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return FOCAL_EINVAL;
+  const long long vecs = n_bc * (plane >> 2);
+  long long blocks = (vecs + 255) / 256;
+  const long long cap = (long long)device_sms() * 16;          // grid-stride: a few waves of 256-thread blocks
+  if (blocks > cap) blocks = cap;
+  fb::spectrum_rotate_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, n_bc, plane, interleaved, cos_angle, sin_angle);
+  return cuda_ok("spectrum_rotate_kernel");
+}
 
 #ifdef FB_TRACE
 // experiment builds only: copy the pipeline trace of the last Gram launch to the host (tools/trace_gram.py)

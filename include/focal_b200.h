@@ -165,6 +165,18 @@ int focal_b200_peer_free(void* ptr);
 int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, const FocalPeers* peers, size_t ws_bytes,
                             float* loss5, float* const* grads, void* stream);
 
+/*
+ * Frequency-domain input stage: the part of Augmenter.fft_preprocess after torch.fft.fft
+ * (/root/reference/src/data_augmenter/Augmenter.py:141-158: view_as_real + permute + reshape to [b, 2c, i, s]) fused
+ * with PhaseShiftAugmenter's rotation (/root/reference/src/data_augmenter/PhaseShiftAugmenter.py:35-57).
+ *   in   interleaved != 0: complex64 [n_bc][plane] (re, im) pairs, e.g. the cuFFT output viewed as float;
+ *        interleaved == 0: planar fp32 [n_bc][2][plane] (what PhaseShiftAugmenter receives)
+ *   out  planar fp32 [n_bc][2][plane]:  re' = re cos - im sin,  im' = re sin + im cos
+ * n_bc = batch x complex channels, plane = intervals x spectrum length (a multiple of 4); 16-byte aligned pointers.
+ */
+int focal_b200_spectrum_rotate(const float* in, float* out, long long n_bc, int plane, int interleaved, float cos_angle,
+                               float sin_angle, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,8 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_multi.py -q -s 2>&1 | grep -E "multi-GPU parity|passed|failed|skipped|Error" | tee gpurun_out/r2_multi_gpu_parity_2.txt
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/r2_bench_2gpu.json 2> gpurun_out/r2_bench_2gpu.err
+tail -c 400 gpurun_out/r2_bench_2gpu.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2_bench_2gpu.json').read().strip().splitlines()[-1])
+print({k:d.get(k) for k in ('n_gpus','value','ms_per_step','config','cuda_graph_replays')}); print(d['e2e'])"
