@@ -21,7 +21,7 @@ EXPORTS = (
     "focal_b200_nce_rowsum", "focal_b200_nce_lse", "focal_b200_nce_grad", "focal_b200_temporal",
     "focal_b200_finalize", "focal_b200_loss", "focal_b200_set_ptrs",
     "focal_b200_peer_alloc", "focal_b200_peer_open", "focal_b200_peer_close", "focal_b200_peer_free",
-    "focal_b200_loss_sharded", "focal_b200_spectrum_rotate",
+    "focal_b200_loss_sharded", "focal_b200_spectrum_rotate", "focal_b200_knn_predict",
 )
 FOCAL_MAX_PEERS = 8
 
@@ -89,6 +89,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.focal_b200_finalize.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
     lib.focal_b200_loss.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
     lib.focal_b200_spectrum_rotate.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_float, vp]
+    lib.focal_b200_knn_predict.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.focal_b200_set_ptrs.argtypes = [cfgp, vp, C.c_size_t, C.POINTER(vp), vp, C.POINTER(vp), vp]
     lib.focal_b200_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
     lib.focal_b200_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]

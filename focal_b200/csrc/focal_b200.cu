@@ -9,6 +9,7 @@
 #include "../../include/focal_b200.h"
 #include "augment_kernels.cuh"
 #include "gram_kernel.cuh"
+#include "knn_kernels.cuh"
 #include "plan.h"
 #include "row_kernels.cuh"
 #include "row_kernels_fast.cuh"
@@ -655,6 +656,24 @@ extern "C" int focal_b200_spectrum_rotate(const float* in, float* out, long long
   fb::spectrum_rotate_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, out, n_bc, plane, interleaved, cos_angle, sin_angle);
   return cuda_ok("spectrum_rotate_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k-nearest-neighbour evaluation
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int focal_b200_knn_predict(const float* train, const int32_t* labels, int n_train, const float* query,
+                                      int n_query, int dim, int k, int n_classes, float* dist_ws, int32_t* out,
+                                      int32_t* neighbours, void* stream) {
+  if (!train || !labels || !query || !dist_ws || !out) return FOCAL_EINVAL;
+  if (n_train <= 0 || n_query <= 0 || dim <= 0 || k <= 0) return FOCAL_EINVAL;
+  if (k > fb::kKnnMaxK || k > n_train || n_classes < 1 || n_classes > 32) return FOCAL_ESHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((n_train + 63) / 64, (n_query + 63) / 64);
+  fb::knn_dist_kernel<<<grid, 256, 0, st>>>(query, train, n_query, n_train, dim, dist_ws);
+  int rc = cuda_ok("knn_dist_kernel");
+  if (rc) return rc;
+  fb::knn_select_kernel<<<(n_query + 3) / 4, 128, 0, st>>>(dist_ws, labels, n_query, n_train, k, n_classes, out, neighbours);
+  return cuda_ok("knn_select_kernel");
 }
 
 #ifdef FB_TRACE

@@ -177,6 +177,18 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
 int focal_b200_spectrum_rotate(const float* in, float* out, long long n_bc, int plane, int interleaved, float cos_angle,
                                float sin_angle, void* stream);
 
+/*
+ * k-nearest-neighbour evaluation: replaces sklearn's KNeighborsClassifier().fit / .predict in
+ * /root/reference/src/train_utils/knn.py:22-42 and eval_functions.py:65-97 (Euclidean, uniform weights, majority vote,
+ * ties to the smallest label; k <= 16, labels in [0, n_classes), n_classes <= 32) without leaving the device.
+ *   train fp32 [n_train, dim], labels int32 [n_train], query fp32 [n_query, dim]
+ *   dist_ws fp32 [n_query, n_train] scratch (squared distances are left there), out int32 [n_query] predicted labels,
+ *   neighbours int32 [n_query, k] indices of the k nearest training rows in order, or NULL
+ */
+int focal_b200_knn_predict(const float* train, const int32_t* labels, int n_train, const float* query, int n_query,
+                           int dim, int k, int n_classes, float* dist_ws, int32_t* out, int32_t* neighbours,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif
