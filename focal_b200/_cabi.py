@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libfocal_b200.so")
+# FOCAL_B200_LIB: an experiment build of the same library (tools/variant_bench.py); never a different implementation
+LIB_PATH = os.environ.get("FOCAL_B200_LIB") or os.path.join(_PKG, "libfocal_b200.so")
 
 FOCAL_TERM_NCE, FOCAL_TERM_ORTH, FOCAL_TERM_TEMPORAL, FOCAL_TERM_ALL = 1, 2, 4, 7
 FOCAL_PREC_BF16, FOCAL_PREC_FP32 = 0, 1
@@ -88,8 +89,10 @@ def load(path: str | None = None) -> C.CDLL:
     lib.focal_b200_temporal.argtypes = [cfgp, vp, C.c_size_t, vp]
     lib.focal_b200_finalize.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
     lib.focal_b200_loss.argtypes = [cfgp, C.POINTER(vp), vp, C.c_size_t, vp, C.POINTER(vp), vp]
-    lib.focal_b200_spectrum_rotate.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_float, vp]
-    lib.focal_b200_knn_predict.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    old = bool(os.environ.get("FOCAL_B200_LIB_BISECT"))    # bisecting with a build of an older commit (tools only)
+    if not old:
+        lib.focal_b200_spectrum_rotate.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_float, vp]
+        lib.focal_b200_knn_predict.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.focal_b200_set_ptrs.argtypes = [cfgp, vp, C.c_size_t, C.POINTER(vp), vp, C.POINTER(vp), vp]
     lib.focal_b200_peer_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
     lib.focal_b200_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
@@ -97,9 +100,9 @@ def load(path: str | None = None) -> C.CDLL:
     lib.focal_b200_peer_free.argtypes = [vp]
     lib.focal_b200_loss_sharded.argtypes = [cfgp, C.POINTER(vp), C.POINTER(FocalPeers), C.c_size_t, vp, C.POINTER(vp), vp]
     for name in EXPORTS:
-        if name != "focal_b200_strerror":
+        if name != "focal_b200_strerror" and not (old and not hasattr(lib, name)):
             getattr(lib, name).restype = C.c_int
-    if lib.focal_b200_abi_version() != ABI_VERSION:
+    if lib.focal_b200_abi_version() != ABI_VERSION and not old:
         raise ImportError(f"{path}: ABI version {lib.focal_b200_abi_version()} != expected {ABI_VERSION}")
     if path == LIB_PATH:
         _lib = lib

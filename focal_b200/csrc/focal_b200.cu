@@ -14,6 +14,7 @@
 #include "row_kernels.cuh"
 #include "row_kernels_fast.cuh"
 #include "row_kernels_v2.cuh"
+#include "row_kernels_v3.cuh"
 
 using namespace fb;
 
@@ -295,6 +296,53 @@ int launch_finalize_v2(int vw, const Plan& p, const FeatPtrs& f, const GradPtrs&
 }
 #undef FB_V2_DISPATCH
 
+// ---- third-generation row kernels (one warp per (sequence, tensor)); plan.h decides when they apply (Plan::rowgen)
+size_t row_v3_smem(const Plan& p) {
+  return ((size_t)p.seqb * p.nT * p.S * p.d + (size_t)p.seqb * p.nT * p.S + (size_t)p.seqb * p.nT) * sizeof(float);
+}
+template <int S, int NQ, int PREC>
+int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st) {
+  const size_t smem = row_v3_smem(p);
+  if (int rc = ensure_dyn_smem(prologue_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(prologue_v3_kernel)")) return rc;
+  prologue_v3_kernel<S, NQ, PREC><<<p.nblk1, 32 * p.seqb * p.nT, smem, st>>>(p, f, pw, w);
+  return cuda_ok("prologue_v3_kernel");
+}
+template <int S, int NQ, int PREC>
+int launch_finalize_v3_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, cudaStream_t st) {
+  const size_t smem = row_v3_smem(p);
+  if (int rc = ensure_dyn_smem(finalize_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(finalize_v3_kernel)")) return rc;
+  const int grid = (p.seq1 - p.seq0 + p.seqb - 1) / p.seqb;
+  finalize_v3_kernel<S, NQ, PREC><<<grid, 32 * p.seqb * p.nT, smem, st>>>(p, f, g, w);
+  return cuda_ok("finalize_v3_kernel");
+}
+#define FB_V3_CASE(FN, SS, QQ, ...)                                                                   \
+  if (p.S == SS && p.nq == QQ)                                                                        \
+    return p.prec == FOCAL_PREC_FP32 ? FN<SS, QQ, FOCAL_PREC_FP32>(__VA_ARGS__) : FN<SS, QQ, FOCAL_PREC_BF16>(__VA_ARGS__)
+#ifdef FB_FAST_BUILD                  // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
+#define FB_V3_DISPATCH(FN, ...)                                                                       \
+  do {                                                                                                \
+    FB_V3_CASE(FN, 4, 4, __VA_ARGS__);                                                                \
+    return FOCAL_ESHAPE;                                                                              \
+  } while (0)
+#else
+#define FB_V3_DISPATCH(FN, ...)                                                                       \
+  do {                                                                                                \
+    FB_V3_CASE(FN, 4, 4, __VA_ARGS__); FB_V3_CASE(FN, 4, 2, __VA_ARGS__);                             \
+    FB_V3_CASE(FN, 4, 1, __VA_ARGS__); FB_V3_CASE(FN, 4, 3, __VA_ARGS__);                             \
+    FB_V3_CASE(FN, 2, 1, __VA_ARGS__); FB_V3_CASE(FN, 2, 2, __VA_ARGS__);                             \
+    FB_V3_CASE(FN, 1, 1, __VA_ARGS__);                                                                \
+    return FOCAL_ESHAPE;                                                                              \
+  } while (0)
+#endif
+int launch_prologue_v3(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st) {
+  FB_V3_DISPATCH(launch_prologue_v3_t, p, f, pw, w, st);
+}
+int launch_finalize_v3(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, cudaStream_t st) {
+  FB_V3_DISPATCH(launch_finalize_v3_t, p, f, g, w, st);
+}
+#undef FB_V3_DISPATCH
+#undef FB_V3_CASE
+
 // local_rows: the caller's tensors start at the first owned row; the kernels index rows globally, so hand them the
 // (virtual) address of row 0 -- only owned rows are ever dereferenced.
 int fill_feats(const Plan& p, const float* const* feats, FeatPtrs& f) {
@@ -341,7 +389,10 @@ int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& 
   }
   const int vw = fast_row_vw(p, no_private);
   bool fused_intra = false;
-  if (vw) {
+  if (p.rowgen == 3) {
+    fused_intra = true;                 // S == 1: the temporal term is degenerate, nothing to fuse
+    if ((rc = launch_prologue_v3(p, f, pw, w, st))) return rc;
+  } else if (vw) {
     fused_intra = (p.S == 2 || p.S == 4);
     const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT + 4 * kMaxT) * sizeof(float);
     // finalize_v2 reads the squared norms prologue_v2 stores, so the two generations are only used as a pair
@@ -374,7 +425,9 @@ int do_finalize(const Plan& p, int no_private, const float* const* feats, float*
     if ((rc = fill_grads(p, grads, g))) return rc;
     const int rows = (p.seq1 - p.seq0) * p.S;
     const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, no_private) : 0;
-    if (vw) {
+    if (p.rowgen == 3) {
+      if ((rc = launch_finalize_v3(p, f, g, w, st))) return rc;
+    } else if (vw) {
       if (use_row_v2(vw) && p.nT <= 8) rc = launch_finalize_v2(vw, p, f, g, w, (rows + 3) / 4, st);
       else rc = launch_finalize_fast(vw, p, f, g, w, (rows + 3) / 4, st);
       if (rc) return rc;

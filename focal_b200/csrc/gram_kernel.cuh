@@ -33,6 +33,7 @@
 #include "peer.cuh"
 #include "plan.h"
 #include "ptx.cuh"
+#include <type_traits>
 
 namespace fb {
 
@@ -54,8 +55,14 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_KB4_SHARE
 #define FB_KB4_SHARE 1          // 256-column operands: 1 = ALL epilogue warpgroups work on every tile (see GramCfg::kShareAll)
 #endif
+#ifndef FB_KB4_SHARE_NW
+#define FB_KB4_SHARE_NW 4       // epilogue warpgroups of the shared-stage configuration (4, or 6 = one 16-column chunk each at BN = 96)
+#endif
 #ifndef FB_EPI_UNROLL
-#define FB_EPI_UNROLL 1         // chunks of one thread's share of a tile that are in flight together (shared-stage configs)
+#define FB_EPI_UNROLL 1         // 2: two chunks of one thread's share of a tile are in flight together
+#endif
+#ifndef FB_EPI_ROTATE
+#define FB_EPI_ROTATE 1         // shared stages: rotate the chunk -> warpgroup assignment from tile to tile (see run_tile)
 #endif
 #ifndef FB_POLY_PER8
 #define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
@@ -109,11 +116,11 @@ struct GramCfg {
   // -> UMMA #2 -> UMMA #1 is serial and the stages interleave), so warpgroups bound to a stage idle half of the time.
   // With kShareAll every warpgroup takes a share of EVERY tile: half the epilogue latency per tile, same issue work.
   static constexpr bool kShareAll = (KB == 4 && SEQ <= 16 && FB_KB4_SHARE != 0);
-  static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? (kShareAll ? 4 : FB_KB4_NW) : (KB == 8 ? FB_KB8_NW : 1));   // warpgroups per tile
+  static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? (kShareAll ? FB_KB4_SHARE_NW : FB_KB4_NW) : (KB == 8 ? FB_KB8_NW : 1));   // warpgroups per tile
   static constexpr int NG = kShareAll ? NW : NS * NW;                            // epilogue warpgroups in total
-  static constexpr int CW = (NG == 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
+  static constexpr int CW = (NG >= 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
   static constexpr int kThreads = 64 + 128 * NG;
-  static_assert(NG <= 4, "partial-sum arrays and register budget are sized for <= 4 epilogue warpgroups");
+  static_assert(NG <= 6, "partial-sum arrays are sized for <= 6 epilogue warpgroups");
   static constexpr int kOKB = kWide ? 4 : KB;        // K blocks of the O accumulator (wide mode: one half per pass)
   static constexpr int kON = kOKB * kEPB;            // columns of the O accumulator = UMMA #2 N
   static_assert(kON <= 256, "UMMA N");
@@ -142,9 +149,9 @@ struct GramBars {
   uint64_t o_full, o_empty;
   uint32_t tmem_base;
   float red[4];
-  float part_acc[3][128];     // per-row partials of epilogue warpgroups 1.., folded into warpgroup 0 at the end of an item
-  float part_hinge[3][128];
-  int32_t part_cnt[3][128];
+  float part_acc[5][128];     // per-row partials of epilogue warpgroups 1.., folded into warpgroup 0 at the end of an item
+  float part_hinge[5][128];
+  int32_t part_cnt[5][128];
 };
 static_assert(sizeof(GramBars) <= 8192, "barrier block");
 
@@ -504,13 +511,14 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
       const int row = row0 + trow;                    // row within side (NCE: sequence index k) / tensor (TMP: i)
       const bool rowpad = padseq && (row & (SQ - 1)) >= Sr;            // phantom row of a padded sequence
       const bool row_ok = row < ncol_valid && row >= x.row_lo && row < x.row_hi && !rowpad;
-      float rowacc = 0.f;                             // NCE_FWD: row sum; TMP: rho_i
+      float rowacc = 0.f;                             // NCE_FWD: row sum; TMP: rho_i (both accumulate in racc, packed pairs)
+      float racc[4] = {0.f, 0.f, 0.f, 0.f};
       float posg = 0.f;                               // NCE_FWD: G_{k,p(k)} as this row's tile computed it
       bool pos_seen = false;
       float ck = 0.f, n_i = 0.f, mim = -1e30f, hinge_acc = 0.f;
       int cnt_i = 0;
       if (MODE == NCE_BWD && row_ok) ck = (side ? x.cv0_1 : x.cv0_0)[row];
-      if (!kIsNce && row_ok) { n_i = x.cv0_0[row]; mim = x.cv1[row] + margin; }   // m_II + margin
+      if (!kIsNce && row_ok) { n_i = x.cv0_0[row]; mim = x.cv1[row]; }            // m_II
       const int seq_i = row / SQ;
       const int ntiles = x.ct_end - ct_begin;
       // first tile of this item that belongs to this warpgroup: (nb + t) % NS == wg0; kShareAll: every tile
@@ -537,14 +545,14 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         // finalize, so that ln(sum_j e^{s_kj}) - s_{k,p(k)} cancels to the last bit where the positive dominates the row
         // (tensor-core accumulation is not round-to-nearest: a separately computed fp32 dot product differs by ~1e-5)
         const bool ptile = (MODE == NCE_FWD) && overlap && cs != side;
-#pragma unroll 1
-        for (int ch = sub; ch < BN / CW; ch += NW) {
-          float v[CW];
-          tmem_ld_chunk<CW>(s_addr + ch * CW, v);
-          tmem_ld_wait();
+        // One chunk of CW columns.  EDGE = the tile touches the (block) diagonal, the padded tail of the columns, or the
+        // sequences are padded (seq_len not a power of two): only those tiles pay for the per-pair validity logic;
+        // interior tiles -- nearly all of them -- run the short path.
+        auto chunk_body = [&](auto edge_c, int ch, auto& v) {
+          constexpr bool EDGE = decltype(edge_c)::value;
           const int cbase = col0 + ch * CW;           // column (within side) of v[0]
-          if (kIsNce) {
-            if (ptile) {
+          if constexpr (kIsNce) {
+            if (EDGE && ptile) {
 #pragma unroll
               for (int j = 0; j < CW; ++j)
                 if (cbase + j == row) { posg = v[j]; pos_seen = true; }
@@ -558,10 +566,14 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
               for (int j = 0; j < CW; j += 4) {
                 const float4 cj = lds128(cv + (ch * CW + j) * 4);
-                v[j] *= ck + cj.x; v[j + 1] *= ck + cj.y; v[j + 2] *= ck + cj.z; v[j + 3] *= ck + cj.w;
+                float c0, c1, c2, c3;
+                add2(c0, c1, cj.x, cj.y, ck, ck);
+                add2(c2, c3, cj.z, cj.w, ck, ck);
+                mul2(v[j], v[j + 1], v[j], v[j + 1], c0, c1);
+                mul2(v[j + 2], v[j + 3], v[j + 2], v[j + 3], c2, c3);
               }
             }
-            if (diag || tail) {
+            if (EDGE) {
 #pragma unroll
               for (int j = 0; j < CW; ++j) {
                 const int col = cbase + j;
@@ -569,10 +581,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               }
             }
             if (MODE == NCE_FWD) {
-              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-              for (int j = 0; j < CW; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
-              rowacc += (s0 + s1) + (s2 + s3);
+              for (int j = 0; j < CW; j += 4) {
+                add2(racc[0], racc[1], racc[0], racc[1], v[j], v[j + 1]);
+                add2(racc[2], racc[3], racc[2], racc[3], v[j + 2], v[j + 3]);
+              }
             }
           } else {
             // ---------------- temporal: delta_ij, S x S block means, hinge, r_ij
@@ -580,48 +593,50 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
             for (int j = 0; j < CW; j += 4) {
               const float4 t4 = lds128(cv + (ch * CW + j) * 4);
-              nj[j] = n_i + t4.x; nj[j + 1] = n_i + t4.y; nj[j + 2] = n_i + t4.z; nj[j + 3] = n_i + t4.w;
+              add2(nj[j], nj[j + 1], t4.x, t4.y, n_i, n_i);
+              add2(nj[j + 2], nj[j + 3], t4.z, t4.w, n_i, n_i);
             }
 #pragma unroll
             for (int g0 = 0; g0 < CW; g0 += SQ) {
               float gsum = 0.f;
-              if (!padseq) {
 #pragma unroll
-                for (int j = 0; j < SQ; ++j) {
-                  // cdist mm form; the floor keeps 1/delta finite for coincident rows (their r_ij (x_i - x_j) is 0)
-                  const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], nj[g0 + j]), 1e-12f);
-                  const float rs = rsqrt_approx(d2);                    // 1 / delta
-                  v[g0 + j] = rs;
-                  gsum = fmaf(d2, rs, gsum);                            // delta = d2 / delta
+              for (int j = 0; j < SQ; j += 2) {
+                // cdist mm form; the floor keeps 1/delta finite for coincident rows (their r_ij (x_i - x_j) is 0)
+                float d0, d1;
+                fma2(d0, d1, v[g0 + j], v[g0 + j + 1], -2.f, -2.f, nj[g0 + j], nj[g0 + j + 1]);
+                d0 = fmaxf(d0, 1e-12f); d1 = fmaxf(d1, 1e-12f);
+                float r0 = rsqrt_approx(d0), r1 = rsqrt_approx(d1);   // 1 / delta
+                if (EDGE && padseq) {
+                  // sequence length not a power of two: columns at positions >= Sr are phantoms (no distance, no weight)
+                  if (j >= Sr) { r0 = 0.f; d0 = 0.f; }
+                  if (j + 1 >= Sr) { r1 = 0.f; d1 = 0.f; }
                 }
-              } else {
-                // sequence length not a power of two: columns at positions >= Sr are phantoms (no distance, no weight)
-#pragma unroll
-                for (int j = 0; j < SQ; ++j) {
-                  const float d2 = fmaxf(fmaf(-2.f, v[g0 + j], nj[g0 + j]), 1e-12f);
-                  const float rs = rsqrt_approx(d2);
-                  const bool real = j < Sr;
-                  v[g0 + j] = real ? rs : 0.f;
-                  gsum = real ? fmaf(d2, rs, gsum) : gsum;
-                }
-                if (rowpad) gsum = 0.f;                                 // phantom rows add nothing to the block sums
+                v[g0 + j] = r0; v[g0 + j + 1] = r1;
+                gsum = fmaf(d0, r0, gsum);                              // delta = d2 / delta
+                gsum = fmaf(d1, r1, gsum);
               }
+              if (EDGE && rowpad) gsum = 0.f;                           // phantom rows add nothing to the block sums
 #pragma unroll
               for (int o = 1; o < SQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
-              const int colg = cbase + g0;
-              const float m_ij = gsum * inv_cnt;
-              const float mjm = lds32(cv + (BN + ch * CW + g0) * 4) + margin;   // m_JJ + margin
-              bool pair_ok = row_ok;
-              if (tail) pair_ok = pair_ok && colg < ncol_valid;
-              if (diag) pair_ok = pair_ok && (colg / SQ) != seq_i;    // the block diagonal is done exactly elsewhere
-              const float h = pair_ok ? mim - m_ij : -1.f;           // hinge argument; active at equality
-              const bool a_ij = h >= 0.f;
-              const bool a_ji = pair_ok && (mjm - m_ij >= 0.f);
-              hinge_acc += fmaxf(h, 0.f);
-              cnt_i += a_ij ? 1 : 0;
+              const float mm = fmaf(gsum, inv_cnt, -margin);            // m_IJ - margin
+              const float h = mim - mm;                                 // hinge argument (mim = m_II; -1e30 on rows that are not ok)
+              const float hj = lds32(cv + (BN + ch * CW + g0) * 4) - mm;   // ... of the transposed pair: m_JJ + margin - m_IJ
+              bool a_ij = h >= 0.f, a_ji = hj >= 0.f;                   // active at equality
+              if (EDGE) {
+                const int colg = cbase + g0;
+                bool pair_ok = row_ok;
+                if (tail) pair_ok = pair_ok && colg < ncol_valid;
+                if (diag) pair_ok = pair_ok && (colg / SQ) != seq_i;    // the block diagonal is done exactly elsewhere
+                a_ij = a_ij && pair_ok;
+                a_ji = a_ji && pair_ok;
+              }
+              if (a_ij) { hinge_acc += h; ++cnt_i; }
               const float coef = a_ij ? (a_ji ? coef2 : coef1) : (a_ji ? coef1 : 0.f);
 #pragma unroll
-              for (int j = 0; j < SQ; ++j) { v[g0 + j] *= coef; rowacc += v[g0 + j]; }
+              for (int j = 0; j < SQ; j += 2) {
+                mul2(v[g0 + j], v[g0 + j + 1], v[g0 + j], v[g0 + j + 1], coef, coef);
+                add2(racc[j & 2], racc[(j & 2) + 1], racc[j & 2], racc[(j & 2) + 1], v[g0 + j], v[g0 + j + 1]);
+              }
             }
           }
           if (kBwd) {
@@ -643,7 +658,36 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               tmem_st_packed<CW>(s_addr + ch * (NW > 1 ? CW : CW / 2), pk);
             }
           }
-        }
+        };
+        // Shared stages whose chunk count is not a multiple of the warpgroup count (96 columns = 6 chunks over 4
+        // warpgroups): rotate the assignment from tile to tile so that every warpgroup does 3 chunks per two tiles
+        // instead of {2, 2, 1, 1} on every tile (the warpgroups move on to the next tile independently).
+        const int sub_t = (kShareAll && FB_EPI_ROTATE && (BN / CW) % NW != 0) ? ((sub + (int)(n & 1) * (NW / 2)) & (NW - 1)) : sub;
+        // FB_EPI_UNROLL == 2: two chunks of this thread in flight together: twice the independent work behind each
+        // tcgen05.ld / MUFU / shuffle latency
+#define FB_RUN_TILE(EDGE_TAG)                                                        \
+  {                                                                                  \
+    int ch = sub_t;                                                                  \
+    if constexpr (FB_EPI_UNROLL == 2) {                                              \
+      _Pragma("unroll 1") for (; ch + NW < BN / CW; ch += 2 * NW) {                  \
+        float v0[CW], v1[CW];                                                        \
+        tmem_ld_chunk<CW>(s_addr + ch * CW, v0);                                     \
+        tmem_ld_chunk<CW>(s_addr + (ch + NW) * CW, v1);                              \
+        tmem_ld_wait();                                                              \
+        chunk_body(EDGE_TAG, ch, v0);                                                \
+        chunk_body(EDGE_TAG, ch + NW, v1);                                           \
+      }                                                                              \
+    }                                                                                \
+    _Pragma("unroll 1") for (; ch < BN / CW; ch += NW) {                             \
+      float v[CW];                                                                   \
+      tmem_ld_chunk<CW>(s_addr + ch * CW, v);                                        \
+      tmem_ld_wait();                                                                \
+      chunk_body(EDGE_TAG, ch, v);                                                   \
+    }                                                                                \
+  }
+        if (diag || tail || padseq || (kIsNce && ptile)) FB_RUN_TILE(std::true_type{})
+        else FB_RUN_TILE(std::false_type{})
+#undef FB_RUN_TILE
         FB_TRACE_EV(2 + wgi, n, 2);
         if (kBwd) {
           tmem_st_wait();
@@ -659,6 +703,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         }
       }
       nb += ntiles;
+      rowacc = (racc[0] + racc[1]) + (racc[2] + racc[3]);
 
       if (MODE == NCE_FWD && pos_seen && row_ok)      // exactly one thread of one piece sees the positive of a row
         reinterpret_cast<float*>(ws + p.pos_off)[(((uint64_t)x.q * p.S + x.s) * 2 + side) * p.bpad + row] = posg;

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/focal_b200.h"
@@ -78,6 +79,9 @@ struct Plan {
   int32_t prec, epb;                                    // tile precision (FOCAL_PREC_*), operand COLUMNS per K block (64 / 32)
   int32_t wide;                                         // bf16, 256 < D <= 512: O accumulator in two 256-column passes
   int32_t indirect;                                     // caller pointers come from the table at ptrs_off (CUDA graphs)
+  // Row-kernel generation: 3 = row_kernels_v3.cuh (a warp per (sequence, tensor); seqb sequences x nT tensors per block,
+  // nq float4 slots per lane and half), 0 = the older kernels (focal_b200.cu picks among them)
+  int32_t rowgen, seqb, nq;
   float T, margin, w_shared, w_private, w_orth, w_rank;
   float alpha;                                          // sqrt(log2(e)/T): operand pre-scale, Gram = log2-domain logit
   OpDesc ops[kMaxOps];
@@ -88,6 +92,7 @@ struct Plan {
   uint64_t sq_off;      // fp32 [2M][Bpad] squared norms of the rounded temporal operands
   uint64_t mintra_off;  // fp32 [2M][Bpad] m_II of the row's sequence (exact fp32)
   uint64_t nrm_off;     // fp32 [2M][Bpad][2] squared norms of the shared / private half (prologue_v2 -> finalize_v2)
+  uint64_t pd_off;      // fp32 [2M][Bpad][4] squared distances of the rounded row to rows g^1, g^2, g^3 of its sequence (v3)
   uint64_t rpart_off;   // fp32 [nsplit_fwd][nProb][S][2][bpad]
   uint64_t rsum_off;    // fp32 [nProb][S][2][bpad]
   uint64_t rinv_off;    // fp32 [nProb][S][2][bpad]
@@ -207,12 +212,21 @@ FB_HD int tmp_row_tiles(const Plan& p) {
 }
 // row of the temporal row space that holds feature row i
 FB_HD int tmp_row(const Plan& p, int i) { return p.Sp == p.S ? i : (i / p.S) * p.Sp + i % p.S; }
+#ifndef FB_ROW_V3
+#define FB_ROW_V3 1             // 0: experiment builds without the third-generation row kernels (A/B measurements)
+#endif
 #ifndef FB_STREAMK_TMP
 #define FB_STREAMK_TMP 1        // 1: always; 0: only when the launch has fewer row blocks than SMs (row shards); -1: never
 #endif
 #ifndef FB_STREAMK_NCE
 #define FB_STREAMK_NCE 1
 #endif
+
+// FOCAL_B200_ROW_KERNELS=v1|v2 in the environment: keep the older row kernels (A/B measurements)
+inline bool row_kernels_forced_old() {
+  const char* e = std::getenv("FOCAL_B200_ROW_KERNELS");
+  return e && (std::strcmp(e, "v1") == 0 || std::strcmp(e, "v2") == 0);
+}
 
 inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   std::memset(&p, 0, sizeof(p));
@@ -348,6 +362,7 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.sq_off = take((uint64_t)p.nT * p.Bpad * 4);
   p.mintra_off = take((uint64_t)p.nT * p.Bpad * 4);
   p.nrm_off = take((uint64_t)p.nT * p.Bpad * 8);
+  p.pd_off = take((uint64_t)p.nT * p.Bpad * 16);
   const uint64_t rs = (uint64_t)p.nProb * p.S * 2 * p.bpad * 4;
   p.rpart_off = take(rs * p.nsplit_fwd);
   p.rsum_off = take(rs);
@@ -372,6 +387,16 @@ inline int build_plan(const FocalCfg& c, Plan& p, int num_sms) {
   p.flag_tmp_off = take((uint64_t)p.nT * (p.Bpad / kTileM) * 4);
   p.flag_nce_off = take((uint64_t)p.nProb * p.S * 2 * (p.bpad / kTileM) * 4);
   p.nblk1 = ((p.local_rows ? (p.seq1 - p.seq0) * p.S : p.B) + kRowsPerBlock - 1) / kRowsPerBlock;
+  // third-generation row kernels: standard topology, S in {1, 2, 4}, a whole number (<= 4) of float4 slots per lane and
+  // half (nq = d * S / 128), D <= 256, up to 8 tensors; their blocks cover seqb sequences each
+  p.rowgen = 0; p.seqb = 0; p.nq = 0;
+  if (!c.no_private && (c.D & 1) == 0 && (c.S == 1 || c.S == 2 || c.S == 4) && (p.d * c.S) % 128 == 0 &&
+      p.d * c.S / 128 <= 4 && c.D <= 256 && p.nT <= 8 && FB_ROW_V3 && !row_kernels_forced_old()) {
+    p.rowgen = 3;
+    p.nq = p.d * c.S / 128;
+    p.seqb = 8 / p.nT;
+    p.nblk1 = ((p.local_rows ? (p.seq1 - p.seq0) : p.b) + p.seqb - 1) / p.seqb;
+  }
   p.nblk2 = (int32_t)((rowsNce * 2 * p.nProb + 255) / 256);
   p.nitems3 = p.np_tmp * p.nT * (p.Bpad / kTileM);   // one hinge-partial slot per piece of a row block
   p.part1_off = take((uint64_t)p.nblk1 * 4 * 4);

@@ -64,15 +64,17 @@ __device__ __forceinline__ float split_round(float v) {
 __device__ __forceinline__ float op_round(int prec, float v) { return prec ? split_round(v) : bf16_round(v); }
 template <int PREC>
 __device__ __forceinline__ float op_round_t(float v) { return PREC ? split_round(v) : bf16_round(v); }
-// What the tiles compute for a product of two operand elements a, b: bf16 tiles hi_a * hi_b; split tiles the three passes
-// hi_a hi_b + hi_a lo_b + lo_a hi_b (the lo * lo term, <= 2^-18 relative, is not computed).  Everything that is
-// subtracted from a tile result (positive logits, squared norms) must be built from exactly this product, otherwise the
-// part of the rounding that is coherent between aligned rows does not cancel.
-__device__ __forceinline__ float tile_product(int prec, float a, float b) {
-  const float ha = bf16_round(a), hb = bf16_round(b);
-  if (!prec) return ha * hb;
-  const float la = bf16_round(a - ha), lb = bf16_round(b - hb);
-  return fmaf(ha, hb + lb, la * hb);
+// Squared operand element as the temporal distances need it: d^2 = n_i + n_j - 2 G_ij with G from the tiles.  bf16 tiles:
+// hi * hi, exactly the tile's own product, so coincident rows give d^2 = 0.  Split tiles: the full (hi + lo)^2.  The tiles
+// never form lo * lo; in G that term is zero-mean noise (2^-18 relative), but in a squared norm it is a sum of squares:
+// leaving it out made every distance 3.1e-5 too small (measured; profiles/r2_accuracy.txt), a systematic bias of the
+// hinge term.  The price is d^2 = 2 sum(lo^2) ~ 1e-3 instead of 0 for coincident rows -- the size of the reference's own
+// fp32 cancellation error in torch.cdist's matmul form.
+__device__ __forceinline__ float tile_sq(int prec, float a) {
+  const float ha = bf16_round(a);
+  if (!prec) return ha * ha;
+  const float r = ha + bf16_round(a - ha);
+  return r * r;
 }
 
 __device__ __forceinline__ float warp_dot(const float* a, const float* b, int n, int lane) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) prologue_kernel(const __gr
             *reinterpret_cast<uint32_t*>(dst + (uint64_t)kh * p.Bpad * 128) = lo;
             l0 = __uint_as_float(lo << 16); l1 = __uint_as_float(lo & 0xffff0000u);
           }
-          sq = fmaf(r0, r0 + 2.f * l0, fmaf(r1, r1 + 2.f * l1, sq));      // = tile_product(x, x) (no lo * lo term)
+          sq = fmaf(r0 + l0, r0 + l0, fmaf(r1 + l1, r1 + l1, sq));        // = tile_sq(x)
         }
         sq = warp_sum(sq);
         if (lane == 0) reinterpret_cast<float*>(ws + p.sq_off)[(uint64_t)t * p.Bpad + it] = sq;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
         float sq = 0.f;
 #pragma unroll
         for (int e = 0; e < VW; ++e) {
-          sq += tile_product(PREC, sh[e], sh[e]) + tile_product(PREC, pr[e], pr[e]);
+          sq += tile_sq(PREC, sh[e]) + tile_sq(PREC, pr[e]);
         }
         sq = warp_sum(sq);
         if (lane < pw.world) reinterpret_cast<float*>(pw.ws[lane] + p.sq_off)[(uint64_t)t * p.Bpad + i] = sq;

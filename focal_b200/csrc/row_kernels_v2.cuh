@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(1024, 1) prologue_v2_kernel(const __grid_const
       q4[3] = fmaf(sh[e], pr[e], q4[3]);
       rsh[e] = op_round_t<PREC>(sh[e]);
       rpr[e] = op_round_t<PREC>(pr[e]);
-      q4[2] += tile_product(PREC, sh[e], sh[e]) + tile_product(PREC, pr[e], pr[e]);
+      q4[2] += tile_sq(PREC, sh[e]) + tile_sq(PREC, pr[e]);
     }
     warp_sum_n<4>(q4);
     na = q4[0]; nb = q4[1];

@@ -19,7 +19,12 @@ def main():
     shapes = ((8192, 256, ("seismic", "audio"), 0.5, 4), (4096, 256, ("acc", "gyr", "mag"), 0.07, 4),
               (1024, 256, ("seismic", "audio"), 0.5, 4), (2048, 128, ("seismic", "audio"), 0.5, 4),
               (128, 128, ("seismic", "audio"), 0.5, 4))
+    modes = [m for m in os.environ.get("FB_MODES", "fp32,bf16").split(",") if m]
+    if os.environ.get("FB_SHAPES"):
+        shapes = shapes[:int(os.environ["FB_SHAPES"])]
     for prec, pname in ((_cabi.FOCAL_PREC_FP32, "fp32"), (_cabi.FOCAL_PREC_BF16, "bf16")):
+        if pname not in modes:
+            continue
         be = CudaBackend(precision=prec)
         report(be, pname, shapes)
     print("tolerances (BASELINE.json north_star): loss 1e-4; gradients 2e-3 (fp32 mode: split-bf16 tiles) / 1e-2 (bf16 mode)")
@@ -39,8 +44,11 @@ def report(be, pname, shapes):
             rg = [ref.grads1[m] for m in mods] + [ref.grads2[m] for m in mods]
             lerr = abs(float(loss5[0]) - float(ref.loss)) / abs(float(ref.loss))
             gerr = [float((g.double() - r.cuda()).norm() / r.cuda().norm()) for g, r in zip(grads, rg)]
+            perr = [abs(float(loss5[1 + k]) - float(ref.parts[n])) / max(abs(float(ref.parts[n])), 1e-30)
+                    for k, n in enumerate(("shared", "private", "orth", "temporal"))]
             print(f"{pname}  B={B:5d} M={len(mods)} S={S} D={D:3d} T={T:<4}  {gen:10s}  {lerr:.2e}       "
-                  + " ".join(f"{e:.2e}" for e in gerr), flush=True)
+                  + " ".join(f"{e:.2e}" for e in gerr) + "   | parts (shared private orth temporal): "
+                  + " ".join(f"{e:.1e}" for e in perr), flush=True)
 
 
 if __name__ == "__main__":
