@@ -211,6 +211,88 @@ extern "C" int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// bring-up micro-benchmark: the tensor-pipe schedule of one column tile of the fused temporal kernel, without any
+// epilogue: UMMA #1 = 16 x (SS, N = BN, K-major B) into S stage (tile & 1), UMMA #2 = BN/16 x (TS, N = 256, MN-major
+// B, A from the S stage) into the O accumulator at column 0.  mode 0: #1 and #2 alternate tile by tile (what the
+// kernel issues); 1: only #1; 2: only #2; 3: #1 of two tiles back to back, then #2 of both.  What the pipe itself
+// needs per tile is the ceiling of the kernel's tensor-pipe share.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+template <int BN>
+__global__ void __launch_bounds__(128, 1) umma_tile_rate_kernel(uint32_t iters, uint32_t mode, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t o = threadIdx.x * 16; o < 64 * 1024 + 64 * 1024; o += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(smem + o) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  if (__shfl_sync(0xffffffffu, warp, 0) == 0) {
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 64 * 1024);
+    constexpr uint32_t idesc1 = umma_idesc(UMMA_BF16, 128, BN, 0, 0);
+    constexpr uint32_t idesc2 = umma_idesc(UMMA_BF16, 128, 256, 0, 1);
+    const uint64_t da0 = umma_smem_desc(a_addr, 16, 1024);
+    const uint64_t db0 = umma_smem_desc(b_addr, 16, 1024);
+    const uint64_t dm0 = umma_smem_desc(b_addr, BN * 128, 1024);
+    auto u1 = [&](uint32_t tile) {
+      const uint32_t d = tmem_u + 256 + (tile & 1) * BN;
+#pragma unroll
+      for (uint32_t k = 0; k < 16; ++k)
+        umma_bf16(d, da0 + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), db0 + (((k >> 2) * (BN * 128) + (k & 3) * 32) >> 4),
+                  idesc1, k > 0);
+    };
+    auto u2 = [&](uint32_t tile) {
+      const uint32_t a = tmem_u + 256 + (tile & 1) * BN;
+#pragma unroll
+      for (uint32_t k = 0; k < BN / 16; ++k) umma_bf16_ts(tmem_u, a + k * 16, dm0 + ((k * 2048) >> 4), idesc2, 1u);
+    };
+    const long long t0 = clock64();
+    for (uint32_t it = 0; it < iters; it += 2) {
+      if (elect_one()) {
+        if (mode == 0) { u1(it); u2(it); u1(it + 1); u2(it + 1); }
+        else if (mode == 1) { u1(it); u1(it + 1); }
+        else if (mode == 2) { u2(it); u2(it + 1); }
+        else { u1(it); u1(it + 1); u2(it); u2(it + 1); }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_u, 512);
+}
+}  // namespace
+
+extern "C" int focal_b200_debug_umma_tile_rate(uint32_t BN, uint32_t mode, uint32_t iters, uint32_t grid, long long* cycles,
+                                               void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t smem = 64 * 1024 + 64 * 1024 + 1024;
+#define FB_TILE_RATE(NN)                                                                                        \
+  if (BN == NN) {                                                                                               \
+    auto k = umma_tile_rate_kernel<NN>;                                                                         \
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)         \
+      return cuda_ok("cudaFuncSetAttribute(umma_tile_rate_kernel)");                                            \
+    k<<<grid, 128, smem, st>>>(iters & ~1u, mode, cycles);                                                      \
+    return cuda_ok("umma_tile_rate_kernel");                                                                    \
+  }
+  FB_TILE_RATE(64) FB_TILE_RATE(80) FB_TILE_RATE(96) FB_TILE_RATE(128)
+#undef FB_TILE_RATE
+  return FOCAL_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // bring-up micro-benchmark: L2 -> shared-memory throughput of linear bulk copies (cp.async.bulk) per SM
 // ---------------------------------------------------------------------------------------------------------
 namespace {

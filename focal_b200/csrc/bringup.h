@@ -16,6 +16,10 @@ int focal_b200_debug_umma(const void* a_img, uint32_t a_bytes, const void* b_img
 /* cycles per tcgen05.mma for a given N / operand placement / per-tile barrier traffic */
 int focal_b200_debug_umma_rate(uint32_t N, uint32_t flags, uint32_t iters, uint32_t sync_mode, uint32_t grid,
                                long long* cycles, void* stream);
+/* tensor-pipe time of one column tile of the fused temporal kernel (16 SS MMAs of N = BN, then BN/16 TS MMAs of N = 256),
+ * no epilogue; mode 0 = alternating as the kernel issues them, 1 = only #1, 2 = only #2, 3 = two tiles batched */
+int focal_b200_debug_umma_tile_rate(uint32_t BN, uint32_t mode, uint32_t iters, uint32_t grid, long long* cycles,
+                                    void* stream);
 /* per-SM throughput of linear TMA bulk copies */
 int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, uint32_t copy_bytes, uint32_t copies_per_stage,
                               uint32_t stages, uint32_t iters, uint32_t grid, long long* cycles, void* stream);

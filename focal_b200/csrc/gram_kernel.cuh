@@ -61,6 +61,14 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_EPI_UNROLL
 #define FB_EPI_UNROLL 1         // 2: two chunks of one thread's share of a tile are in flight together
 #endif
+#ifndef FB_EPI_HALF_CHUNKS
+#define FB_EPI_HALF_CHUNKS 1    // see GramCfg::kHalfChunks
+#endif
+#ifndef FB_EPI_PIPE
+#define FB_EPI_PIPE 0           // 1: one warpgroup per tile (narrow operands): software-pipelined tcgen05.ld, see FB_RUN_TILE.
+                                // Measured (profiles/r2_variants.txt): row sums 88.5 -> 101.1 us, gradient pass 138.2 -> 142.3 us
+                                // (the second register set spills at the 96 / 128 registers these kernels have): off
+#endif
 #ifndef FB_EPI_ROTATE
 #define FB_EPI_ROTATE 1         // shared stages: rotate the chunk -> warpgroup assignment from tile to tile (see run_tile)
 #endif
@@ -119,6 +127,12 @@ struct GramCfg {
   static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? (kShareAll ? FB_KB4_SHARE_NW : FB_KB4_NW) : (KB == 8 ? FB_KB8_NW : 1));   // warpgroups per tile
   static constexpr int NG = kShareAll ? NW : NS * NW;                            // epilogue warpgroups in total
   static constexpr int CW = (NG >= 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
+  // kHalfChunks (bf16 shared stages, 6 chunks of 16 columns over 4 warpgroups): every warpgroup takes one 16-column chunk
+  // plus one 8-column half of chunks 4 / 5 -- 24 columns each -- instead of {2, 2, 1, 1} whole chunks: the epilogue latency
+  // of a tile, which is on the critical path of each S stage's UMMA #1 -> epilogue -> UMMA #2 chain, drops from two chunk
+  // times to one and a half.  The W of a split chunk k sits at packed columns [16k + 4, 16k + 12): both halves stay
+  // inside the S columns their own warpgroup consumed, and the 8 columns of the K step remain contiguous.
+  static constexpr bool kHalfChunks = kShareAll && EL == 0 && NW == 4 && CW == 16 && BN == 96 && SEQ <= 8 && FB_EPI_HALF_CHUNKS != 0;
   static constexpr int kThreads = 64 + 128 * NG;
   static_assert(NG <= 6, "partial-sum arrays are sized for <= 6 epilogue warpgroups");
   static constexpr int kOKB = kWide ? 4 : KB;        // K blocks of the O accumulator (wide mode: one half per pass)
@@ -431,7 +445,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                   if constexpr (!kSplit) {
 #pragma unroll
                     for (int k = 0; k < BN / 16; ++k)
-                      umma_bf16_ts(tmem + kOCol, a + k * kWStep, dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
+                      umma_bf16_ts(tmem + kOCol, a + k * kWStep + ((G::kHalfChunks && k >= NW) ? 4 : 0),
+                                   dm + (uint64_t)((k * 2048) >> 4), idesc2, k > 0 ? 1u : acc);
                   } else {
                     // split tiles: chunk c of CW columns holds [W_hi pairs | W_lo pairs]; O += Wh Xh + Wh Xl + Wl Xh
                     constexpr uint64_t lo_img = (uint64_t)((kKH * (BN * 128)) >> 4);
@@ -548,24 +563,27 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         // One chunk of CW columns.  EDGE = the tile touches the (block) diagonal, the padded tail of the columns, or the
         // sequences are padded (seq_len not a power of two): only those tiles pay for the per-pair validity logic;
         // interior tiles -- nearly all of them -- run the short path.
-        auto chunk_body = [&](auto edge_c, int ch, auto& v) {
+        // coff: first column of the chunk within the tile; its width W comes with the register array; wcol: TMEM column
+        // (relative to the S stage) where the chunk's W goes
+        auto chunk_body = [&](auto edge_c, int coff, auto& v, int wcol) {
           constexpr bool EDGE = decltype(edge_c)::value;
-          const int cbase = col0 + ch * CW;           // column (within side) of v[0]
+          constexpr int W = (int)(sizeof(v) / sizeof(float));
+          const int cbase = col0 + coff;              // column (within side) of v[0]
           if constexpr (kIsNce) {
             if (EDGE && ptile) {
 #pragma unroll
-              for (int j = 0; j < CW; ++j)
+              for (int j = 0; j < W; ++j)
                 if (cbase + j == row) { posg = v[j]; pos_seen = true; }
             }
             // ---------------- InfoNCE: E = 2^G (logits arrive pre-scaled to the log2 domain)
 #pragma unroll
-            for (int j = 0; j < CW; ++j)
+            for (int j = 0; j < W; ++j)
               v[j] = ((j & 7) >= 8 - (MODE == NCE_FWD ? FB_POLY_FWD_PER8 : FB_POLY_PER8)) ? ex2_poly(v[j]) : ex2_approx(v[j]);
             if (MODE == NCE_BWD) {
               // W_kj = E_kj (1/r_k + 1/r_j)  ==  P_kj + P_jk  
 #pragma unroll
-              for (int j = 0; j < CW; j += 4) {
-                const float4 cj = lds128(cv + (ch * CW + j) * 4);
+              for (int j = 0; j < W; j += 4) {
+                const float4 cj = lds128(cv + (coff + j) * 4);
                 float c0, c1, c2, c3;
                 add2(c0, c1, cj.x, cj.y, ck, ck);
                 add2(c2, c3, cj.z, cj.w, ck, ck);
@@ -575,29 +593,29 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
             }
             if (EDGE) {
 #pragma unroll
-              for (int j = 0; j < CW; ++j) {
+              for (int j = 0; j < W; ++j) {
                 const int col = cbase + j;
                 if ((diag && col == row) || col >= ncol_valid) v[j] = 0.f;
               }
             }
             if (MODE == NCE_FWD) {
 #pragma unroll
-              for (int j = 0; j < CW; j += 4) {
+              for (int j = 0; j < W; j += 4) {
                 add2(racc[0], racc[1], racc[0], racc[1], v[j], v[j + 1]);
                 add2(racc[2], racc[3], racc[2], racc[3], v[j + 2], v[j + 3]);
               }
             }
           } else {
             // ---------------- temporal: delta_ij, S x S block means, hinge, r_ij
-            float nj[CW];
+            float nj[W];
 #pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-              const float4 t4 = lds128(cv + (ch * CW + j) * 4);
+            for (int j = 0; j < W; j += 4) {
+              const float4 t4 = lds128(cv + (coff + j) * 4);
               add2(nj[j], nj[j + 1], t4.x, t4.y, n_i, n_i);
               add2(nj[j + 2], nj[j + 3], t4.z, t4.w, n_i, n_i);
             }
 #pragma unroll
-            for (int g0 = 0; g0 < CW; g0 += SQ) {
+            for (int g0 = 0; g0 < W; g0 += SQ) {
               float gsum = 0.f;
 #pragma unroll
               for (int j = 0; j < SQ; j += 2) {
@@ -620,7 +638,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
               for (int o = 1; o < SQ; o <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
               const float mm = fmaf(gsum, inv_cnt, -margin);            // m_IJ - margin
               const float h = mim - mm;                                 // hinge argument (mim = m_II; -1e30 on rows that are not ok)
-              const float hj = lds32(cv + (BN + ch * CW + g0) * 4) - mm;   // ... of the transposed pair: m_JJ + margin - m_IJ
+              const float hj = lds32(cv + (BN + coff + g0) * 4) - mm;   // ... of the transposed pair: m_JJ + margin - m_IJ
               bool a_ij = h >= 0.f, a_ji = hj >= 0.f;                   // active at equality
               if (EDGE) {
                 const int colg = cbase + g0;
@@ -630,8 +648,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                 a_ij = a_ij && pair_ok;
                 a_ji = a_ji && pair_ok;
               }
-              if (a_ij) { hinge_acc += h; ++cnt_i; }
-              const float coef = a_ij ? (a_ji ? coef2 : coef1) : (a_ji ? coef1 : 0.f);
+              // branch-free on purpose: a branch per group ends the basic block, and the groups of a chunk then run one
+              // after the other instead of interleaved (coef2 == 2 coef1 exactly, so the sum of the two selects is exact)
+              hinge_acc += a_ij ? h : 0.f;
+              cnt_i += a_ij ? 1 : 0;
+              const float coef = (a_ij ? coef1 : 0.f) + (a_ji ? coef1 : 0.f);
 #pragma unroll
               for (int j = 0; j < SQ; j += 2) {
                 mul2(v[g0 + j], v[g0 + j + 1], v[g0 + j], v[g0 + j + 1], coef, coef);
@@ -642,52 +663,80 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           if (kBwd) {
             if (kSplit) {
               // ---------------- W chunk, split: [hi pairs | lo pairs] over the CW columns this chunk came from
-              uint32_t wv[CW];
+              uint32_t wv[W];
 #pragma unroll
-              for (int j = 0; j < CW / 2; ++j) {
+              for (int j = 0; j < W / 2; ++j) {
                 const uint32_t hi = pack_bf16x2(v[2 * j], v[2 * j + 1]);
                 wv[j] = hi;
-                wv[CW / 2 + j] = pack_bf16x2(v[2 * j] - __uint_as_float(hi << 16), v[2 * j + 1] - __uint_as_float(hi & 0xffff0000u));
+                wv[W / 2 + j] = pack_bf16x2(v[2 * j] - __uint_as_float(hi << 16), v[2 * j + 1] - __uint_as_float(hi & 0xffff0000u));
               }
-              tmem_st_full<CW>(s_addr + ch * CW, wv);
+              if constexpr (W >= 16) tmem_st_full<W>(s_addr + wcol, wv);
             } else {
               // ---------------- W chunk: packed bf16 over the S columns this thread has already consumed
-              uint32_t pk[CW / 2];
+              uint32_t pk[W / 2];
 #pragma unroll
-              for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-              tmem_st_packed<CW>(s_addr + ch * (NW > 1 ? CW : CW / 2), pk);
+              for (int j = 0; j < W / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              tmem_st_packed<W>(s_addr + wcol, pk);
             }
           }
         };
         // Shared stages whose chunk count is not a multiple of the warpgroup count (96 columns = 6 chunks over 4
         // warpgroups): rotate the assignment from tile to tile so that every warpgroup does 3 chunks per two tiles
         // instead of {2, 2, 1, 1} on every tile (the warpgroups move on to the next tile independently).
-        const int sub_t = (kShareAll && FB_EPI_ROTATE && (BN / CW) % NW != 0) ? ((sub + (int)(n & 1) * (NW / 2)) & (NW - 1)) : sub;
+        const int sub_t = (kShareAll && !G::kHalfChunks && FB_EPI_ROTATE && (BN / CW) % NW != 0) ? ((sub + (int)(n & 1) * (NW / 2)) & (NW - 1)) : sub;
         // FB_EPI_UNROLL == 2: two chunks of this thread in flight together: twice the independent work behind each
         // tcgen05.ld / MUFU / shuffle latency
+#define FB_WCOL(ch) ((ch) * (kSplit ? CW : (NW > 1 ? CW : CW / 2)))
 #define FB_RUN_TILE(EDGE_TAG)                                                        \
   {                                                                                  \
-    int ch = sub_t;                                                                  \
-    if constexpr (FB_EPI_UNROLL == 2) {                                              \
-      _Pragma("unroll 1") for (; ch + NW < BN / CW; ch += 2 * NW) {                  \
-        float v0[CW], v1[CW];                                                        \
-        tmem_ld_chunk<CW>(s_addr + ch * CW, v0);                                     \
-        tmem_ld_chunk<CW>(s_addr + (ch + NW) * CW, v1);                              \
-        tmem_ld_wait();                                                              \
-        chunk_body(EDGE_TAG, ch, v0);                                                \
-        chunk_body(EDGE_TAG, ch + NW, v1);                                           \
-      }                                                                              \
-    }                                                                                \
-    _Pragma("unroll 1") for (; ch < BN / CW; ch += NW) {                             \
-      float v[CW];                                                                   \
-      tmem_ld_chunk<CW>(s_addr + ch * CW, v);                                        \
+    if constexpr (G::kHalfChunks) {                                                  \
+      /* chunk `sub` whole + one half of chunk 4 / 5 (24 columns per warpgroup) */   \
+      const int hoff = (NW + (sub >> 1)) * CW + (sub & 1) * (CW / 2);                \
+      float v0[CW], v1[CW / 2];                                                      \
+      tmem_ld_chunk<CW>(s_addr + sub * CW, v0);                                      \
+      tmem_ld_chunk<CW / 2>(s_addr + hoff, v1);                                      \
       tmem_ld_wait();                                                                \
-      chunk_body(EDGE_TAG, ch, v);                                                   \
+      chunk_body(EDGE_TAG, sub * CW, v0, sub * CW);                                  \
+      chunk_body(EDGE_TAG, hoff, v1, (NW + (sub >> 1)) * CW + 4 + (sub & 1) * 4);    \
+    } else if constexpr (NW == 1 && FB_EPI_PIPE != 0) {                              \
+      /* one warpgroup per tile: the tcgen05.ld of chunk c + 1 is in flight while chunk c is computed */ \
+      constexpr int kCh = BN / CW;                                                   \
+      float va[CW], vb[CW];                                                          \
+      tmem_ld_chunk<CW>(s_addr, va);                                                 \
+      _Pragma("unroll") for (int ch = 0; ch < kCh; ch += 2) {                        \
+        tmem_ld_wait();                                                              \
+        if (ch + 1 < kCh) tmem_ld_chunk<CW>(s_addr + (ch + 1) * CW, vb);             \
+        chunk_body(EDGE_TAG, ch * CW, va, FB_WCOL(ch));                              \
+        if (ch + 1 < kCh) {                                                          \
+          tmem_ld_wait();                                                            \
+          if (ch + 2 < kCh) tmem_ld_chunk<CW>(s_addr + (ch + 2) * CW, va);           \
+          chunk_body(EDGE_TAG, (ch + 1) * CW, vb, FB_WCOL(ch + 1));                  \
+        }                                                                            \
+      }                                                                              \
+    } else {                                                                         \
+      int ch = sub_t;                                                                \
+      if constexpr (FB_EPI_UNROLL == 2) {                                            \
+        _Pragma("unroll 1") for (; ch + NW < BN / CW; ch += 2 * NW) {                \
+          float v0[CW], v1[CW];                                                      \
+          tmem_ld_chunk<CW>(s_addr + ch * CW, v0);                                   \
+          tmem_ld_chunk<CW>(s_addr + (ch + NW) * CW, v1);                            \
+          tmem_ld_wait();                                                            \
+          chunk_body(EDGE_TAG, ch * CW, v0, FB_WCOL(ch));                            \
+          chunk_body(EDGE_TAG, (ch + NW) * CW, v1, FB_WCOL(ch + NW));                \
+        }                                                                            \
+      }                                                                              \
+      _Pragma("unroll 1") for (; ch < BN / CW; ch += NW) {                           \
+        float v[CW];                                                                 \
+        tmem_ld_chunk<CW>(s_addr + ch * CW, v);                                      \
+        tmem_ld_wait();                                                              \
+        chunk_body(EDGE_TAG, ch * CW, v, FB_WCOL(ch));                               \
+      }                                                                              \
     }                                                                                \
   }
         if (diag || tail || padseq || (kIsNce && ptile)) FB_RUN_TILE(std::true_type{})
         else FB_RUN_TILE(std::false_type{})
 #undef FB_RUN_TILE
+#undef FB_WCOL
         FB_TRACE_EV(2 + wgi, n, 2);
         if (kBwd) {
           tmem_st_wait();

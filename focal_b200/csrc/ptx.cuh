@@ -156,6 +156,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // registers -> TMEM: thread t of the warp writes lane (base_lane + t), 32 / 16 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -168,6 +177,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
@@ -185,12 +199,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 
 template <int CW>
 __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, float (&v)[CW]) {
-  static_assert(CW == 16 || CW == 32, "chunk width");
-  if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+  static_assert(CW == 8 || CW == 16 || CW == 32, "chunk width");
+  if constexpr (CW == 32) tmem_ld32(taddr, v); else if constexpr (CW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
 }
 template <int CW>
 __device__ __forceinline__ void tmem_st_packed(uint32_t taddr, const uint32_t (&r)[CW / 2]) {
-  if constexpr (CW == 32) tmem_st16(taddr, r); else tmem_st8(taddr, r);
+  if constexpr (CW == 32) tmem_st16(taddr, r); else if constexpr (CW == 16) tmem_st8(taddr, r); else tmem_st4(taddr, r);
 }
 template <int CW>
 __device__ __forceinline__ void tmem_st_full(uint32_t taddr, const uint32_t (&r)[CW]) {

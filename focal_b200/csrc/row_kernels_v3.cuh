@@ -33,6 +33,17 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float f4_get(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
 
+// Blocks per SM ahead whose feature rows a block prefetches into L2 (0 = off).  Measured (profiles/r2_variants.txt): 0 / 2 /
+// 4 ahead = 44.8 / 44.6 / 44.7 us prologue, 65.3 / 67.0 / 67.2 us finalize: the first-phase latency is not what bounds
+// either kernel, so it stays off.
+#ifndef FB_ROW_PF_AHEAD
+#define FB_ROW_PF_AHEAD 0
+#endif
+// Start moving [p, p + bytes) (16-byte aligned, a multiple of 16) towards L2: no register, no scoreboard.
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // reduce N values over the LPR lanes of a row group (all lanes of the group end up with the sums); butterflies interleaved
 template <int LPR, int N>
 __device__ __forceinline__ void group_sum_n(float (&v)[N]) {
@@ -115,6 +126,11 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
     for (int k = 0; k < NQ; ++k) sh[k] = ldg4(src + 4 * (k * LPR + l));
 #pragma unroll
     for (int k = 0; k < NQ; ++k) pr[k] = ldg4(src + d + 4 * (k * LPR + l));
+    // the (sequence, tensor) that the block taking this SM slot next will read: start it towards L2 now
+    if (FB_ROW_PF_AHEAD) {
+      const int In = I + FB_ROW_PF_AHEAD * p.num_sms * seqb;
+      if (In < I1 && lane == 0) prefetch_l2(feat_base(p, f, ws, t) + feat_row_off(p, In * S), (uint32_t)(S * p.D * 4));
+    }
     // ---- rounded rows (what the temporal tiles see), norms, shared . private
     uint2 hsh[NQ], lsh[NQ], hpr[NQ], lpr[NQ];
     float q4[4] = {0.f, 0.f, 0.f, 0.f};                       // |shared|^2, |private|^2, |rounded row|^2 (tile product), shared . private
@@ -287,8 +303,11 @@ __device__ __forceinline__ float4 ld_op4(const uint8_t* op, uint64_t lo_img, uin
 // finalize: gradient rows of one (sequence, tensor) = temporal part + the InfoNCE operands of the tensor + its
 // orthogonality pairs
 // ---------------------------------------------------------------------------------------------------------
+#ifndef FB_FIN_MINBLOCKS
+#define FB_FIN_MINBLOCKS 2
+#endif
 template <int S, int NQ, int PREC>
-__global__ void __launch_bounds__(256, 2) finalize_v3_kernel(const __grid_constant__ Plan p,
+__global__ void __launch_bounds__(256, FB_FIN_MINBLOCKS) finalize_v3_kernel(const __grid_constant__ Plan p,
                                                              const __grid_constant__ FeatPtrs f,
                                                              const __grid_constant__ GradPtrs gp,
                                                              const uint8_t* __restrict__ ws) {
@@ -312,6 +331,43 @@ __global__ void __launch_bounds__(256, 2) finalize_v3_kernel(const __grid_consta
 #pragma unroll
     for (int k = 0; k < NQ; ++k) pr[k] = ldg4(src + d + 4 * (k * LPR + l));
     const float2 n2 = __ldg(reinterpret_cast<const float2*>(ws + p.nrm_off + ((uint64_t)t * p.Bpad + i) * 8));
+    if (FB_ROW_PF_AHEAD) {        // feature rows of the block that takes this SM slot next
+      const int In = I + FB_ROW_PF_AHEAD * p.num_sms * seqb;
+      if (In < p.seq1 && lane == 0) prefetch_l2(feat_base(p, f, ws, t) + feat_row_off(p, In * S), (uint32_t)(S * p.D * 4));
+    }
+    // ---- The phases below read the accumulator rows of this (sequence, tensor) one after the other, and some of those
+    // reads depend on flags (how many stream-K pieces a row block has): a chain of DRAM round trips per warp, which is what
+    // bounded this kernel (ncu: 25 % issue-active, long-scoreboard stalls, 2.4 TB/s).  So, while the feature rows are in
+    // flight, ask for everything else to be brought to L2: the later phases then run at L2 latency.
+    if ((p.terms & FOCAL_TERM_TEMPORAL) && p.b > 1 && S > 1) {
+      const int Dp = p.kbFull * p.epb;
+      const uint64_t t0 = (uint64_t)t * p.Bpad + (uint64_t)I * S;                 // the S rows of the sequence are adjacent
+      const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_tmp_off) + (uint64_t)t * (p.Bpad / kTileM) + i / kTileM);
+      if (lane == 0) {
+        prefetch_l2(ws + p.dx_off + t0 * Dp * 4, (uint32_t)(S * Dp * 4));
+        for (int e = 1; e <= extra; ++e) prefetch_l2(ws + p.dx_off + e * p.dx2_delta + t0 * Dp * 4, (uint32_t)(S * Dp * 4));
+      }
+    }
+    if (p.terms & FOCAL_TERM_NCE) {
+      const uint64_t rowN = (uint64_t)g * p.bpad + I, rowsNce = (uint64_t)S * p.bpad;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const OpDesc& op = p.ops[2 * t + half];
+        const int wp = op.kb * p.epb;
+        for (int u = 0; u < op.nuse; ++u) {
+          const int qp = op.use_prob[u], side = op.use_side[u];
+          const OpDesc& po = p.ops[op.use_partner[u]];
+          const uint64_t arow = ((uint64_t)side * S * p.bpad + rowN) * wp;
+          const uint64_t fidx = ((uint64_t)qp * S + g) * 2 + side;
+          const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_nce_off) + fidx * (p.bpad / kTileM) + I / kTileM);
+          if (l == 0) {
+            prefetch_l2(ws + p.probs[qp].dz_off + arow * 4, (uint32_t)(wp * 4));
+            for (int e = 1; e <= extra; ++e) prefetch_l2(ws + p.probs[qp].dz_off + e * p.dz2_delta + arow * 4, (uint32_t)(wp * 4));
+          }
+          if (l >= 1 && l <= po.kb) prefetch_l2(ws + po.off + ((uint64_t)(l - 1) * rowsNce + rowN) * 128, 128u);
+        }
+      }
+    }
     na = n2.x; nb = n2.y;
     if (orth_on && p.M > 1) {
       float* mine = prv + ((size_t)(q * nT + t) * S + g) * d;
@@ -385,16 +441,18 @@ __global__ void __launch_bounds__(256, 2) finalize_v3_kernel(const __grid_consta
     }
   }
 
-  // ---- InfoNCE: operands 2t (shared half) and 2t + 1 (private half) of this tensor
+  // ---- InfoNCE: operands 2t (shared half) and 2t + 1 (private half) of this tensor, one half at a time.  All loads of
+  // a phase are issued together (the accumulator row, the positive-pair operand row; then the rows of the secondary
+  // stream-K pieces): loads inside data-dependent loops would go out one round trip at a time.
   if (p.terms & FOCAL_TERM_NCE) {
     const uint64_t rowN = (uint64_t)g * p.bpad + I, rowsNce = (uint64_t)S * p.bpad;
     const float inv_tsn = 1.f / (p.T * (float)S * (float)(2 * p.b));
     const float inv_alpha = 1.f / p.alpha;
-    float4 tmp[2][NQ];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
+      float4 tmp[NQ];
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) tmp[half][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < NQ; ++k) tmp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       const OpDesc& op = p.ops[2 * t + half];
       const int wp = op.kb * p.epb;
       for (int u = 0; u < op.nuse; ++u) {
@@ -409,46 +467,51 @@ __global__ void __launch_bounds__(256, 2) finalize_v3_kernel(const __grid_consta
         const int extra = __ldg(reinterpret_cast<const int32_t*>(ws + p.flag_nce_off) + fidx * (p.bpad / kTileM) + I / kTileM);
         const float* rs = reinterpret_cast<const float*>(ws + p.rsum_off) + ((uint64_t)(qp * S + g) * 2) * p.bpad;
         const float r_k = __ldg(rs + (uint64_t)side * p.bpad + I), r_p = __ldg(rs + (uint64_t)(1 - side) * p.bpad + I);
+        const float gpos = __ldg(reinterpret_cast<const float*>(ws + p.pos_off) + fidx * p.bpad + I);
+        float4 acc[NQ], zp[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) acc[k] = ldg4(accp + 4 * (k * LPR + l));
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) zp[k] = ld_op4<PREC>(pop, lo_img, op_off8(rowsNce, rowN, 4 * (k * LPR + l)));
+        for (int e = 1; e <= extra; ++e) {
+          const float* acc2 = reinterpret_cast<const float*>(ws + prb.dz_off + e * p.dz2_delta) + arow;
+          float4 a2[NQ];
+#pragma unroll
+          for (int k = 0; k < NQ; ++k) a2[k] = ldg4(acc2 + 4 * (k * LPR + l));
+#pragma unroll
+          for (int k = 0; k < NQ; ++k) { acc[k].x += a2[k].x; acc[k].y += a2[k].y; acc[k].z += a2[k].z; acc[k].w += a2[k].w; }
+        }
         // positive column in fp32 (masked out of the tiles): W_kp - 2 is a tiny difference when the positive dominates;
         // its logit is the one the row-sum tile of this row saw
-        const float gpos = __ldg(reinterpret_cast<const float*>(ws + p.pos_off) + fidx * p.bpad + I);
         const float wkp2 = ex2_approx(gpos) * (__frcp_rn(r_k) + __frcp_rn(r_p)) - 2.f;
         const float wq = prb.weight * inv_tsn * inv_alpha;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
-          const int c = 4 * (k * LPR + l);
-          float4 acc = ldg4(accp + c);
-          for (int e = 1; e <= extra; ++e) {
-            const float4 a2 = ldg4(reinterpret_cast<const float*>(ws + prb.dz_off + e * p.dz2_delta) + arow + c);
-            acc.x += a2.x; acc.y += a2.y; acc.z += a2.z; acc.w += a2.w;
-          }
-          const float4 zp = ld_op4<PREC>(pop, lo_img, op_off8(rowsNce, rowN, c));
-          tmp[half][k].x = fmaf(wq, fmaf(wkp2, zp.x, acc.x), tmp[half][k].x);
-          tmp[half][k].y = fmaf(wq, fmaf(wkp2, zp.y, acc.y), tmp[half][k].y);
-          tmp[half][k].z = fmaf(wq, fmaf(wkp2, zp.z, acc.z), tmp[half][k].z);
-          tmp[half][k].w = fmaf(wq, fmaf(wkp2, zp.w, acc.w), tmp[half][k].w);
+          tmp[k].x = fmaf(wq, fmaf(wkp2, zp[k].x, acc[k].x), tmp[k].x);
+          tmp[k].y = fmaf(wq, fmaf(wkp2, zp[k].y, acc[k].y), tmp[k].y);
+          tmp[k].z = fmaf(wq, fmaf(wkp2, zp[k].z, acc[k].z), tmp[k].z);
+          tmp[k].w = fmaf(wq, fmaf(wkp2, zp[k].w, acc[k].w), tmp[k].w);
         }
       }
-    }
-    float dots[2] = {0.f, 0.f};                         // d zh / d z = (I - zh zh^T) / n
+      // d zh / d z = (I - zh zh^T) / n
+      float dot[1] = {0.f};
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-      dots[0] = fmaf(tmp[0][k].x, sh[k].x, fmaf(tmp[0][k].y, sh[k].y, fmaf(tmp[0][k].z, sh[k].z, fmaf(tmp[0][k].w, sh[k].w, dots[0]))));
-      dots[1] = fmaf(tmp[1][k].x, pr[k].x, fmaf(tmp[1][k].y, pr[k].y, fmaf(tmp[1][k].z, pr[k].z, fmaf(tmp[1][k].w, pr[k].w, dots[1]))));
-    }
-    group_sum_n<LPR, 2>(dots);
-    const float ia = fminf(rsqrtf(na), 1.f / kNceEps), ib = fminf(rsqrtf(nb), 1.f / kNceEps);      // 1 / max(|z|, eps)
-    const float da = dots[0] * ia * ia, db = dots[1] * ib * ib;
+      for (int k = 0; k < NQ; ++k) {
+        const float4 xk = half ? pr[k] : sh[k];
+        dot[0] = fmaf(tmp[k].x, xk.x, fmaf(tmp[k].y, xk.y, fmaf(tmp[k].z, xk.z, fmaf(tmp[k].w, xk.w, dot[0]))));
+      }
+      group_sum_n<LPR, 1>(dot);
+      const float inrm = fminf(rsqrtf(half ? nb : na), 1.f / kNceEps);     // 1 / max(|z|, eps)
+      const float dd = dot[0] * inrm * inrm;
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-      gsh[k].x = fmaf(fmaf(-da, sh[k].x, tmp[0][k].x), ia, gsh[k].x);
-      gsh[k].y = fmaf(fmaf(-da, sh[k].y, tmp[0][k].y), ia, gsh[k].y);
-      gsh[k].z = fmaf(fmaf(-da, sh[k].z, tmp[0][k].z), ia, gsh[k].z);
-      gsh[k].w = fmaf(fmaf(-da, sh[k].w, tmp[0][k].w), ia, gsh[k].w);
-      gpr[k].x = fmaf(fmaf(-db, pr[k].x, tmp[1][k].x), ib, gpr[k].x);
-      gpr[k].y = fmaf(fmaf(-db, pr[k].y, tmp[1][k].y), ib, gpr[k].y);
-      gpr[k].z = fmaf(fmaf(-db, pr[k].z, tmp[1][k].z), ib, gpr[k].z);
-      gpr[k].w = fmaf(fmaf(-db, pr[k].w, tmp[1][k].w), ib, gpr[k].w);
+      for (int k = 0; k < NQ; ++k) {
+        const float4 xk = half ? pr[k] : sh[k];
+        float4& gk = half ? gpr[k] : gsh[k];
+        gk.x = fmaf(fmaf(-dd, xk.x, tmp[k].x), inrm, gk.x);
+        gk.y = fmaf(fmaf(-dd, xk.y, tmp[k].y), inrm, gk.y);
+        gk.z = fmaf(fmaf(-dd, xk.z, tmp[k].z), inrm, gk.z);
+        gk.w = fmaf(fmaf(-dd, xk.w, tmp[k].w), inrm, gk.w);
+      }
     }
   }
 

@@ -67,6 +67,7 @@ def run(B=int(os.environ.get('FB_B', 8192)), D=int(os.environ.get('FB_D', 256)),
             fptr = _cabi.ptr_array([t.data_ptr() for t in feats])
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            torch.cuda._sleep(1_500_000)     # the host enqueues the whole sequence behind this: no launch latency in the stage times
             ev[0].record()
             assert lib.focal_b200_prologue(ref, fptr, wsp, wsn, st) == 0; ev[1].record()
             assert lib.focal_b200_nce_rowsum(ref, wsp, wsn, st) == 0; ev[2].record()
