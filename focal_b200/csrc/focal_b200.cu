@@ -308,11 +308,13 @@ int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uin
   return cuda_ok("prologue_v3_kernel");
 }
 template <int S, int NQ, int PREC>
-int launch_finalize_v3_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, cudaStream_t st) {
+int launch_finalize_v3_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const PeerWs& pw, uint8_t* w, float* loss5,
+                         cudaStream_t st) {
   const size_t smem = row_v3_smem(p);
   if (int rc = ensure_dyn_smem(finalize_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(finalize_v3_kernel)")) return rc;
-  const int grid = (p.seq1 - p.seq0 + p.seqb - 1) / p.seqb;
-  finalize_v3_kernel<S, NQ, PREC><<<grid, 32 * p.seqb * p.nT, smem, st>>>(p, f, g, w);
+  const int grid = (p.seq1 - p.seq0 + p.seqb - 1) / p.seqb + 1;          // + the block that reduces the loss partials
+  finalize_v3_kernel<S, NQ, PREC><<<grid, 32 * p.seqb * p.nT, smem, st>>>(p, f, g, pw, w, loss5, lse_blocks(p, 0),
+                                                                           temporal_degenerate(p) ? 1 : 0);
   return cuda_ok("finalize_v3_kernel");
 }
 #define FB_V3_CASE(FN, SS, QQ, ...)                                                                   \
@@ -337,8 +339,9 @@ int launch_finalize_v3_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, co
 int launch_prologue_v3(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st) {
   FB_V3_DISPATCH(launch_prologue_v3_t, p, f, pw, w, st);
 }
-int launch_finalize_v3(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const uint8_t* w, cudaStream_t st) {
-  FB_V3_DISPATCH(launch_finalize_v3_t, p, f, g, w, st);
+int launch_finalize_v3(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const PeerWs& pw, uint8_t* w, float* loss5,
+                       cudaStream_t st) {
+  FB_V3_DISPATCH(launch_finalize_v3_t, p, f, g, pw, w, loss5, st);
 }
 #undef FB_V3_DISPATCH
 #undef FB_V3_CASE
@@ -426,7 +429,7 @@ int do_finalize(const Plan& p, int no_private, const float* const* feats, float*
     const int rows = (p.seq1 - p.seq0) * p.S;
     const int vw = (p.S == 1 || p.S == 2 || p.S == 4) ? fast_row_vw(p, no_private) : 0;
     if (p.rowgen == 3) {
-      if ((rc = launch_finalize_v3(p, f, g, w, st))) return rc;
+      return launch_finalize_v3(p, f, g, pw, w, loss5, st);           // its last block is the loss reduction
     } else if (vw) {
       if (use_row_v2(vw) && p.nT <= 8) rc = launch_finalize_v2(vw, p, f, g, w, (rows + 3) / 4, st);
       else rc = launch_finalize_fast(vw, p, f, g, w, (rows + 3) / 4, st);

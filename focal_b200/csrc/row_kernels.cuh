@@ -491,36 +491,42 @@ __global__ void __launch_bounds__(32) peer_wait_kernel(const __grid_constant__ P
   peer_wait(pw.ws[pw.rank], p, pw.world, pw.rank);
 }
 
-__global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant__ Plan p,
-                                                          const __grid_constant__ PeerWs pw, uint8_t* __restrict__ ws,
-                                                          float* __restrict__ loss5, int nce_blocks_valid,
-                                                          int temporal_nan) {
+// Sum of the loss partials of every kernel of the step, in double and in a fixed order (bit-reproducible); ranks of a
+// row-sharded job exchange their four sums through peer memory.  Runs in ONE block of any size (all of its threads call
+// it): its own launch (loss_reduce_kernel), or an extra block of finalize_v3_kernel.
+__device__ __forceinline__ void loss_reduce_body(const Plan& p, const PeerWs& pw, uint8_t* __restrict__ ws,
+                                                 float* __restrict__ loss5, int nce_blocks_valid, int temporal_nan) {
   __shared__ double red[256];
+  const int tid = threadIdx.x, nthr = blockDim.x < 256 ? (int)blockDim.x : 256;
   const float* p1 = reinterpret_cast<const float*>(ws + p.part1_off);
   const float* p2 = reinterpret_cast<const float*>(ws + p.part2_off);
   const float* p3 = reinterpret_cast<const float*>(ws + p.part3_off);
   double acc[4] = {0, 0, 0, 0};     // shared, private, orth, temporal
-  for (int k = threadIdx.x; k < p.nblk1; k += 256) {
-    acc[2] += p1[(size_t)k * 4 + 0];
-    acc[0] += p1[(size_t)k * 4 + 1];
-    acc[1] += p1[(size_t)k * 4 + 2];
-  }
-  if (p.terms & FOCAL_TERM_NCE)
-    for (int k = threadIdx.x; k < nce_blocks_valid; k += 256) {
-      acc[0] += p2[(size_t)k * 2 + 0];
-      acc[1] += p2[(size_t)k * 2 + 1];
+  if (tid < nthr) {
+    for (int k = tid; k < p.nblk1; k += nthr) {
+      acc[2] += p1[(size_t)k * 4 + 0];
+      acc[0] += p1[(size_t)k * 4 + 1];
+      acc[1] += p1[(size_t)k * 4 + 2];
     }
-  if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_nan) {
-    const int t0 = (p.seq0 * p.Sp) / kTileM;
-    const int nrt = (p.seq1 * p.Sp + kTileM - 1) / kTileM - t0;
-    for (int k = threadIdx.x; k < p.np_tmp * p.nT * nrt; k += 256) acc[3] += p3[k];
+    if (p.terms & FOCAL_TERM_NCE)
+      for (int k = tid; k < nce_blocks_valid; k += nthr) {
+        acc[0] += p2[(size_t)k * 2 + 0];
+        acc[1] += p2[(size_t)k * 2 + 1];
+      }
+    if ((p.terms & FOCAL_TERM_TEMPORAL) && !temporal_nan) {
+      const int t0 = (p.seq0 * p.Sp) / kTileM;
+      const int nrt = (p.seq1 * p.Sp + kTileM - 1) / kTileM - t0;
+      for (int k = tid; k < p.np_tmp * p.nT * nrt; k += nthr) acc[3] += p3[k];
+    }
   }
   double out[4];
   for (int a = 0; a < 4; ++a) {
-    red[threadIdx.x] = acc[a];
+    for (int k = tid; k < 256; k += blockDim.x) red[k] = 0.0;
+    __syncthreads();
+    if (tid < nthr) red[tid] = acc[a];
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      if (tid < o) red[tid] += red[tid + o];
       __syncthreads();
     }
     out[a] = red[0];
@@ -528,8 +534,8 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant_
   }
   if (pw.world > 1) {
     // all-reduce over the ranks: publish the partial sums of the owned rows, barrier, add them in rank order
-    if ((int)threadIdx.x < pw.world) {
-      double* slot = reinterpret_cast<double*>(pw.ws[threadIdx.x] + p.lossx_off) + pw.rank * 8;
+    if (tid < pw.world) {
+      double* slot = reinterpret_cast<double*>(pw.ws[tid] + p.lossx_off) + pw.rank * 8;
       for (int a = 0; a < 4; ++a) slot[a] = out[a];
     }
     peer_barrier(p, pw);
@@ -540,7 +546,7 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant_
       out[a] = s;
     }
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     if (p.indirect) loss5 = reinterpret_cast<const PtrTable*>(ws + p.ptrs_off)->loss5;
     if (temporal_nan && (p.terms & FOCAL_TERM_TEMPORAL)) out[3] = __longlong_as_double(0x7ff8000000000000LL);
     const double total = (double)p.w_shared * out[0] + (double)p.w_private * out[1] + (double)p.w_orth * out[2] +
@@ -550,6 +556,12 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant_
     double* ld = reinterpret_cast<double*>(ws + p.lossd_off);
     ld[0] = total; ld[1] = out[0]; ld[2] = out[1]; ld[3] = out[2]; ld[4] = out[3];
   }
+}
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const __grid_constant__ Plan p,
+                                                          const __grid_constant__ PeerWs pw, uint8_t* __restrict__ ws,
+                                                          float* __restrict__ loss5, int nce_blocks_valid,
+                                                          int temporal_nan) {
+  loss_reduce_body(p, pw, ws, loss5, nce_blocks_valid, temporal_nan);
 }
 
 }  // namespace fb

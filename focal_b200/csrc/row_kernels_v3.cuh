@@ -310,9 +310,17 @@ template <int S, int NQ, int PREC>
 __global__ void __launch_bounds__(256, FB_FIN_MINBLOCKS) finalize_v3_kernel(const __grid_constant__ Plan p,
                                                              const __grid_constant__ FeatPtrs f,
                                                              const __grid_constant__ GradPtrs gp,
-                                                             const uint8_t* __restrict__ ws) {
+                                                             const __grid_constant__ PeerWs pw,
+                                                             uint8_t* __restrict__ ws, float* __restrict__ loss5,
+                                                             int nce_blocks_valid, int temporal_nan) {
   constexpr int LPR = 32 / S;
   extern __shared__ float smem_f[];
+  // The last block adds up the loss partials of the step (they were all written by earlier launches): the step needs no
+  // separate loss_reduce launch, and on the row-sharded path the ranks' loss exchange overlaps the gradient rows.
+  if (blockIdx.x == gridDim.x - 1) {
+    loss_reduce_body(p, pw, ws, loss5, nce_blocks_valid, temporal_nan);
+    return;
+  }
   const int nT = p.nT, d = p.d, seqb = p.seqb;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int q = warp / nT, t = warp - q * nT;
