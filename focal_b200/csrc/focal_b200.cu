@@ -301,10 +301,10 @@ size_t row_v3_smem(const Plan& p) {
   return ((size_t)p.seqb * p.nT * p.S * p.d + (size_t)p.seqb * p.nT * p.S + (size_t)p.seqb * p.nT) * sizeof(float);
 }
 template <int S, int NQ, int PREC>
-int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st) {
+int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, int pad_blocks, cudaStream_t st) {
   const size_t smem = row_v3_smem(p);
   if (int rc = ensure_dyn_smem(prologue_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(prologue_v3_kernel)")) return rc;
-  prologue_v3_kernel<S, NQ, PREC><<<p.nblk1, 32 * p.seqb * p.nT, smem, st>>>(p, f, pw, w);
+  prologue_v3_kernel<S, NQ, PREC><<<p.nblk1 + pad_blocks, 32 * p.seqb * p.nT, smem, st>>>(p, f, pw, w);
   return cuda_ok("prologue_v3_kernel");
 }
 template <int S, int NQ, int PREC>
@@ -336,8 +336,8 @@ int launch_finalize_v3_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, co
     return FOCAL_ESHAPE;                                                                              \
   } while (0)
 #endif
-int launch_prologue_v3(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st) {
-  FB_V3_DISPATCH(launch_prologue_v3_t, p, f, pw, w, st);
+int launch_prologue_v3(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, int pad_blocks, cudaStream_t st) {
+  FB_V3_DISPATCH(launch_prologue_v3_t, p, f, pw, w, pad_blocks, st);
 }
 int launch_finalize_v3(const Plan& p, const FeatPtrs& f, const GradPtrs& g, const PeerWs& pw, uint8_t* w, float* loss5,
                        cudaStream_t st) {
@@ -386,7 +386,9 @@ PeerWs solo(void* ws) {
 int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, cudaStream_t st,
                 bool zero_pads = true) {
   int rc;
-  if (zero_pads && (p.bpad != p.b || p.Bpad != p.Bt || p.Sp != p.S)) {
+  const bool pads = zero_pads && (p.bpad != p.b || p.Bpad != p.Bt || p.Sp != p.S);
+  const bool pads_in_prologue = pads && p.rowgen == 3 && pw.world == 1;     // extra blocks of prologue_v3 do it
+  if (pads && !pads_in_prologue) {
     zero_pad_kernel<<<64, 256, 0, st>>>(p, w);
     if ((rc = cuda_ok("zero_pad_kernel"))) return rc;
   }
@@ -394,7 +396,7 @@ int do_prologue(const Plan& p, int no_private, const FeatPtrs& f, const PeerWs& 
   bool fused_intra = false;
   if (p.rowgen == 3) {
     fused_intra = true;                 // S == 1: the temporal term is degenerate, nothing to fuse
-    if ((rc = launch_prologue_v3(p, f, pw, w, st))) return rc;
+    if ((rc = launch_prologue_v3(p, f, pw, w, pads_in_prologue ? 8 : 0, st))) return rc;
   } else if (vw) {
     fused_intra = (p.S == 2 || p.S == 4);
     const size_t smem = ((size_t)4 * p.nT * p.D + 4 * 2 * kMaxT + 4 * kMaxT) * sizeof(float);

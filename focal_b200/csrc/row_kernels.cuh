@@ -86,11 +86,11 @@ __device__ __forceinline__ float warp_dot(const float* a, const float* b, int n,
 // ---------------------------------------------------------------------------------------------------------
 // K0: zero the padding rows of the operand tiles and per-row vectors (only launched when padding exists)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void zero_pad_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws) {
+// `tid` of `stride` threads; only the padding is visited (an earlier version scanned every row of the operand arrays and
+// cost 18 us per step at the headline shape, where the padding is 128 rows).
+__device__ __forceinline__ void zero_pad_body(const Plan& p, uint8_t* __restrict__ ws, long tid, long stride) {
   const int padN = p.bpad - p.b;      // per (op, kb, s)
   const int padT = p.Bpad - p.Bt;     // per (tensor, kb)
-  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long stride = (long)gridDim.x * blockDim.x;
   const uint4 z = make_uint4(0, 0, 0, 0);
   if (padN > 0) {
     for (int o = 0; o < p.nOps; ++o) {
@@ -115,8 +115,11 @@ __global__ void zero_pad_kernel(const __grid_constant__ Plan p, uint8_t* __restr
       rsum[grp * p.bpad + p.b + pr] = 1.f;
     }
   }
-  if (padT > 0 || p.Sp != p.S) {
-    // temporal row space: rows beyond the batch and the phantom rows of padded sequences (position >= S)
+  float* sq = reinterpret_cast<float*>(ws + p.sq_off);
+  float* mi = reinterpret_cast<float*>(ws + p.mintra_off);
+  if (p.Sp != p.S) {
+    // padded sequences (seq_len not a power of two): phantom rows (position >= S) are spread over the whole temporal row
+    // space, so every row is looked at
     const long chunks = (long)p.nT * p.kbFull * p.Bpad * 8;
     for (long e = tid; e < chunks; e += stride) {
       const int c = e & 7;
@@ -126,15 +129,31 @@ __global__ void zero_pad_kernel(const __grid_constant__ Plan p, uint8_t* __restr
       const uint64_t tk = r;      // t * kbFull + kb
       *reinterpret_cast<uint4*>(ws + p.xt_off + (tk * p.Bpad + row) * 128 + c * 16) = z;
     }
-    float* sq = reinterpret_cast<float*>(ws + p.sq_off);
-    float* mi = reinterpret_cast<float*>(ws + p.mintra_off);
     for (long e = tid; e < (long)p.nT * p.Bpad; e += stride) {
       const int row = e % p.Bpad;
       if (row < p.Bt && (row % p.Sp) < p.S) continue;
       sq[e] = 0.f;
       mi[e] = 0.f;
     }
+  } else if (padT > 0) {
+    // temporal row space: the rows beyond the batch, [Bt, Bpad) of every (tensor, K block)
+    const long chunks = (long)p.nT * p.kbFull * padT * 8;
+    for (long e = tid; e < chunks; e += stride) {
+      const int c = e & 7;
+      long r = e >> 3;
+      const int row = p.Bt + (int)(r % padT); r /= padT;
+      const uint64_t tk = r;      // t * kbFull + kb
+      *reinterpret_cast<uint4*>(ws + p.xt_off + (tk * p.Bpad + row) * 128 + c * 16) = z;
+    }
+    for (long e = tid; e < (long)p.nT * padT; e += stride) {
+      const long idx = (e / padT) * p.Bpad + p.Bt + (e % padT);
+      sq[idx] = 0.f;
+      mi[idx] = 0.f;
+    }
   }
+}
+__global__ void zero_pad_kernel(const __grid_constant__ Plan p, uint8_t* __restrict__ ws) {
+  zero_pad_body(p, ws, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------

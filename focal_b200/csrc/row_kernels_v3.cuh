@@ -104,6 +104,12 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
                                                              uint8_t* __restrict__ ws) {
   constexpr int LPR = 32 / S;
   extern __shared__ float smem_f[];
+  // blocks behind the row blocks (single-GPU launches only): zero the padding rows of the operand arrays -- no launch of
+  // its own for that
+  if ((int)blockIdx.x >= p.nblk1) {
+    zero_pad_body(p, ws, (long)(blockIdx.x - p.nblk1) * blockDim.x + threadIdx.x, (long)(gridDim.x - p.nblk1) * blockDim.x);
+    return;
+  }
   const int nT = p.nT, d = p.d, seqb = p.seqb;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int q = warp / nT, t = warp - q * nT;                 // sequence within the block, tensor
