@@ -58,6 +58,18 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_KB4_SHARE_NW
 #define FB_KB4_SHARE_NW 4       // epilogue warpgroups of the shared-stage configuration (4, or 6 = one 16-column chunk each at BN = 96)
 #endif
+#ifndef FB_KB2_NS_BWD
+#define FB_KB2_NS_BWD 3         // narrow operands (<= 128 columns): S stages x warpgroups per stage of the backward passes
+#endif
+#ifndef FB_KB2_NW_BWD
+#define FB_KB2_NW_BWD 1
+#endif
+#ifndef FB_KB2_NS_FWD
+#define FB_KB2_NS_FWD 4         // ... and of the forward passes
+#endif
+#ifndef FB_KB2_NW_FWD
+#define FB_KB2_NW_FWD 1
+#endif
 #ifndef FB_EPI_UNROLL
 #define FB_EPI_UNROLL 1         // 2: two chunks of one thread's share of a tile are in flight together
 #endif
@@ -117,14 +129,14 @@ struct GramCfg {
   static_assert(EL == 0 || KB % 2 == 0, "split tiles: as many lo blocks as hi blocks");
   static constexpr bool kWide = (EL == 0 && KB > 4);                             // bf16, 256 < D <= 512: O in two passes
   static constexpr int BN = tile_bn(KB);                                         // column tile
-  static constexpr int NS = KB <= 2 ? (kBwd ? 3 : 4) : (KB == 4 ? FB_KB4_NS : (KB == 8 ? FB_KB8_NS : 4));  // S stages
+  static constexpr int NS = KB <= 2 ? (kBwd ? FB_KB2_NS_BWD : FB_KB2_NS_FWD) : (KB == 4 ? FB_KB4_NS : (KB == 8 ? FB_KB8_NS : 4));  // S stages
   static constexpr int NB = KB <= 3 ? 5 : (KB == 4 ? FB_KB4_NB : 1);             // B-tile ring stages (smem budget)
   // kShareAll (256-column operands, two S stages): the pipeline trace (tools/trace_gram.py, profiles/r2_trace_temporal.txt)
   // showed the two stages' epilogues running one after the other, never together (each stage's chain UMMA #1 -> epilogue
   // -> UMMA #2 -> UMMA #1 is serial and the stages interleave), so warpgroups bound to a stage idle half of the time.
   // With kShareAll every warpgroup takes a share of EVERY tile: half the epilogue latency per tile, same issue work.
   static constexpr bool kShareAll = (KB == 4 && SEQ <= 16 && FB_KB4_SHARE != 0);
-  static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? (kShareAll ? FB_KB4_SHARE_NW : FB_KB4_NW) : (KB == 8 ? FB_KB8_NW : 1));   // warpgroups per tile
+  static constexpr int NW = SEQ > 16 ? 1 : (KB == 4 ? (kShareAll ? FB_KB4_SHARE_NW : FB_KB4_NW) : (KB == 8 ? FB_KB8_NW : (KB <= 2 ? (kBwd ? FB_KB2_NW_BWD : FB_KB2_NW_FWD) : 1)));   // warpgroups per tile
   static constexpr int NG = kShareAll ? NW : NS * NW;                            // epilogue warpgroups in total
   static constexpr int CW = (NG >= 4 && (kTmp || NW > 1) && SEQ <= 16) ? 16 : 32;  // columns per tcgen05.ld (registers)
   // kHalfChunks (bf16 shared stages, 6 chunks of 16 columns over 4 warpgroups): every warpgroup takes one 16-column chunk
