@@ -22,7 +22,7 @@ EXPORTS = (
     "focal_b200_nce_rowsum", "focal_b200_nce_lse", "focal_b200_nce_grad", "focal_b200_temporal",
     "focal_b200_finalize", "focal_b200_loss", "focal_b200_set_ptrs",
     "focal_b200_peer_alloc", "focal_b200_peer_open", "focal_b200_peer_close", "focal_b200_peer_free",
-    "focal_b200_loss_sharded", "focal_b200_spectrum_rotate", "focal_b200_knn_predict",
+    "focal_b200_loss_sharded", "focal_b200_spectrum_rotate", "focal_b200_knn_predict", "focal_b200_debug_stage_times",
 )
 FOCAL_MAX_PEERS = 8
 

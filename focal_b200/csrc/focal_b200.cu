@@ -304,7 +304,15 @@ template <int S, int NQ, int PREC>
 int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, int pad_blocks, cudaStream_t st) {
   const size_t smem = row_v3_smem(p);
   if (int rc = ensure_dyn_smem(prologue_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(prologue_v3_kernel)")) return rc;
-  prologue_v3_kernel<S, NQ, PREC><<<p.nblk1 + pad_blocks, 32 * p.seqb * p.nT, smem, st>>>(p, f, pw, w);
+  // row shards: replicas of the launch share the peers among them (see the kernel); at most 4, and only while the
+  // replicated launch still fits about two waves of blocks
+  int nrep = 1;
+  if (pw.world > 1) {
+    static const int forced = [] { const char* e = std::getenv("FOCAL_B200_PROLOGUE_REPLICAS"); return e ? std::atoi(e) : 0; }();
+    nrep = forced > 0 ? forced : (pw.world >= 4 ? 4 : 2);
+    while (nrep > 1 && ((long)p.nblk1 * nrep > 4L * p.num_sms || pw.world % nrep)) nrep /= 2;
+  }
+  prologue_v3_kernel<S, NQ, PREC><<<dim3(p.nblk1 + pad_blocks, nrep), 32 * p.seqb * p.nT, smem, st>>>(p, f, pw, w);
   return cuda_ok("prologue_v3_kernel");
 }
 template <int S, int NQ, int PREC>
@@ -626,6 +634,31 @@ int focal_b200_peer_free(void* ptr) {
 }
 
 namespace {
+// Diagnostics (FOCAL_B200_STAGE_TIMES=1 in the environment, eager launches only -- tools/shard_stage_times.py): CUDA
+// events between the launches of focal_b200_loss_sharded, read back with focal_b200_debug_stage_times.
+struct StageTimer {
+  bool on = false, init = false;
+  cudaEvent_t ev[8];
+  int n = 0;
+  void begin() {
+    if (!init) {
+      const char* e = std::getenv("FOCAL_B200_STAGE_TIMES");
+      on = e && e[0] == '1';
+      if (on)
+        for (auto& x : ev) cudaEventCreate(&x);
+      init = true;
+    }
+    n = 0;
+  }
+  void mark(cudaStream_t st) {
+    if (!on || n >= 8) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    cudaEventRecord(ev[n++], st);
+  }
+};
+StageTimer g_stage_timer;
+
 // Do two ranks of this peer table keep their workspace on the same device (several ranks emulated on one GPU)?
 bool ranks_share_a_device(const FocalPeers* peers) {
   static FocalPeers seen{};
@@ -661,10 +694,14 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FeatPtrs f;
   if ((rc = fill_feats(p, feats, f))) return rc;
+  StageTimer& tm = g_stage_timer;
+  tm.begin();
+  tm.mark(st);
   // phase 1: operands of the owned rows -> every workspace; the last block of the prologue announces epoch 1 and the
   // first Gram launch waits for every rank's announcement before it reads operands.  (No zero_pad launch: workspaces
   // from focal_b200_peer_alloc start zeroed and nobody ever writes a padding row.)
   if ((rc = do_prologue(p, cfg->no_private, f, pw, w, st, /*zero_pads=*/false))) return rc;
+  tm.mark(st);
   // several ranks on one device: the waits become one-block launches of their own (see peer_wait_kernel)
   const bool split_wait = pw.world > 1 && ranks_share_a_device(peers);
   const int nwait = (pw.world > 1 && !split_wait) ? pw.world : 0;
@@ -682,20 +719,39 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   }
   if (nce) {
     if ((rc = launch_nce<NCE_FWD>(p, w, st, nwait))) return rc;
-    nce_lse_kernel<<<lse_blocks(p, 0), 256, 0, st>>>(p, pw, w, 0);
+    tm.mark(st);
+    nce_lse_kernel<<<dim3(lse_blocks(p, 0), pw.world >= 4 ? 4 : pw.world), 256, 0, st>>>(p, pw, w, 0);
     if ((rc = cuda_ok("nce_lse_kernel"))) return rc;
+    tm.mark(st);
   }
   if (tmp) {
     const int wt = nce ? 0 : nwait;
     rc = p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp, wt) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp, wt);
     if (rc) return rc;
+    tm.mark(st);
   }
   if (nce && p.need_grad) {
     if ((rc = wait_launch())) return rc;
     if ((rc = launch_nce<NCE_BWD>(p, w, st, nwait))) return rc;
+    tm.mark(st);
   }
-  // phase 3: gradients of the owned rows; loss partials all-reduced inside loss_reduce_kernel (third barrier)
-  return do_finalize(p, cfg->no_private, feats, grads, pw, w, loss5, st);
+  // phase 3: gradients of the owned rows; loss partials all-reduced by the last block of the finalize launch (third barrier)
+  rc = do_finalize(p, cfg->no_private, feats, grads, pw, w, loss5, st);
+  tm.mark(st);
+  return rc;
+}
+
+// Diagnostics: milliseconds between the stage marks of the last eager focal_b200_loss_sharded call of this process
+// (prologue, nce_rowsum, nce_lse, temporal, nce_grad, finalize for the full loss); synchronises.  Returns the number of
+// intervals written, 0 when FOCAL_B200_STAGE_TIMES is not set.
+int focal_b200_debug_stage_times(float* out_ms, int n) {
+  StageTimer& tm = g_stage_timer;
+  if (!tm.on || !out_ms || tm.n < 2) return 0;
+  if (cudaEventSynchronize(tm.ev[tm.n - 1]) != cudaSuccess) return 0;
+  int k = 0;
+  for (; k + 1 < tm.n && k < n; ++k)
+    if (cudaEventElapsedTime(&out_ms[k], tm.ev[k], tm.ev[k + 1]) != cudaSuccess) return 0;
+  return k;
 }
 
 }  // extern "C"

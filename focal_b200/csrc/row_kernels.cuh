@@ -316,8 +316,9 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
       const float* rp = reinterpret_cast<const float*>(ws + p.rpart_off);
       float r = 0.f;
       for (int sp = 0; sp < p.nsplit_fwd; ++sp) r += rp[(long)sp * n + e];
-      // row-sharded jobs: every rank needs r and 1/r of every row -> store into all workspaces (pw.world == 1 otherwise)
-      for (int rk = 0; rk < pw.world; ++rk) {
+      // row-sharded jobs: every rank needs r and 1/r of every row -> store into all workspaces (pw.world == 1 otherwise);
+      // the launch is replicated gridDim.y times and the replicas share the peers (more stores in flight over NVLink)
+      for (int rk = blockIdx.y; rk < pw.world; rk += gridDim.y) {
         reinterpret_cast<float*>(pw.ws[rk] + p.rsum_off)[e] = r;
         reinterpret_cast<float*>(pw.ws[rk] + p.rinv_off)[e] = 1.f / r;
       }
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
     ls = warp_sum(ls); lp = warp_sum(lp);
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = ls; red[threadIdx.x >> 5][1] = lp; }
     __syncthreads();
-    if (threadIdx.x < 2) {
+    if (threadIdx.x < 2 && blockIdx.y == 0) {
       float s = 0.f;
       for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
       reinterpret_cast<float*>(ws + p.part2_off)[(size_t)blockIdx.x * 2 + threadIdx.x] = s;

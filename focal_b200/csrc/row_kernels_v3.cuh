@@ -88,6 +88,19 @@ __device__ __forceinline__ float tile_sq4(const uint2& hi, const uint2& lo, floa
   return fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, acc))));
 }
 
+// Lanes 2j and 2j + 1 of a row hold the two 8-byte halves of one 16-byte operand chunk, for slot k and for slot k + 1.
+// After one exchange the even lane holds the whole chunk of slot k (`a`) and the odd lane the whole chunk of slot k + 1
+// (`b`): every store instruction then writes full 128-byte operand rows in 16-byte pieces -- half the store
+// instructions, and the granularity remote (NVLink) writes want.
+__device__ __forceinline__ uint4 pair_chunk(const uint2& a, const uint2& b, bool odd) {
+  const uint2 send = odd ? a : b;
+  const uint32_t gx = __shfl_xor_sync(0xffffffffu, send.x, 1), gy = __shfl_xor_sync(0xffffffffu, send.y, 1);
+  return odd ? make_uint4(gx, gy, b.x, b.y) : make_uint4(a.x, a.y, gx, gy);
+}
+// byte offset of the 16-byte chunk that holds elements [c, c + 8) (c % 8 == 0) of row `row`
+__device__ __forceinline__ uint64_t op_off16(uint64_t krows, uint64_t row, int c) {
+  return ((uint64_t)(c >> 6) * krows + row) * 128 + ((((uint32_t)(c & 63) >> 3) ^ (uint32_t)(row & 7)) << 4);
+}
 // byte offset of the 8-byte group that holds elements [c, c + 4) (c % 4 == 0) of row `row` in a swizzled operand array
 // with `krows` rows per K block
 __device__ __forceinline__ uint64_t op_off8(uint64_t krows, uint64_t row, int c) {
@@ -114,6 +127,12 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int q = warp / nT, t = warp - q * nT;                 // sequence within the block, tensor
   const int g = lane / LPR, l = lane % LPR;                   // row of the sequence, lane within the row
+  // Row-sharded launches are replicated gridDim.y times: replica j computes the same rows and stores them into the
+  // workspaces of the ranks r with r % gridDim.y == j.  A row shard has few rows (1024 at 8 ranks: 7 warps per SM), and one
+  // warp pushing every row to 8 workspaces over NVLink one store after the other made this launch 87 us at 8 GPUs
+  // (tools/shard_stage_times.py) -- the arithmetic is cheap, the stores need warps in flight.
+  const int rep = blockIdx.y, nrep = gridDim.y;
+  const bool rep0 = rep == 0;
   const int I0 = p.local_rows ? p.seq0 : 0, I1 = p.local_rows ? p.seq1 : p.b;
   const int I = I0 + blockIdx.x * seqb + q;
   const bool live = I < I1;
@@ -155,7 +174,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
     const float na = q4[0];
     nb = q4[1];
     if (l == 0) {
-      *reinterpret_cast<float2*>(ws + p.nrm_off + ((uint64_t)t * p.Bpad + i) * 8) = make_float2(na, nb);
+      if (rep0) *reinterpret_cast<float2*>(ws + p.nrm_off + ((uint64_t)t * p.Bpad + i) * 8) = make_float2(na, nb);
       nbs[(q * nT + t) * S + g] = nb;
     }
     if (orth_on && p.M > 1) {
@@ -169,8 +188,34 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
       const uint64_t rowN = (uint64_t)g * p.bpad + I, rowsNce = (uint64_t)S * p.bpad;
       const uint64_t off_s = p.ops[2 * t].off, off_p = p.ops[2 * t + 1].off;
       const uint64_t lo_img = (uint64_t)(p.ops[2 * t].kb / 2) * rowsNce * 128;      // split tiles: lo image behind the hi blocks
+      const bool odd = (l & 1) != 0;
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) {
+      for (int k = 0; k + 1 < NQ; k += 2) {                   // slot pairs: 16-byte chunks after a lane-pair exchange
+        uint2 hs[2], ls[2], hp[2], lp[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 zs = make_float4(sh[k + u].x * fa, sh[k + u].y * fa, sh[k + u].z * fa, sh[k + u].w * fa);
+          const float4 zp = make_float4(pr[k + u].x * fb2, pr[k + u].y * fb2, pr[k + u].z * fb2, pr[k + u].w * fb2);
+          float4 rr;
+          round4<PREC>(zs, rr, hs[u], ls[u]);
+          round4<PREC>(zp, rr, hp[u], lp[u]);
+        }
+        const uint4 cs = pair_chunk(hs[0], hs[1], odd), cp = pair_chunk(hp[0], hp[1], odd);
+        uint4 cls = make_uint4(0u, 0u, 0u, 0u), clp = cls;
+        if (PREC == FOCAL_PREC_FP32) { cls = pair_chunk(ls[0], ls[1], odd); clp = pair_chunk(lp[0], lp[1], odd); }
+        const uint64_t o = op_off16(rowsNce, rowN, 4 * ((k + (odd ? 1 : 0)) * LPR + (l & ~1)));
+        for (int rk = rep; rk < pw.world; rk += nrep) {
+          uint8_t* w = pw.ws[rk];
+          *reinterpret_cast<uint4*>(w + off_s + o) = cs;
+          *reinterpret_cast<uint4*>(w + off_p + o) = cp;
+          if (PREC == FOCAL_PREC_FP32) {
+            *reinterpret_cast<uint4*>(w + off_s + lo_img + o) = cls;
+            *reinterpret_cast<uint4*>(w + off_p + lo_img + o) = clp;
+          }
+        }
+      }
+      if (NQ & 1) {                                           // odd slot count: the last slot goes out in 8-byte pieces
+        constexpr int k = NQ - 1;
         const int c = 4 * (k * LPR + l);
         const float4 zs = make_float4(sh[k].x * fa, sh[k].y * fa, sh[k].z * fa, sh[k].w * fa);
         const float4 zp = make_float4(pr[k].x * fb2, pr[k].y * fb2, pr[k].z * fb2, pr[k].w * fb2);
@@ -179,7 +224,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         round4<PREC>(zs, rr, hs, ls);
         round4<PREC>(zp, rr, hp, lp);
         const uint64_t o = op_off8(rowsNce, rowN, c);
-        for (int rk = 0; rk < pw.world; ++rk) {
+        for (int rk = rep; rk < pw.world; rk += nrep) {
           uint8_t* w = pw.ws[rk];
           *reinterpret_cast<uint2*>(w + off_s + o) = hs;
           *reinterpret_cast<uint2*>(w + off_p + o) = hp;
@@ -191,7 +236,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
       }
       if (d & 63) {                                           // d = 32 or 96: zero the unused half of the last K block
         const uint64_t o = op_off8(rowsNce, rowN, 4 * (NQ * LPR + l));
-        for (int rk = 0; rk < pw.world; ++rk) {
+        for (int rk = rep; rk < pw.world; rk += nrep) {
           uint8_t* w = pw.ws[rk];
           *reinterpret_cast<uint2*>(w + off_s + o) = make_uint2(0u, 0u);
           *reinterpret_cast<uint2*>(w + off_p + o) = make_uint2(0u, 0u);
@@ -207,11 +252,29 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
       const uint64_t krows = (uint64_t)p.Bpad;
       const uint64_t xoff = p.xt_off + (uint64_t)t * p.kbFull * krows * 128;
       const uint64_t lo_img = (uint64_t)(p.kbFull / 2) * krows * 128;
+      const bool odd = (l & 1) != 0;
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) {
+      for (int k = 0; k + 1 < NQ; k += 2) {                   // slot pairs -> 16-byte chunks, full 128-byte rows per store
+        const uint4 cs = pair_chunk(hsh[k], hsh[k + 1], odd), cp = pair_chunk(hpr[k], hpr[k + 1], odd);
+        uint4 cls = make_uint4(0u, 0u, 0u, 0u), clp = cls;
+        if (PREC == FOCAL_PREC_FP32) { cls = pair_chunk(lsh[k], lsh[k + 1], odd); clp = pair_chunk(lpr[k], lpr[k + 1], odd); }
+        const int cc = 4 * ((k + (odd ? 1 : 0)) * LPR + (l & ~1));
+        const uint64_t o1 = op_off16(krows, (uint64_t)i, cc), o2 = op_off16(krows, (uint64_t)i, d + cc);
+        for (int rk = rep; rk < pw.world; rk += nrep) {
+          uint8_t* xt = pw.ws[rk] + xoff;
+          *reinterpret_cast<uint4*>(xt + o1) = cs;
+          *reinterpret_cast<uint4*>(xt + o2) = cp;
+          if (PREC == FOCAL_PREC_FP32) {
+            *reinterpret_cast<uint4*>(xt + lo_img + o1) = cls;
+            *reinterpret_cast<uint4*>(xt + lo_img + o2) = clp;
+          }
+        }
+      }
+      if (NQ & 1) {
+        constexpr int k = NQ - 1;
         const int c = 4 * (k * LPR + l);
         const uint64_t o1 = op_off8(krows, (uint64_t)i, c), o2 = op_off8(krows, (uint64_t)i, d + c);
-        for (int rk = 0; rk < pw.world; ++rk) {
+        for (int rk = rep; rk < pw.world; rk += nrep) {
           uint8_t* xt = pw.ws[rk] + xoff;
           *reinterpret_cast<uint2*>(xt + o1) = hsh[k];
           *reinterpret_cast<uint2*>(xt + o2) = hpr[k];
@@ -221,7 +284,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
           }
         }
       }
-      if (l < pw.world) reinterpret_cast<float*>(pw.ws[l] + p.sq_off)[(uint64_t)t * p.Bpad + i] = q4[2];
+      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(pw.ws[l] + p.sq_off)[(uint64_t)t * p.Bpad + i] = q4[2];
     }
     // ---- orthogonality (loss.py:96-104), pair (shared_t, private_t)
     if (owned && orth_on) acc_orth = fmaxf(q4[3] * rsqrtf((na + kOrthEps) * (nb + kOrthEps)), 0.f);
@@ -251,11 +314,11 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
 #pragma unroll
       for (int o = LPR; o < 32; o <<= 1) m += __shfl_xor_sync(0xffffffffu, m, o);       // ordered pairs of the sequence
       m = m / (float)(S * S - S);
-      if (l == 0) {
+      if (l == 0 && rep0) {
         float4 pd4 = make_float4(d2[0], S > 2 ? d2[(S > 2) ? 1 : 0] : 0.f, S > 2 ? d2[(S > 2) ? 2 : 0] : 0.f, 0.f);
         *reinterpret_cast<float4*>(ws + p.pd_off + ((uint64_t)t * p.Bpad + i) * 16) = pd4;
       }
-      if (l < pw.world) reinterpret_cast<float*>(pw.ws[l] + p.mintra_off)[(uint64_t)t * p.Bpad + i] = m;
+      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(pw.ws[l] + p.mintra_off)[(uint64_t)t * p.Bpad + i] = m;
     }
   }
   __syncthreads();
@@ -282,7 +345,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
     if (lane == 0) red[warp] = a;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && rep0) {
     float s2 = 0.f;
     for (int w = 0; w < seqb * nT; ++w) s2 += red[w];
     float* p1 = reinterpret_cast<float*>(ws + p.part1_off) + (size_t)blockIdx.x * 4;

@@ -164,6 +164,11 @@ int focal_b200_peer_free(void* ptr);
  * of 32, S in {1, 2, 4}, no noPrivate) -- callers then use the staged functions with a collective library. */
 int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, const FocalPeers* peers, size_t ws_bytes,
                             float* loss5, float* const* grads, void* stream);
+/* Diagnostics of the row-sharded path (no reference counterpart): with FOCAL_B200_STAGE_TIMES=1 in the environment,
+ * eager (not stream-captured) calls of focal_b200_loss_sharded record CUDA events between their launches; this returns
+ * the milliseconds of each stage of the last call (prologue, nce_rowsum, nce_lse, temporal, nce_grad, finalize --
+ * including what a stage waits for from the peers).  Synchronises.  Returns the number of values written (0: disabled). */
+int focal_b200_debug_stage_times(float* out_ms, int n);
 
 /*
  * Frequency-domain input stage: the part of Augmenter.fft_preprocess after torch.fft.fft
