@@ -349,3 +349,41 @@ extern "C" int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, u
                                                                         cycles);
   return cuda_ok("tma_rate_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// peer-memory store rate (tools/peer_store_rate.py): how fast can SM stores push one rank's operand slice into the
+// workspaces of its peers -- one plain 16-byte store per destination, or one NVSwitch multicast store (multimem.st)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct PeerDsts { uint8_t* p[8]; };
+// mode 0: every 16-byte chunk stored to each of the n destinations (chunk-major, as the row kernels do);
+// mode 1: multimem.st of every chunk to p[0] (a multicast address); mode 2: destination-major unicast.
+__global__ void __launch_bounds__(256) peer_store_kernel(PeerDsts d, int n, uint32_t off0, uint32_t bytes, int mode) {
+  const uint32_t stride = gridDim.x * blockDim.x * 16u;
+  const uint4 v = make_uint4(threadIdx.x, blockIdx.x, 0x3f800000u, 0x3f800000u);
+  if (mode == 1) {
+    for (uint32_t o = (blockIdx.x * blockDim.x + threadIdx.x) * 16u; o < bytes; o += stride)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d.p[0] + off0 + o),
+                   "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                   "f"(__uint_as_float(v.w)) : "memory");
+  } else if (mode == 0) {
+    for (uint32_t o = (blockIdx.x * blockDim.x + threadIdx.x) * 16u; o < bytes; o += stride)
+      for (int k = 0; k < n; ++k) *reinterpret_cast<uint4*>(d.p[k] + off0 + o) = v;
+  } else {
+    for (int k = 0; k < n; ++k)
+      for (uint32_t o = (blockIdx.x * blockDim.x + threadIdx.x) * 16u; o < bytes; o += stride)
+        *reinterpret_cast<uint4*>(d.p[k] + off0 + o) = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+}
+}  // namespace
+
+extern "C" int focal_b200_debug_peer_store(void* const* dsts, int n, uint32_t off0, uint32_t bytes, int mode, int grid,
+                                           void* stream) {
+  if (n < 1 || n > 8 || grid < 1) return FOCAL_EINVAL;
+  PeerDsts d{};
+  for (int k = 0; k < n; ++k) d.p[k] = static_cast<uint8_t*>(dsts[k]);
+  peer_store_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d, n, off0, bytes, mode);
+  return cuda_ok("peer_store_kernel");
+}

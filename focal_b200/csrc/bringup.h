@@ -23,6 +23,10 @@ int focal_b200_debug_umma_tile_rate(uint32_t BN, uint32_t mode, uint32_t iters, 
 /* per-SM throughput of linear TMA bulk copies */
 int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, uint32_t copy_bytes, uint32_t copies_per_stage,
                               uint32_t stages, uint32_t iters, uint32_t grid, long long* cycles, void* stream);
+/* SM stores of `bytes` (16 per thread and iteration) at offset off0 of n destination buffers (peer-mapped or multicast
+ * addresses): mode 0 = chunk-major unicast, 1 = multimem.st to dsts[0], 2 = destination-major unicast */
+int focal_b200_debug_peer_store(void* const* dsts, int n, uint32_t off0, uint32_t bytes, int mode, int grid,
+                                void* stream);
 
 #ifdef __cplusplus
 }

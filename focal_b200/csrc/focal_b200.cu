@@ -147,9 +147,8 @@ int launch_gram_prec(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_
 }
 
 template <int MODE>
-int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid, int peer_wait = 0) {
-  ProbSel sel{};
-  sel.peer_wait = peer_wait;
+int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid, const ProbSel& sync = ProbSel{}) {
+  ProbSel sel = sync;                 // peer announce / wait of the row-sharded path (none otherwise)
   switch (p.Sp) {                     // lanes per (padded) sequence; p.S itself may be any length up to 32
     case 4: return launch_gram_prec<MODE, 4>(p, sel, ws, st, p.kbFull, grid);
 #ifndef FB_FAST_BUILD                 // experiment builds (tools/variant_bench.py) only instantiate the headline shapes
@@ -165,15 +164,18 @@ int launch_temporal(const Plan& p, uint8_t* ws, cudaStream_t st, int grid, int p
 // InfoNCE problems are launched in groups of equal operand width (they differ only under noPrivate, where the
 // shared problems use the full D columns and the private ones D/2).
 template <int MODE>
-int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st, int peer_wait = 0) {
+int launch_nce(const Plan& p, uint8_t* ws, cudaStream_t st, const ProbSel& sync = ProbSel{}) {
+  bool first = true;
   for (int kb = 1; kb <= 4; ++kb) {
-    ProbSel sel{};
-    sel.peer_wait = peer_wait;
+    ProbSel sel = sync;               // peer announce / wait of the row-sharded path (none otherwise)
+    sel.n = 0;
+    if (!first) sel.ann_world = 0;    // one announcement per producer launch
     for (int q = 0; q < p.nProb; ++q)
       if (p.ops[p.probs[q].opA].kb == kb) sel.idx[sel.n++] = q;
     if (!sel.n) continue;
     const int rc = launch_gram_prec<MODE, 0>(p, sel, ws, st, kb, p.grid_nce[kb]);
     if (rc) return rc;
+    first = false;
   }
   return FOCAL_OK;
 }
@@ -304,12 +306,13 @@ template <int S, int NQ, int PREC>
 int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uint8_t* w, int pad_blocks, cudaStream_t st) {
   const size_t smem = row_v3_smem(p);
   if (int rc = ensure_dyn_smem(prologue_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(prologue_v3_kernel)")) return rc;
-  // row shards: replicas of the launch share the peers among them (see the kernel); at most 4, and only while the
-  // replicated launch still fits about two waves of blocks
+  // row shards: the launch can be replicated, the replicas sharing the peers among them (see the kernel).  Measured
+  // at 4 GPUs (gpurun_out/r2_prologue_dbg_4.txt): 4 replicas 79 us, 1 replica 60 us -- so the default is 1; the knob stays
+  // for experiments.
   int nrep = 1;
   if (pw.world > 1) {
     static const int forced = [] { const char* e = std::getenv("FOCAL_B200_PROLOGUE_REPLICAS"); return e ? std::atoi(e) : 0; }();
-    nrep = forced > 0 ? forced : (pw.world >= 4 ? 4 : 2);
+    nrep = forced > 0 ? forced : 1;
     while (nrep > 1 && ((long)p.nblk1 * nrep > 4L * p.num_sms || pw.world % nrep)) nrep /= 2;
   }
   prologue_v3_kernel<S, NQ, PREC><<<dim3(p.nblk1 + pad_blocks, nrep), 32 * p.seqb * p.nT, smem, st>>>(p, f, pw, w);
@@ -686,6 +689,7 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   if (peers->world < 1 || peers->world > kMaxPeers || peers->rank < 0 || peers->rank >= peers->world) return FOCAL_EINVAL;
   PeerWs pw{};
   pw.rank = peers->rank; pw.world = peers->world;
+  { static const int dbg = [] { const char* e = std::getenv("FOCAL_B200_PROLOGUE_DBG"); return e ? std::atoi(e) : 0; }(); pw.dbg = dbg; }
   for (int r = 0; r < pw.world; ++r) {
     if ((rc = check_ws(p, peers->ws[r], ws_bytes))) return rc;
     pw.ws[r] = static_cast<uint8_t*>(peers->ws[r]);
@@ -697,42 +701,59 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   StageTimer& tm = g_stage_timer;
   tm.begin();
   tm.mark(st);
-  // phase 1: operands of the owned rows -> every workspace; the last block of the prologue announces epoch 1 and the
-  // first Gram launch waits for every rank's announcement before it reads operands.  (No zero_pad launch: workspaces
-  // from focal_b200_peer_alloc start zeroed and nobody ever writes a padding row.)
+  // phase 1: operands of the owned rows -> every workspace.  The prologue only counts the epoch; block 0 of the NEXT launch
+  // (stream order: every store of the prologue is complete) announces it to the peers, and every block of that launch
+  // waits for all announcements before it reads operands.  (No zero_pad launch: workspaces from focal_b200_peer_alloc
+  // start zeroed and nobody ever writes a padding row.)
   if ((rc = do_prologue(p, cfg->no_private, f, pw, w, st, /*zero_pads=*/false))) return rc;
   tm.mark(st);
-  // several ranks on one device: the waits become one-block launches of their own (see peer_wait_kernel)
-  const bool split_wait = pw.world > 1 && ranks_share_a_device(peers);
-  const int nwait = (pw.world > 1 && !split_wait) ? pw.world : 0;
-  auto wait_launch = [&]() -> int {
-    if (!split_wait) return FOCAL_OK;
-    peer_wait_kernel<<<1, 32, 0, st>>>(p, pw);
+  // several ranks on one device: announce / wait become one-block launches of their own (see peer_wait_kernel)
+  const bool multi = pw.world > 1;
+  const bool split = multi && ranks_share_a_device(peers);
+  auto sync_launch = [&](bool announce, bool wait) -> int {
+    if (!split) return FOCAL_OK;
+    peer_wait_kernel<<<1, 32, 0, st>>>(p, pw, announce ? 1 : 0, wait ? 1 : 0);
     return cuda_ok("peer_wait_kernel");
+  };
+  auto sync_sel = [&](bool announce, bool wait) {
+    ProbSel s{};
+    if (multi && !split) {
+      s.peer_wait = wait ? pw.world : 0;
+      s.ann_world = announce ? pw.world : 0;
+      s.ann_rank = pw.rank;
+      for (int r = 0; r < pw.world; ++r) s.peer_ws[r] = pw.ws[r];
+    }
+    return s;
   };
   const bool nce = (p.terms & FOCAL_TERM_NCE) != 0;
   const bool tmp = (p.terms & FOCAL_TERM_TEMPORAL) && !temporal_degenerate(p);
-  // phase 2: row sums of the owned rows -> every workspace (announced by the last block of nce_lse).  The temporal launch
-  // needs nothing from the peers beyond phase 1, so it runs between those stores and the launch that waits for them.
+  // phase 2: row sums of the owned rows -> every workspace (counted by nce_lse, announced by the launch after it).  The
+  // temporal launch needs nothing from the peers beyond phase 1, so it runs between those stores and the launch that
+  // waits for them.
   if (nce || tmp) {
-    if ((rc = wait_launch())) return rc;
+    if ((rc = sync_launch(true, true))) return rc;
   }
+  bool pending = false;               // a counted epoch that has not been announced yet
   if (nce) {
-    if ((rc = launch_nce<NCE_FWD>(p, w, st, nwait))) return rc;
+    if ((rc = launch_nce<NCE_FWD>(p, w, st, sync_sel(true, true)))) return rc;
     tm.mark(st);
-    nce_lse_kernel<<<dim3(lse_blocks(p, 0), pw.world >= 4 ? 4 : pw.world), 256, 0, st>>>(p, pw, w, 0);
+    nce_lse_kernel<<<lse_blocks(p, 0), 256, 0, st>>>(p, pw, w, 0);
     if ((rc = cuda_ok("nce_lse_kernel"))) return rc;
+    pending = multi;
     tm.mark(st);
   }
   if (tmp) {
-    const int wt = nce ? 0 : nwait;
-    rc = p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp, wt) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp, wt);
+    if (pending && (rc = sync_launch(true, false))) return rc;
+    const ProbSel s = nce ? sync_sel(pending, false) : sync_sel(true, true);
+    rc = p.need_grad ? launch_temporal<TMP_BWD>(p, w, st, p.grid_tmp, s) : launch_temporal<TMP_FWD>(p, w, st, p.grid_tmp, s);
     if (rc) return rc;
+    pending = false;
     tm.mark(st);
   }
   if (nce && p.need_grad) {
-    if ((rc = wait_launch())) return rc;
-    if ((rc = launch_nce<NCE_BWD>(p, w, st, nwait))) return rc;
+    if ((rc = sync_launch(pending, true))) return rc;
+    if ((rc = launch_nce<NCE_BWD>(p, w, st, sync_sel(pending, true)))) return rc;
+    pending = false;
     tm.mark(st);
   }
   // phase 3: gradients of the owned rows; loss partials all-reduced by the last block of the finalize launch (third barrier)

@@ -328,9 +328,11 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
   }
+  // row-sharded path: the launch before this one stored operands / row sums into the peers' workspaces -- tell them
+  if (sel.ann_world > 0 && blockIdx.x == 0) peer_announce_epoch(p, sel.peer_ws, sel.ann_world, sel.ann_rank);
   if (sel.peer_wait > 0) {
     // row-sharded path: the operands / row sums this launch reads were stored by the peers; wait for their
-    // announcements (the last block of their producing launch sent them), then order the TMA reads behind the wait
+    // announcements (block 0 of the launch after their producing launch sent them), then order the TMA reads behind the wait
     peer_wait(ws, p, sel.peer_wait, -1);
     asm volatile("fence.proxy.async;" ::: "memory");
   }

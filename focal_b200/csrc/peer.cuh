@@ -8,8 +8,9 @@ namespace fb {
 
 // Device-side barrier over the ranks of a row-sharded job, split in two phases so that no launch exists only to
 // synchronise.  Flags live in every rank's workspace: slot r of rank q's array = the last epoch rank r announced to q.
-//   announce: store the rank's next epoch into its slot of every peer's array (st.release.sys after a system fence:
-//             everything this rank wrote to peer memory before is visible first);
+//   announce: store the rank's epoch into its slot of every peer's array (st.release.sys after a system fence:
+//             everything this rank wrote to peer memory before is visible first) -- done by the launch AFTER the one
+//             that produced the data (peer_epoch_bump / peer_announce_epoch);
 //   wait:     spin (ld.acquire.sys, bounded: a lost rank traps instead of hanging) until every peer's slot in the own
 //             array has reached the own epoch.
 // Epochs are counted on the device (slot 8), so the sequence replays unchanged inside a CUDA graph.
@@ -55,27 +56,27 @@ __device__ __forceinline__ void peer_barrier(const Plan& p, const PeerWs& pw) {
   peer_wait(pw.ws[pw.rank], p, pw.world, pw.rank);
   __syncthreads();
 }
-// Announce from the LAST block of a multi-block launch to finish (every block calls this at its end, all threads):
-// the launch's stores into peer memory are complete before the epoch goes out; nobody waits here.
-__device__ __forceinline__ void peer_announce_when_launch_done(const Plan& p, const PeerWs& pw) {
-  __shared__ uint32_t last_sh;
-  uint32_t* mine = reinterpret_cast<uint32_t*>(pw.ws[pw.rank] + p.bar_off);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();                             // this block's stores (seen through the bar.sync) first
-    const uint32_t done = atomicAdd(mine + 9, 1u);
-    uint32_t e = 0;
-    if (done == gridDim.x * gridDim.y - 1) {
-      __threadfence_system();                           // ... and everything the other blocks published before theirs
-      mine[9] = 0;
-      e = mine[8] + 1;
-      mine[8] = e;
-      __threadfence();
-    }
-    last_sh = e;
+// Producer launches (prologue, nce_lse) only COUNT the epoch: one thread of the launch bumps the rank's counter; the
+// announcement itself is sent by block 0 of the NEXT launch on the stream (peer_announce_epoch below), when stream order
+// has already completed every store of the producer.  (The first version announced from the last block to finish, which
+// needed a system fence + an atomic at the end of EVERY block: measured 11-15 us of the prologue and 6 us of nce_lse at
+// 4 GPUs -- gpurun_out/r2_prologue_dbg_4.txt.)
+__device__ __forceinline__ void peer_epoch_bump(const Plan& p, uint8_t* ws) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    uint32_t* mine = reinterpret_cast<uint32_t*>(ws + p.bar_off);
+    mine[8] = mine[8] + 1;
   }
-  __syncthreads();
-  if (last_sh) peer_announce(p, pw, last_sh);
+}
+// Block 0 of the launch that follows a producer: send the rank's current epoch to every peer.  `peer_ws` = the R mapped
+// workspaces, own rank included.
+__device__ __forceinline__ void peer_announce_epoch(const Plan& p, uint8_t* const* peer_ws, int world, int rank) {   // threads < world
+  if ((int)threadIdx.x < world) {
+    uint32_t e;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(reinterpret_cast<const uint32_t*>(peer_ws[rank] + p.bar_off) + 8) : "memory");
+    __threadfence_system();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(peer_ws[threadIdx.x] + p.bar_off) + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(e) : "memory");
+  }
 }
 
 }  // namespace fb

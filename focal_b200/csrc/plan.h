@@ -61,6 +61,10 @@ struct ProbSel {
   int32_t n;
   int32_t idx[kMaxProb];
   int32_t peer_wait;   // row-sharded path: number of ranks whose barrier announcement this launch waits for (0 = none)
+  // row-sharded path: block 0 first announces the rank's epoch (the stores of the previous launch are complete) to the
+  // ann_world mapped workspaces in peer_ws (0 = nothing to announce)
+  int32_t ann_world, ann_rank;
+  uint8_t* peer_ws[8];
 };
 
 struct Plan {
@@ -131,6 +135,8 @@ struct PtrTable {
 constexpr int kMaxPeers = 8;
 struct PeerWs {
   int32_t rank, world;
+  int32_t dbg, pad_;          // experiments (FOCAL_B200_PROLOGUE_DBG): bits 1 / 2 / 4 keep the InfoNCE operand / temporal operand /
+                              // per-row scalar stores of the prologue in the own workspace (timing only: results are wrong)
   uint8_t* ws[kMaxPeers];
 };
 

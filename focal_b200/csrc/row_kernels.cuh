@@ -316,9 +316,8 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
       const float* rp = reinterpret_cast<const float*>(ws + p.rpart_off);
       float r = 0.f;
       for (int sp = 0; sp < p.nsplit_fwd; ++sp) r += rp[(long)sp * n + e];
-      // row-sharded jobs: every rank needs r and 1/r of every row -> store into all workspaces (pw.world == 1 otherwise);
-      // the launch is replicated gridDim.y times and the replicas share the peers (more stores in flight over NVLink)
-      for (int rk = blockIdx.y; rk < pw.world; rk += gridDim.y) {
+      // row-sharded jobs: every rank needs r and 1/r of every row -> store into all workspaces (pw.world == 1 otherwise)
+      for (int rk = 0; rk < pw.world; ++rk) {
         reinterpret_cast<float*>(pw.ws[rk] + p.rsum_off)[e] = r;
         reinterpret_cast<float*>(pw.ws[rk] + p.rinv_off)[e] = 1.f / r;
       }
@@ -332,12 +331,12 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
     ls = warp_sum(ls); lp = warp_sum(lp);
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = ls; red[threadIdx.x >> 5][1] = lp; }
     __syncthreads();
-    if (threadIdx.x < 2 && blockIdx.y == 0) {
+    if (threadIdx.x < 2) {
       float s = 0.f;
       for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
       reinterpret_cast<float*>(ws + p.part2_off)[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
     }
-    if (pw.world > 1) peer_announce_when_launch_done(p, pw);      // row sums of the owned rows are out
+    if (pw.world > 1) peer_epoch_bump(p, ws);      // row sums of the owned rows are out
   }
 }
 
@@ -504,11 +503,13 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) finalize_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------
 // K5: deterministic reduction of the per-block partials -> {total, shared, private, orth, temporal}
 // ---------------------------------------------------------------------------------------------------------
-// Wait phase alone, as a one-block launch: used instead of the wait inside the persistent Gram kernels when several ranks
-// share one device (tests), where a spinning 148-CTA launch would keep the other ranks' kernels off the SMs.
+// Announce and / or wait phase alone, as a one-block launch: used instead of the ones at the head of the persistent Gram
+// kernels when several ranks share one device (tests), where a spinning 148-CTA launch would keep the other ranks'
+// kernels off the SMs.
 __global__ void __launch_bounds__(32) peer_wait_kernel(const __grid_constant__ Plan p,
-                                                       const __grid_constant__ PeerWs pw) {
-  peer_wait(pw.ws[pw.rank], p, pw.world, pw.rank);
+                                                       const __grid_constant__ PeerWs pw, int announce, int wait) {
+  if (announce) peer_announce_epoch(p, pw.ws, pw.world, pw.rank);
+  if (wait) peer_wait(pw.ws[pw.rank], p, pw.world, pw.rank);
 }
 
 // Sum of the loss partials of every kernel of the step, in double and in a fixed order (bit-reproducible); ranks of a

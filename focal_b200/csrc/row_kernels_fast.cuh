@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) prologue_fast_kernel(const __grid_constan
     for (int r = 0; r < pw.world; ++r)
       reinterpret_cast<float*>(pw.ws[r] + p.mintra_off)[(uint64_t)lane * p.Bpad + i] = m / (float)(S * S - S);
   }
-  if (pw.world > 1) peer_announce_when_launch_done(p, pw);        // operands of the owned rows are out
+  if (pw.world > 1) peer_epoch_bump(p, ws);        // operands of the owned rows are out
 }
 
 // ---------------------------------------------------------------------------------------------------------

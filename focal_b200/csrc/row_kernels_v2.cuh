@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(1024, 1) prologue_v2_kernel(const __grid_const
     for (int rk = 0; rk < pw.world; ++rk)
       reinterpret_cast<float*>(pw.ws[rk] + p.mintra_off)[(uint64_t)t * p.Bpad + i] = m;
   }
-  if (pw.world > 1) peer_announce_when_launch_done(p, pw);      // operands of the owned rows are out
+  if (pw.world > 1) peer_epoch_bump(p, ws);      // operands of the owned rows are out
 }
 
 // ---------------------------------------------------------------------------------------------------------

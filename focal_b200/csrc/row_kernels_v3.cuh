@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         if (PREC == FOCAL_PREC_FP32) { cls = pair_chunk(ls[0], ls[1], odd); clp = pair_chunk(lp[0], lp[1], odd); }
         const uint64_t o = op_off16(rowsNce, rowN, 4 * ((k + (odd ? 1 : 0)) * LPR + (l & ~1)));
         for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* w = pw.ws[rk];
+          uint8_t* w = (pw.dbg & 1) ? ws : pw.ws[rk];
           *reinterpret_cast<uint4*>(w + off_s + o) = cs;
           *reinterpret_cast<uint4*>(w + off_p + o) = cp;
           if (PREC == FOCAL_PREC_FP32) {
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         round4<PREC>(zp, rr, hp, lp);
         const uint64_t o = op_off8(rowsNce, rowN, c);
         for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* w = pw.ws[rk];
+          uint8_t* w = (pw.dbg & 1) ? ws : pw.ws[rk];
           *reinterpret_cast<uint2*>(w + off_s + o) = hs;
           *reinterpret_cast<uint2*>(w + off_p + o) = hp;
           if (PREC == FOCAL_PREC_FP32) {
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
       if (d & 63) {                                           // d = 32 or 96: zero the unused half of the last K block
         const uint64_t o = op_off8(rowsNce, rowN, 4 * (NQ * LPR + l));
         for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* w = pw.ws[rk];
+          uint8_t* w = (pw.dbg & 1) ? ws : pw.ws[rk];
           *reinterpret_cast<uint2*>(w + off_s + o) = make_uint2(0u, 0u);
           *reinterpret_cast<uint2*>(w + off_p + o) = make_uint2(0u, 0u);
           if (PREC == FOCAL_PREC_FP32) {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         const int cc = 4 * ((k + (odd ? 1 : 0)) * LPR + (l & ~1));
         const uint64_t o1 = op_off16(krows, (uint64_t)i, cc), o2 = op_off16(krows, (uint64_t)i, d + cc);
         for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* xt = pw.ws[rk] + xoff;
+          uint8_t* xt = ((pw.dbg & 2) ? ws : pw.ws[rk]) + xoff;
           *reinterpret_cast<uint4*>(xt + o1) = cs;
           *reinterpret_cast<uint4*>(xt + o2) = cp;
           if (PREC == FOCAL_PREC_FP32) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         const int c = 4 * (k * LPR + l);
         const uint64_t o1 = op_off8(krows, (uint64_t)i, c), o2 = op_off8(krows, (uint64_t)i, d + c);
         for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* xt = pw.ws[rk] + xoff;
+          uint8_t* xt = ((pw.dbg & 2) ? ws : pw.ws[rk]) + xoff;
           *reinterpret_cast<uint2*>(xt + o1) = hsh[k];
           *reinterpret_cast<uint2*>(xt + o2) = hpr[k];
           if (PREC == FOCAL_PREC_FP32) {
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
           }
         }
       }
-      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(pw.ws[l] + p.sq_off)[(uint64_t)t * p.Bpad + i] = q4[2];
+      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(((pw.dbg & 4) ? ws : pw.ws[l]) + p.sq_off)[(uint64_t)t * p.Bpad + i] = q4[2];
     }
     // ---- orthogonality (loss.py:96-104), pair (shared_t, private_t)
     if (owned && orth_on) acc_orth = fmaxf(q4[3] * rsqrtf((na + kOrthEps) * (nb + kOrthEps)), 0.f);
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         float4 pd4 = make_float4(d2[0], S > 2 ? d2[(S > 2) ? 1 : 0] : 0.f, S > 2 ? d2[(S > 2) ? 2 : 0] : 0.f, 0.f);
         *reinterpret_cast<float4*>(ws + p.pd_off + ((uint64_t)t * p.Bpad + i) * 16) = pd4;
       }
-      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(pw.ws[l] + p.mintra_off)[(uint64_t)t * p.Bpad + i] = m;
+      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(((pw.dbg & 4) ? ws : pw.ws[l]) + p.mintra_off)[(uint64_t)t * p.Bpad + i] = m;
     }
   }
   __syncthreads();
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
     float* p1 = reinterpret_cast<float*>(ws + p.part1_off) + (size_t)blockIdx.x * 4;
     p1[0] = s2 / (float)p.B; p1[1] = 0.f; p1[2] = 0.f;
   }
-  if (pw.world > 1) peer_announce_when_launch_done(p, pw);      // operands of the owned rows are out
+  if (pw.world > 1) peer_epoch_bump(p, ws);      // operands of the owned rows are out
 }
 
 // 4 consecutive bf16 operand elements -> fp32 (split tiles: hi + lo image)
