@@ -387,3 +387,57 @@ extern "C" int focal_b200_debug_peer_store(void* const* dsts, int n, uint32_t of
   peer_store_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d, n, off0, bytes, mode);
   return cuda_ok("peer_store_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// launch floor (tools/launch_floor.py): what does a launch cost on the device, as a function of what the kernel asks
+// for -- a 10 KB by-value parameter block, ~200 KB of dynamic shared memory, tensor memory -- and of what ran before it
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct BigParam { uint32_t w[2688]; };     // 10752 bytes: the size of Plan + ProbSel
+__global__ void __launch_bounds__(576, 1) floor_small_kernel(uint32_t* out, uint32_t tm) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t slot;
+  if (tm) {
+    if (threadIdx.x < 32) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x < 32) tmem_dealloc(slot, 512);
+  }
+  if (threadIdx.x == 0) { smem_raw[0] = 1; if (out && smem_raw[0] == 77) out[blockIdx.x] = 1; }
+}
+__global__ void __launch_bounds__(576, 1) floor_big_kernel(const __grid_constant__ BigParam bp, uint32_t* out, uint32_t tm) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t slot;
+  if (tm) {
+    if (threadIdx.x < 32) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x < 32) tmem_dealloc(slot, 512);
+  }
+  if (threadIdx.x == 0) { smem_raw[0] = (uint8_t)bp.w[blockIdx.x]; if (out && smem_raw[0] == 77) out[blockIdx.x] = bp.w[2687]; }
+}
+__global__ void __launch_bounds__(256, 2) floor_row_kernel(uint32_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) { smem_raw[0] = 1; if (out && smem_raw[0] == 77) out[blockIdx.x] = 1; }
+}
+}  // namespace
+
+// Enqueues `iters` launches.  flags: 1 = 10.7 KB by-value parameter block, 2 = 200 KB dynamic shared memory, 4 = tensor
+// memory allocated and freed, 8 = a 1024-block x 256-thread launch with 16 KB of shared memory between any two (the row
+// kernels between the Gram launches: a different shared-memory carve-out).
+extern "C" int focal_b200_debug_launch_floor(uint32_t flags, uint32_t iters, uint32_t* out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = (flags & 2) ? 200 * 1024 : 0;
+  if (cudaFuncSetAttribute(floor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(floor_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    return cuda_ok("cudaFuncSetAttribute(floor kernels)");
+  static BigParam bp{};
+  for (uint32_t i = 0; i < iters; ++i) {
+    if (flags & 1) floor_big_kernel<<<148, 576, smem, st>>>(bp, out, (flags & 4) ? 1u : 0u);
+    else floor_small_kernel<<<148, 576, smem, st>>>(out, (flags & 4) ? 1u : 0u);
+    if (flags & 8) floor_row_kernel<<<1024, 256, 16 * 1024, st>>>(out);
+  }
+  return cuda_ok("launch floor kernels");
+}

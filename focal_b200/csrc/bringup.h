@@ -27,6 +27,9 @@ int focal_b200_debug_tma_rate(const void* src, uint32_t span_bytes, uint32_t cop
  * addresses): mode 0 = chunk-major unicast, 1 = multimem.st to dsts[0], 2 = destination-major unicast */
 int focal_b200_debug_peer_store(void* const* dsts, int n, uint32_t off0, uint32_t bytes, int mode, int grid,
                                 void* stream);
+/* enqueues `iters` launches of an (almost) empty 148 x 576 kernel: flags 1 = 10.7 KB by-value parameters, 2 = 200 KB
+ * dynamic shared memory, 4 = tensor memory allocated + freed, 8 = a small-shared-memory 1024-block launch in between */
+int focal_b200_debug_launch_floor(uint32_t flags, uint32_t iters, uint32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

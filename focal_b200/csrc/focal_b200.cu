@@ -100,6 +100,23 @@ int lse_blocks(const Plan& p, int all_rows) {
   return (int)(((long)p.nProb * p.S * 2 * (p.seq1 - p.seq0) + 255) / 256);
 }
 
+// Launch with programmatic stream serialisation: the kernel may be scheduled while the launch before it on the stream
+// drains.  ONLY for kernels that call pdl_wait() before their first global-memory access (gram_kernel, prologue_v3,
+// finalize_v3, nce_lse).  OFF unless FOCAL_B200_PDL=1 is in the environment: measured (profiles/r2_pdl_ab.txt) it makes
+// the step SLOWER -- headline 515.7 -> 523.8 us, cfg2 72.7 -> 80.1 us, cfg1 80.9 -> 82.9 us: the early-resident blocks
+// of the next launch only take SM slots from the tail of the current one, and there is no set-up worth overlapping.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kfn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool on = [] { const char* e = std::getenv("FOCAL_B200_PDL"); return e && e[0] == '1'; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kfn, static_cast<KArgs>(args)...);
+}
+
 template <int MODE, int KB, int SEQ, int EL>
 int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st, int grid) {
   using G = GramCfg<MODE, KB, SEQ, EL>;
@@ -108,7 +125,7 @@ int launch_gram(const Plan& p, const ProbSel& sel, uint8_t* ws, cudaStream_t st,
   auto kfn = gram_kernel<MODE, KB, SEQ, EL>;
   if (int rc = ensure_dyn_smem(kfn, L::kDynamic, "cudaFuncSetAttribute(gram_kernel)")) return rc;
   if (grid <= 0) return FOCAL_OK;                                 // persistent: at most one CTA per SM (plan.h)
-  kfn<<<grid, G::kThreads, L::kDynamic, st>>>(p, sel, ws);
+  launch_pdl(kfn, dim3(grid), dim3(G::kThreads), L::kDynamic, st, p, sel, ws);
   return cuda_ok("gram_kernel launch");
 }
 
@@ -315,7 +332,7 @@ int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uin
     nrep = forced > 0 ? forced : 1;
     while (nrep > 1 && ((long)p.nblk1 * nrep > 4L * p.num_sms || pw.world % nrep)) nrep /= 2;
   }
-  prologue_v3_kernel<S, NQ, PREC><<<dim3(p.nblk1 + pad_blocks, nrep), 32 * p.seqb * p.nT, smem, st>>>(p, f, pw, w);
+  launch_pdl(prologue_v3_kernel<S, NQ, PREC>, dim3(p.nblk1 + pad_blocks, nrep), dim3(32 * p.seqb * p.nT), smem, st, p, f, pw, w);
   return cuda_ok("prologue_v3_kernel");
 }
 template <int S, int NQ, int PREC>
@@ -324,8 +341,8 @@ int launch_finalize_v3_t(const Plan& p, const FeatPtrs& f, const GradPtrs& g, co
   const size_t smem = row_v3_smem(p);
   if (int rc = ensure_dyn_smem(finalize_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(finalize_v3_kernel)")) return rc;
   const int grid = (p.seq1 - p.seq0 + p.seqb - 1) / p.seqb + 1;          // + the block that reduces the loss partials
-  finalize_v3_kernel<S, NQ, PREC><<<grid, 32 * p.seqb * p.nT, smem, st>>>(p, f, g, pw, w, loss5, lse_blocks(p, 0),
-                                                                           temporal_degenerate(p) ? 1 : 0);
+  launch_pdl(finalize_v3_kernel<S, NQ, PREC>, dim3(grid), dim3(32 * p.seqb * p.nT), smem, st, p, f, g, pw, w, loss5,
+             lse_blocks(p, 0), temporal_degenerate(p) ? 1 : 0);
   return cuda_ok("finalize_v3_kernel");
 }
 #define FB_V3_CASE(FN, SS, QQ, ...)                                                                   \
@@ -524,7 +541,8 @@ int focal_b200_nce_lse(const FocalCfg* cfg, void* ws, size_t ws_bytes, int all_r
   if (rc) return rc;
   if ((rc = check_ws(p, ws, ws_bytes))) return rc;
   if (!(p.terms & FOCAL_TERM_NCE)) return FOCAL_OK;
-  nce_lse_kernel<<<lse_blocks(p, all_rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, solo(ws), static_cast<uint8_t*>(ws), all_rows);
+  launch_pdl(nce_lse_kernel, dim3(lse_blocks(p, all_rows)), dim3(256), 0, static_cast<cudaStream_t>(stream), p, solo(ws),
+             static_cast<uint8_t*>(ws), all_rows);
   return cuda_ok("nce_lse_kernel");
 }
 
@@ -737,7 +755,7 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   if (nce) {
     if ((rc = launch_nce<NCE_FWD>(p, w, st, sync_sel(true, true)))) return rc;
     tm.mark(st);
-    nce_lse_kernel<<<lse_blocks(p, 0), 256, 0, st>>>(p, pw, w, 0);
+    launch_pdl(nce_lse_kernel, dim3(lse_blocks(p, 0)), dim3(256), 0, st, p, pw, w, 0);
     if ((rc = cuda_ok("nce_lse_kernel"))) return rc;
     pending = multi;
     tm.mark(st);

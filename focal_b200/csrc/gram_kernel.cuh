@@ -278,6 +278,21 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
+// Exchange lane bit LB with register-index bit RB of a 32 x 32 block held as v[column] in lane = row: afterwards lane L,
+// register c holds the element whose (row, column) are (L, c) with those two bits swapped.  16 shuffles.
+template <int LB, int RB>
+__device__ __forceinline__ void xchg_lane_reg_bit(float (&v)[32], int lane) {
+  const bool hi = ((lane >> LB) & 1) != 0;
+#pragma unroll
+  for (int a = 0; a < 32; ++a) {
+    if (a & (1 << RB)) continue;
+    constexpr int kB = 1 << RB;
+    const float send = hi ? v[a] : v[a | kB];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1 << LB);
+    if (hi) v[a] = recv; else v[a | kB] = recv;
+  }
+}
+
 template <int MODE, int KB, int SEQ, int EL>
 __global__ void __launch_bounds__((GramCfg<MODE, KB, SEQ, EL>::kThreads), 1)
 gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel, uint8_t* __restrict__ ws) {
@@ -308,6 +323,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   // warp-uniform role index (the compiler must be able to prove uniformity, see the issue-loop note below)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();      // the next launch may be scheduled; it waits for this grid's completion itself
+  if (threadIdx.x == 0) FB_TRACE_EV(0, 0u, 2);       // kernel entry
   if (threadIdx.x == 0) {
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
@@ -328,6 +345,8 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
     tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
   }
+  // everything above overlapped the tail of the previous launch; from here on its results are needed
+  pdl_wait();
   // row-sharded path: the launch before this one stored operands / row sums into the peers' workspaces -- tell them
   if (sel.ann_world > 0 && blockIdx.x == 0) peer_announce_epoch(p, sel.peer_ws, sel.ann_world, sel.ann_rank);
   if (sel.peer_wait > 0) {
@@ -341,6 +360,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
   const int n_items = gram_num_items<MODE>(p, sel);
+  if (threadIdx.x == 0) FB_TRACE_EV(0, 0u, 3);       // set-up done (barriers, TMEM, peer wait)
 
   // Issue-loop note (measured, tools/umma_rate.py / tools/tma_rate.py): tcgen05.mma, tcgen05.commit and cp.async.bulk
   // take their operands from uniform registers.  If ptxas cannot prove an operand warp-uniform it wraps EVERY such
@@ -360,6 +380,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         gram_decode<MODE, BN>(p, sel, ws, it, x);
         x.ct_begin = pt0; x.ct_end = pt1;
         mbar_wait_warp(&bars->a_empty, (ni & 1) ^ 1);
+        FB_TRACE_EV(0, nb, 1);                        // A tile of the piece that starts with column tile nb requested
         if (elect_one()) {
           mbar_arrive_expect_tx(&bars->a_full, L::kABytes);
 #pragma unroll
@@ -816,19 +837,33 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
           if (!second && trow == 0)
             reinterpret_cast<int32_t*>(ws + p.flag_tmp_off)[(uint64_t)x.c * (p.Bpad / kTileM) + row0 / kTileM] = npi - 1;
         }
+        // Each lane holds one row of O (32 columns per tcgen05.ld).  Stored as they are, a warp's 16-byte stores go to 32
+        // different 128-byte lines -- 32 L1 tag cycles per instruction, ~12 000 clk per 128 x 256 accumulator
+        // (profiles/r2_timeline_r8.txt), paid at the end of every stream-K piece with the tensor pipe idle.  Three
+        // lane-bit <-> register-bit exchanges turn the 32 x 32 block so that 8 lanes write the 128 bytes of one row: 4
+        // lines per instruction.
+        const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+        const size_t ostride = kIsNce ? (size_t)kON : (size_t)(KB * G::kEPB);
+        float* out_w = out - (size_t)lane * ostride;       // row of lane 0 of this warp
 #pragma unroll 1
         for (int ch = wgi; ch < kON / 32; ch += NG) {    // the warpgroups split the columns of O
           float v[32];
           tmem_ld32(tmem + tlane + kOCol + ch * 32, v);
           tmem_ld_wait();
-          if (row_ok) {
+          xchg_lane_reg_bit<0, 2>(v, lane);
+          xchg_lane_reg_bit<1, 3>(v, lane);
+          xchg_lane_reg_bit<2, 4>(v, lane);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(out + ch * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 8; ++j) {                  // register 4 j + e: row (lane & 24) | j, column 4 (lane & 7) + e
+            const int r = (lane & 24) | j;
+            if ((okmask >> r) & 1u)
+              *reinterpret_cast<float4*>(out_w + (size_t)r * ostride + ch * 32 + 4 * (lane & 7)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
         tc_fence_before();
         mbar_arrive(&bars->o_empty);
+        FB_TRACE_EV(2 + wgi, nb - 1, 3);              // O accumulator of the piece that ended with tile nb - 1 written out
       }
       if (MODE != NCE_BWD) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // partial arrays / red[] may be reused now
@@ -848,6 +883,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FB_TRACE_EV(0, 1u, 2);       // kernel exit
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 

@@ -364,4 +364,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Byte offset of the 16-byte chunk (row r, chunk c of 8) inside a SWIZZLE_128B tile whose rows are 128 B.
 __device__ __host__ __forceinline__ uint32_t swz128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
+// Programmatic dependent launch (launches made with fb::launch_pdl in focal_b200.cu): a kernel lets the next launch on
+// the stream be scheduled early (its blocks become resident and run their set-up while this grid drains), and waits
+// itself -- before it first touches global memory -- until the grid before it has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace fb

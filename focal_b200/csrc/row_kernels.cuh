@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(128) intra_kernel(const __grid_constant__ Plan
 __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Plan p,
                                                       const __grid_constant__ PeerWs pw, uint8_t* __restrict__ ws,
                                                       int all_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][2];
   const long n = (long)p.nProb * p.S * 2 * p.bpad;
   float ls = 0.f, lp = 0.f;

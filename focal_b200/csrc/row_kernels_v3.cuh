@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
                                                              uint8_t* __restrict__ ws) {
   constexpr int LPR = 32 / S;
   extern __shared__ float smem_f[];
+  pdl_launch_dependents();
+  pdl_wait();
   // blocks behind the row blocks (single-GPU launches only): zero the padding rows of the operand arrays -- no launch of
   // its own for that
   if ((int)blockIdx.x >= p.nblk1) {
@@ -384,6 +386,8 @@ __global__ void __launch_bounds__(256, FB_FIN_MINBLOCKS) finalize_v3_kernel(cons
                                                              int nce_blocks_valid, int temporal_nan) {
   constexpr int LPR = 32 / S;
   extern __shared__ float smem_f[];
+  pdl_launch_dependents();
+  pdl_wait();
   // The last block adds up the loss partials of the step (they were all written by earlier launches): the step needs no
   // separate loss_reduce launch, and on the row-sharded path the ranks' loss exchange overlaps the gradient rows.
   if (blockIdx.x == gridDim.x - 1) {

@@ -28,11 +28,12 @@ def run(stage="temporal"):
     lib = _cabi.load(os.path.join(ROOT, "focal_b200", "libfocal_b200_trace.so"))
     B, D, M, S = int(os.environ.get("FB_B", 8192)), int(os.environ.get("FB_D", 256)), 2, 4
     prec = int(os.environ.get("FB_PREC", 0))
+    R = int(os.environ.get("FB_R", 1))                 # FB_R = 8: one rank's share of a row-sharded step (owned rows = 1/8)
     cfg = _cabi.FocalCfg(B=B, S=S, M=M, D=D, temperature=0.5, margin=1.0, w_shared=1, w_private=1, w_orth=3, w_rank=5,
-                         need_grad=1, terms=7, seq_begin=0, seq_end=B // S, precision=prec)
+                         need_grad=1, terms=7, seq_begin=0, seq_end=B // S // R, precision=prec)
     info = _cabi.FocalWsInfo()
     assert lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info)) == 0
-    raw = torch.empty(info.total_bytes + 1024, dtype=torch.uint8, device="cuda")
+    raw = torch.zeros(info.total_bytes + 1024, dtype=torch.uint8, device="cuda")
     off = (-raw.data_ptr()) % 1024
     wsp, wsn = C.c_void_p(raw.data_ptr() + off), C.c_size_t(info.total_bytes)
     feats = [torch.randn(B, D, device="cuda") for _ in range(2 * M)]
@@ -58,6 +59,9 @@ def run(stage="temporal"):
     lib.focal_b200_debug_trace.argtypes = [C.c_void_p, C.c_size_t]
     assert lib.focal_b200_debug_trace(buf, n) == 0
     tr = np.frombuffer(buf, dtype=np.int64).reshape(BLOCKS, ROLES, TILES, TAGS)
+    if os.environ.get("FB_TIMELINE"):
+        timeline(tr)
+        return
     for cta in (0, 74):
         t = tr[cta]
         nz = t[t > 0]
@@ -75,6 +79,26 @@ def run(stage="temporal"):
         # per-tile period of the issuer over tiles 8..40
         u1 = rel[1, 8:40, 0]
         print("   mean UMMA#1 issue period (tiles 8-40):", float(np.diff(u1[u1 >= 0]).mean()) if (u1 >= 0).sum() > 2 else None)
+
+
+def timeline(tr):
+    """Whole-kernel timeline of a few CTAs (clk since the CTA entered the kernel): set-up, per piece the A request, per
+    tile UMMA#1 issue / UMMA#2 done / slowest epilogue done, O written out, kernel exit."""
+    import numpy as np
+    for cta in (0, 37, 74, 111, 147):
+        t = tr[cta]
+        t0 = t[0, 0, 2]
+        if t0 <= 0:
+            continue
+        rel = np.where(t > 0, t - t0, -1)
+        ntile = int((rel[1, :, 0] >= 0).sum())
+        print(f"--- CTA {cta}: set-up done {rel[0, 0, 3]}, {ntile} tiles, exit {rel[0, 1, 2]} clk")
+        for n_ in range(ntile):
+            a = rel[0, n_, 1]
+            epi = max(int(rel[2 + g, n_, 2]) for g in range(4))
+            odone = max(int(rel[2 + g, n_, 3]) for g in range(4))
+            print(f"   tile {n_:3d}: " + (f"A req {a:7d} " if a >= 0 else " " * 14) + f"B req {rel[0, n_, 0]:7d}  U1 {rel[1, n_, 0]:7d}  U2 done {rel[1, n_, 3]:7d}"
+                  f"  epi done {epi:7d}" + (f"  O out {odone:7d}" if odone >= 0 else ""))
 
 
 if __name__ == "__main__":
