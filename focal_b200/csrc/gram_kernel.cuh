@@ -511,6 +511,10 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
                 if (elect_one()) {
                   issue_gram(tmem + kSCol + ss * BN, db0 + (uint64_t)(st * (L::kBStage >> 4)));
                   umma_commit(&bars->s_full[ss]);
+                  // The A tile is only read by UMMA #1: hand it back as soon as the LAST one of the piece has executed,
+                  // so the next piece's A load overlaps this piece's last epilogue + UMMA #2 (it used to start after
+                  // them: ~7 700 clk lost per piece boundary of the temporal launch, profiles/r2_timeline_r1.txt).
+                  if (t1 + 1 == ntiles) umma_commit(&bars->a_empty);
                 }
                 __syncwarp();
                 FB_TRACE_EV(1, n, 1);
@@ -523,12 +527,13 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         }
         nb += ntiles;
         if (elect_one()) {
-          umma_commit(&bars->a_empty);
+          if (!kBwd || ntiles == 0) umma_commit(&bars->a_empty);   // backward: went out behind the last UMMA #1 above
           if (kBwd) umma_commit(&bars->o_full);
         }
         __syncwarp();
       }
-      // commits complete in issue order: once the last one has landed no arrival is still in flight
+      // Commits complete in issue order.  Forward passes: once the last a_empty has landed no arrival is still in flight.
+      // Backward passes: the last commit is o_full, which the epilogue warps wait for before the final __syncthreads.
       if (ni > 0) mbar_wait_warp(&bars->a_empty, (ni - 1) & 1);
     }
   } else {
