@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("FOCAL_B200_LIB") or os.path.join(_PKG, "libfocal_b200
 FOCAL_TERM_NCE, FOCAL_TERM_ORTH, FOCAL_TERM_TEMPORAL, FOCAL_TERM_ALL = 1, 2, 4, 7
 FOCAL_PREC_BF16, FOCAL_PREC_FP32 = 0, 1
 FOCAL_MAX_MODALITIES = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 FOCAL_OK, FOCAL_EINVAL, FOCAL_ESHAPE, FOCAL_ECUDA, FOCAL_EWORKSPACE = 0, -1, -2, -3, -4
 
 EXPORTS = (
@@ -40,7 +40,7 @@ class FocalCfg(C.Structure):
 
 
 class FocalPeers(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ws", C.c_void_p * 8)]
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("ws", C.c_void_p * 8), ("mc", C.c_void_p)]
 
 
 class FocalWsInfo(C.Structure):

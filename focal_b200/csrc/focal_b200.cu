@@ -324,7 +324,7 @@ int launch_prologue_v3_t(const Plan& p, const FeatPtrs& f, const PeerWs& pw, uin
   const size_t smem = row_v3_smem(p);
   if (int rc = ensure_dyn_smem(prologue_v3_kernel<S, NQ, PREC>, smem, "cudaFuncSetAttribute(prologue_v3_kernel)")) return rc;
   // row shards: the launch can be replicated, the replicas sharing the peers among them (see the kernel).  Measured
-  // at 4 GPUs (gpurun_out/r2_prologue_dbg_4.txt): 4 replicas 79 us, 1 replica 60 us -- so the default is 1; the knob stays
+  // at 4 GPUs (profiles/r2_prologue_dbg_4.txt): 4 replicas 79 us, 1 replica 60 us -- so the default is 1; the knob stays
   // for experiments.
   int nrep = 1;
   if (pw.world > 1) {
@@ -707,7 +707,8 @@ int focal_b200_loss_sharded(const FocalCfg* cfg, const float* const* feats, cons
   if (peers->world < 1 || peers->world > kMaxPeers || peers->rank < 0 || peers->rank >= peers->world) return FOCAL_EINVAL;
   PeerWs pw{};
   pw.rank = peers->rank; pw.world = peers->world;
-  { static const int dbg = [] { const char* e = std::getenv("FOCAL_B200_PROLOGUE_DBG"); return e ? std::atoi(e) : 0; }(); pw.dbg = dbg; }
+  // the multicast mapping only serves the kernels that know it (prologue_v3, nce_lse); the older row kernels store per peer
+  pw.mc = (peers->world > 1 && p.rowgen == 3) ? static_cast<uint8_t*>(peers->mc) : nullptr;
   for (int r = 0; r < pw.world; ++r) {
     if ((rc = check_ws(p, peers->ws[r], ws_bytes))) return rc;
     pw.ws[r] = static_cast<uint8_t*>(peers->ws[r]);

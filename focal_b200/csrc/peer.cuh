@@ -60,7 +60,7 @@ __device__ __forceinline__ void peer_barrier(const Plan& p, const PeerWs& pw) {
 // announcement itself is sent by block 0 of the NEXT launch on the stream (peer_announce_epoch below), when stream order
 // has already completed every store of the producer.  (The first version announced from the last block to finish, which
 // needed a system fence + an atomic at the end of EVERY block: measured 11-15 us of the prologue and 6 us of nce_lse at
-// 4 GPUs -- gpurun_out/r2_prologue_dbg_4.txt.)
+// 4 GPUs -- profiles/r2_prologue_dbg_4.txt.)
 __device__ __forceinline__ void peer_epoch_bump(const Plan& p, uint8_t* ws) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     uint32_t* mine = reinterpret_cast<uint32_t*>(ws + p.bar_off);

@@ -135,9 +135,8 @@ struct PtrTable {
 constexpr int kMaxPeers = 8;
 struct PeerWs {
   int32_t rank, world;
-  int32_t dbg, pad_;          // experiments (FOCAL_B200_PROLOGUE_DBG): bits 1 / 2 / 4 keep the InfoNCE operand / temporal operand /
-                              // per-row scalar stores of the prologue in the own workspace (timing only: results are wrong)
   uint8_t* ws[kMaxPeers];
+  uint8_t* mc;                // NVSwitch multicast mapping of all workspaces (nullptr: store to every ws[r] instead)
 };
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }

@@ -364,6 +364,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Byte offset of the 16-byte chunk (row r, chunk c of 8) inside a SWIZZLE_128B tile whose rows are 128 B.
 __device__ __host__ __forceinline__ uint32_t swz128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
+// NVSwitch multicast stores (row-sharded path): one store to a multicast address lands in the workspace of every rank.
+// Plain bit copies -- the .f32 type only names the element size.
+__device__ __forceinline__ void mc_st16(void* p, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+__device__ __forceinline__ void mc_st8(void* p, const uint2& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)) : "memory");
+}
+__device__ __forceinline__ void mc_st4(void* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // Programmatic dependent launch (launches made with fb::launch_pdl in focal_b200.cu): a kernel lets the next launch on
 // the stream be scheduled early (its blocks become resident and run their set-up while this grid drains), and waits
 // itself -- before it first touches global memory -- until the grid before it has completed and its writes are visible.

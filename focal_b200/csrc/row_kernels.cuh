@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(256) nce_lse_kernel(const __grid_constant__ Pl
       float r = 0.f;
       for (int sp = 0; sp < p.nsplit_fwd; ++sp) r += rp[(long)sp * n + e];
       // row-sharded jobs: every rank needs r and 1/r of every row -> store into all workspaces (pw.world == 1 otherwise)
-      for (int rk = 0; rk < pw.world; ++rk) {
+      if (pw.mc) {                      // NVSwitch multicast: one store serves every rank
+        mc_st4(pw.mc + p.rsum_off + (uint64_t)e * 4, r);
+        mc_st4(pw.mc + p.rinv_off + (uint64_t)e * 4, 1.f / r);
+      } else for (int rk = 0; rk < pw.world; ++rk) {
         reinterpret_cast<float*>(pw.ws[rk] + p.rsum_off)[e] = r;
         reinterpret_cast<float*>(pw.ws[rk] + p.rinv_off)[e] = 1.f / r;
       }

@@ -206,8 +206,18 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         uint4 cls = make_uint4(0u, 0u, 0u, 0u), clp = cls;
         if (PREC == FOCAL_PREC_FP32) { cls = pair_chunk(ls[0], ls[1], odd); clp = pair_chunk(lp[0], lp[1], odd); }
         const uint64_t o = op_off16(rowsNce, rowN, 4 * ((k + (odd ? 1 : 0)) * LPR + (l & ~1)));
-        for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* w = (pw.dbg & 1) ? ws : pw.ws[rk];
+        if (pw.mc) {                                          // one multicast store serves every rank
+          if (rep0) {
+            uint8_t* w = pw.mc;
+            mc_st16(w + off_s + o, cs);
+            mc_st16(w + off_p + o, cp);
+            if (PREC == FOCAL_PREC_FP32) {
+              mc_st16(w + off_s + lo_img + o, cls);
+              mc_st16(w + off_p + lo_img + o, clp);
+            }
+          }
+        } else for (int rk = rep; rk < pw.world; rk += nrep) {
+          uint8_t* w = pw.ws[rk];
           *reinterpret_cast<uint4*>(w + off_s + o) = cs;
           *reinterpret_cast<uint4*>(w + off_p + o) = cp;
           if (PREC == FOCAL_PREC_FP32) {
@@ -226,8 +236,18 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         round4<PREC>(zs, rr, hs, ls);
         round4<PREC>(zp, rr, hp, lp);
         const uint64_t o = op_off8(rowsNce, rowN, c);
-        for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* w = (pw.dbg & 1) ? ws : pw.ws[rk];
+        if (pw.mc) {                                          // one multicast store serves every rank
+          if (rep0) {
+            uint8_t* w = pw.mc;
+            mc_st8(w + off_s + o, hs);
+            mc_st8(w + off_p + o, hp);
+            if (PREC == FOCAL_PREC_FP32) {
+              mc_st8(w + off_s + lo_img + o, ls);
+              mc_st8(w + off_p + lo_img + o, lp);
+            }
+          }
+        } else for (int rk = rep; rk < pw.world; rk += nrep) {
+          uint8_t* w = pw.ws[rk];
           *reinterpret_cast<uint2*>(w + off_s + o) = hs;
           *reinterpret_cast<uint2*>(w + off_p + o) = hp;
           if (PREC == FOCAL_PREC_FP32) {
@@ -238,8 +258,18 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
       }
       if (d & 63) {                                           // d = 32 or 96: zero the unused half of the last K block
         const uint64_t o = op_off8(rowsNce, rowN, 4 * (NQ * LPR + l));
-        for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* w = (pw.dbg & 1) ? ws : pw.ws[rk];
+        if (pw.mc) {                                          // one multicast store serves every rank
+          if (rep0) {
+            uint8_t* w = pw.mc;
+            mc_st8(w + off_s + o, make_uint2(0u, 0u));
+            mc_st8(w + off_p + o, make_uint2(0u, 0u));
+            if (PREC == FOCAL_PREC_FP32) {
+              mc_st8(w + off_s + lo_img + o, make_uint2(0u, 0u));
+              mc_st8(w + off_p + lo_img + o, make_uint2(0u, 0u));
+            }
+          }
+        } else for (int rk = rep; rk < pw.world; rk += nrep) {
+          uint8_t* w = pw.ws[rk];
           *reinterpret_cast<uint2*>(w + off_s + o) = make_uint2(0u, 0u);
           *reinterpret_cast<uint2*>(w + off_p + o) = make_uint2(0u, 0u);
           if (PREC == FOCAL_PREC_FP32) {
@@ -262,8 +292,18 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         if (PREC == FOCAL_PREC_FP32) { cls = pair_chunk(lsh[k], lsh[k + 1], odd); clp = pair_chunk(lpr[k], lpr[k + 1], odd); }
         const int cc = 4 * ((k + (odd ? 1 : 0)) * LPR + (l & ~1));
         const uint64_t o1 = op_off16(krows, (uint64_t)i, cc), o2 = op_off16(krows, (uint64_t)i, d + cc);
-        for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* xt = ((pw.dbg & 2) ? ws : pw.ws[rk]) + xoff;
+        if (pw.mc) {                                          // one multicast store serves every rank
+          if (rep0) {
+            uint8_t* xt = pw.mc + xoff;
+            mc_st16(xt + o1, cs);
+            mc_st16(xt + o2, cp);
+            if (PREC == FOCAL_PREC_FP32) {
+              mc_st16(xt + lo_img + o1, cls);
+              mc_st16(xt + lo_img + o2, clp);
+            }
+          }
+        } else for (int rk = rep; rk < pw.world; rk += nrep) {
+          uint8_t* xt = pw.ws[rk] + xoff;
           *reinterpret_cast<uint4*>(xt + o1) = cs;
           *reinterpret_cast<uint4*>(xt + o2) = cp;
           if (PREC == FOCAL_PREC_FP32) {
@@ -276,8 +316,18 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         constexpr int k = NQ - 1;
         const int c = 4 * (k * LPR + l);
         const uint64_t o1 = op_off8(krows, (uint64_t)i, c), o2 = op_off8(krows, (uint64_t)i, d + c);
-        for (int rk = rep; rk < pw.world; rk += nrep) {
-          uint8_t* xt = ((pw.dbg & 2) ? ws : pw.ws[rk]) + xoff;
+        if (pw.mc) {                                          // one multicast store serves every rank
+          if (rep0) {
+            uint8_t* xt = pw.mc + xoff;
+            mc_st8(xt + o1, hsh[k]);
+            mc_st8(xt + o2, hpr[k]);
+            if (PREC == FOCAL_PREC_FP32) {
+              mc_st8(xt + lo_img + o1, lsh[k]);
+              mc_st8(xt + lo_img + o2, lpr[k]);
+            }
+          }
+        } else for (int rk = rep; rk < pw.world; rk += nrep) {
+          uint8_t* xt = pw.ws[rk] + xoff;
           *reinterpret_cast<uint2*>(xt + o1) = hsh[k];
           *reinterpret_cast<uint2*>(xt + o2) = hpr[k];
           if (PREC == FOCAL_PREC_FP32) {
@@ -286,7 +336,11 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
           }
         }
       }
-      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(((pw.dbg & 4) ? ws : pw.ws[l]) + p.sq_off)[(uint64_t)t * p.Bpad + i] = q4[2];
+      if (pw.mc) {
+        if (l == 0 && rep0) mc_st4(pw.mc + p.sq_off + ((uint64_t)t * p.Bpad + i) * 4, q4[2]);
+      } else if (l < pw.world && l % nrep == rep) {
+        reinterpret_cast<float*>(pw.ws[l] + p.sq_off)[(uint64_t)t * p.Bpad + i] = q4[2];
+      }
     }
     // ---- orthogonality (loss.py:96-104), pair (shared_t, private_t)
     if (owned && orth_on) acc_orth = fmaxf(q4[3] * rsqrtf((na + kOrthEps) * (nb + kOrthEps)), 0.f);
@@ -320,7 +374,11 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
         float4 pd4 = make_float4(d2[0], S > 2 ? d2[(S > 2) ? 1 : 0] : 0.f, S > 2 ? d2[(S > 2) ? 2 : 0] : 0.f, 0.f);
         *reinterpret_cast<float4*>(ws + p.pd_off + ((uint64_t)t * p.Bpad + i) * 16) = pd4;
       }
-      if (l < pw.world && l % nrep == rep) reinterpret_cast<float*>(((pw.dbg & 4) ? ws : pw.ws[l]) + p.mintra_off)[(uint64_t)t * p.Bpad + i] = m;
+      if (pw.mc) {
+        if (l == 0 && rep0) mc_st4(pw.mc + p.mintra_off + ((uint64_t)t * p.Bpad + i) * 4, m);
+      } else if (l < pw.world && l % nrep == rep) {
+        reinterpret_cast<float*>(pw.ws[l] + p.mintra_off)[(uint64_t)t * p.Bpad + i] = m;
+      }
     }
   }
   __syncthreads();

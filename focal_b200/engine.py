@@ -20,6 +20,7 @@ P_kj + P_jk for its own rows -- no gradient reduce-scatter is needed.  Two imple
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -233,6 +234,15 @@ class CudaBackend:
         own = C.c_void_p()
         handle = C.create_string_buffer(64)
         ok = lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info)) == 0
+        # NVSwitch multicast stores: measured slower than per-peer stores at 2 GPUs (prologue 60 vs 37 us: every byte,
+        # the rank's own copy included, crosses the switch at ~200 GB/s of multimem.st egress), so "auto" only takes
+        # them where they cut the egress 8-fold
+        mc_env = os.environ.get("FOCAL_B200_MULTICAST", "auto")
+        if ok and world > 1 and (mc_env == "1" or (mc_env == "auto" and world >= 8)):
+            ent = self._symm_setup(int(info.total_bytes), group, dev, world, rank)
+            if ent is not None:
+                self._peers[key] = ent
+                return ent
         ok = ok and lib.focal_b200_peer_alloc(info.total_bytes, C.byref(own), handle) == 0
         got: List[Optional[tuple]] = [None] * world
         dist.all_gather_object(got, (bool(ok), handle.raw, int(info.total_bytes)), group=group)
@@ -263,6 +273,41 @@ class CudaBackend:
         self._peers[key] = (peers, int(info.total_bytes), opened, own)
         return self._peers[key]
 
+    def _symm_setup(self, total_bytes: int, group, dev: torch.device, world: int, rank: int):
+        """Workspaces from torch's symmetric memory: besides the peer mappings it hands out an NVSwitch MULTICAST address
+        of the same buffers, so the kernels store the operands / row sums of the owned rows once (multimem.st) instead of
+        once per peer.  Collective over ``group``; None (on every rank) when any rank has no multicast support -- the
+        caller then falls back to cudaMalloc + CUDA IPC."""
+        import torch.distributed as dist
+        t = h = None
+        try:                                                # ask first: rendezvous is collective, nobody may enter it alone
+            import torch.distributed._symmetric_memory as symm
+            can = bool(symm._SymmetricMemory.has_multicast_support(symm.DeviceType.CUDA, dev.index))
+        except Exception:
+            can = False
+        cans: List[Optional[bool]] = [None] * world
+        dist.all_gather_object(cans, can, group=group)
+        if not all(cans):
+            return None
+        try:
+            t = symm.empty(total_bytes, dtype=torch.uint8, device=dev)
+            h = symm.rendezvous(t, group.group_name)
+            mine_ok = bool(h.multicast_ptr) and len(h.buffer_ptrs) == world and t.data_ptr() % 1024 == 0
+        except Exception:                                   # no symmetric memory in this build / on this fabric
+            mine_ok = False
+        flags: List[Optional[bool]] = [None] * world
+        dist.all_gather_object(flags, bool(mine_ok), group=group)
+        if not all(flags):
+            return None
+        t.zero_()                                           # barrier epochs start at 0; padding rows are never written
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                           # nobody stores into a workspace that is not zeroed yet
+        peers = _cabi.FocalPeers(rank=rank, world=world)
+        for r in range(world):
+            peers.ws[r] = int(h.buffer_ptrs[r])
+        peers.mc = int(h.multicast_ptr)
+        return (peers, total_bytes, [], C.c_void_p(), (t, h))
+
     def close(self) -> None:
         """Release the peer-memory resources (IPC mappings, the cudaMalloc'ed workspaces) and the cached workspaces.
         Every rank must have finished its last step (callers barrier first): peers may still be storing into a
@@ -272,7 +317,7 @@ class CudaBackend:
         for ent in self._peers.values():
             if ent is None:
                 continue
-            _, _, opened, own = ent
+            opened, own = ent[2], ent[3]
             for p in opened:
                 self.lib.focal_b200_peer_close(p)
             if own.value:

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FOCAL_B200_ABI_VERSION 4
+#define FOCAL_B200_ABI_VERSION 5
 #define FOCAL_MAX_MODALITIES 8
 
 enum {
@@ -150,6 +150,11 @@ int focal_b200_loss(const FocalCfg* cfg, const float* const* feats, void* ws, si
 typedef struct FocalPeers {
   int32_t rank, world;
   void* ws[FOCAL_MAX_PEERS];   /* this process's mapping of every rank's workspace; ws[rank] is its own */
+  void* mc;                    /* optional (NULL = none): an NVSwitch MULTICAST mapping of the same workspaces -- a store to
+                                * mc + off lands at ws[r] + off of every rank r.  With it the kernels send the operands and
+                                * row sums of the owned rows once (multimem.st) instead of once per peer.  The workspaces
+                                * then come from a multicast-capable allocator (e.g. torch symmetric memory), zeroed, not
+                                * from focal_b200_peer_alloc. */
 } FocalPeers;
 
 /* cudaMalloc + zero-fill + cudaIpcGetMemHandle; the workspace must come from here so that peers can map it. */
