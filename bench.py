@@ -593,10 +593,14 @@ def run_ours(args):
 
 
 def launches_per_step(engine, B, D, world):
-    """Kernels of libfocal_b200.so per step: [zero_pad], prologue (fused intra), nce_rowsum, nce_lse, nce_grad, temporal,
-    finalize, loss_reduce (+ nce_lse(all rows) on the collective multi-GPU path; the peer path has no extra launches:
-    its barriers are split into the producing and consuming kernels).  Counted from the plan of this workload."""
+    """Kernels of libfocal_b200.so per step, counted from the plan of this workload (plan.h / focal_b200.cu).
+    Third-generation row kernels (S in {1, 2, 4}, D/2 * S a multiple of 128 and <= 512, D <= 256, <= 8 tensors):
+    prologue_v3 (zeroes the padding rows itself), nce_rowsum, nce_lse, nce_grad, temporal, finalize_v3 (its last block is
+    the loss reduction).  Older row kernels: [zero_pad], prologue, [intra], ..., finalize, loss_reduce.  The collective
+    multi-GPU path adds nce_lse over all rows; the peer path has no extra launches (its barriers live at the head of
+    the consuming kernels).  + set_ptrs before every graph replay."""
     import ctypes as C
+    import os
 
     from focal_b200 import _cabi
     hp = engine.hp
@@ -605,17 +609,20 @@ def launches_per_step(engine, B, D, world):
     info = _cabi.FocalWsInfo()
     _cabi.check(be.lib.focal_b200_workspace_info(C.byref(cfg), C.byref(info)), "workspace_info")
     peer = world > 1 and any(v is not None for v in getattr(be, "_peers", {}).values())
+    S, d, nT = hp.seq_len, D // 2, 2 * len(hp.modalities)
+    v3 = (not hp.no_private and D % 2 == 0 and S in (1, 2, 4) and (d * S) % 128 == 0 and d * S // 128 <= 4 and D <= 256
+          and nT <= 8 and os.environ.get("FOCAL_B200_ROW_KERNELS") not in ("v1", "v2"))
     n = 0
-    if not peer:
+    if not peer and not v3:
         n += 1 if (info.bpad != info.b or info.Bpad != B) else 0    # zero_pad_kernel (peer workspaces start zeroed)
     n += 1                                                          # prologue (m_II fused for S in {2, 4})
-    n += 0 if hp.seq_len in (2, 4) or not (hp.terms & 4) else 1     # separate intra_kernel otherwise
+    n += 0 if S in (2, 4) or v3 or not (hp.terms & 4) else 1        # separate intra_kernel otherwise
     if hp.terms & 1:
         n += 3                                                      # nce_rowsum, nce_lse, nce_grad
         n += 1 if (world > 1 and not peer) else 0                   # collective path: nce_lse again over all rows
-    if (hp.terms & 4) and hp.seq_len > 1:
+    if (hp.terms & 4) and S > 1:
         n += 1                                                      # temporal
-    n += 2                                                          # finalize, loss_reduce
+    n += 1 if v3 else 2                                             # finalize (+ loss_reduce on the older path)
     n += 1 if engine.use_cuda_graph else 0                          # set_ptrs before every graph replay
     return n
 
