@@ -81,3 +81,37 @@ def test_product_never_imports_the_oracle(repo_root):
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, fn)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(root, fn)
+
+
+def test_o_drain_turn_maps_eight_lanes_to_one_row():
+    """The O-accumulator drain of the Gram kernels (gram_kernel.cuh: xchg_lane_reg_bit<0, 2>, <1, 3>, <2, 4>) restated in
+    numpy: a 32 x 32 block held as v[lane = row][register = column] ends up with register 4 j + e of lane L holding
+    row (L & 24) | j, column 4 (L & 7) + e -- so the 8 lanes L & 7 = 0..7 store the 128 bytes of one row."""
+    import numpy as np
+    rows, cols = np.meshgrid(np.arange(32), np.arange(32), indexing="ij")
+    v = np.stack([rows, cols], axis=-1)                       # v[lane, reg] = (row, col) of the element held there
+
+    def xchg(v, lb, rb):
+        out = v.copy()
+        for lane in range(32):
+            hi = (lane >> lb) & 1
+            partner = lane ^ (1 << lb)
+            for a in range(32):
+                if a & (1 << rb):
+                    continue
+                b = a | (1 << rb)
+                send_of_partner = v[partner, a] if ((partner >> lb) & 1) else v[partner, b]
+                if hi:
+                    out[lane, a] = send_of_partner
+                else:
+                    out[lane, b] = send_of_partner
+        return out
+
+    for lb, rb in ((0, 2), (1, 3), (2, 4)):
+        v = xchg(v, lb, rb)
+    for lane in range(32):
+        for j in range(8):
+            for e in range(4):
+                assert tuple(v[lane, 4 * j + e]) == ((lane & 24) | j, 4 * (lane & 7) + e)
+    # every element exactly once
+    assert len({tuple(x) for x in v.reshape(-1, 2)}) == 1024
