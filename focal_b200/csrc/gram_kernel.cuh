@@ -84,6 +84,9 @@ enum GramMode : int { NCE_FWD = 0, NCE_BWD = 1, TMP_FWD = 2, TMP_BWD = 3 };
 #ifndef FB_EPI_ROTATE
 #define FB_EPI_ROTATE 1         // shared stages: rotate the chunk -> warpgroup assignment from tile to tile (see run_tile)
 #endif
+#ifndef FB_L2_HINTS
+#define FB_L2_HINTS 0           // experiment: bit 0 = O-accumulator drain stores with L2 evict_last, bit 1 = feature loads /
+#endif                          // gradient stores of the row kernels with evict_first (profiles/r2_l2_hints.txt)
 #ifndef FB_POLY_PER8
 #define FB_POLY_PER8 0          // columns (of every 8) whose exp2 runs as a polynomial on the FMA pipe instead of MUFU
 #endif
@@ -848,6 +851,7 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
         // lane-bit <-> register-bit exchanges turn the 32 x 32 block so that 8 lanes write the 128 bytes of one row: 4
         // lines per instruction.
         const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+        const uint64_t l2_keep = (FB_L2_HINTS & 1) ? l2_policy_evict_last() : 0ull;
         const size_t ostride = kIsNce ? (size_t)kON : (size_t)(KB * G::kEPB);
         float* out_w = out - (size_t)lane * ostride;       // row of lane 0 of this warp
 #pragma unroll 1
@@ -861,9 +865,12 @@ gram_kernel(const __grid_constant__ Plan p, const __grid_constant__ ProbSel sel,
 #pragma unroll
           for (int j = 0; j < 8; ++j) {                  // register 4 j + e: row (lane & 24) | j, column 4 (lane & 7) + e
             const int r = (lane & 24) | j;
-            if ((okmask >> r) & 1u)
-              *reinterpret_cast<float4*>(out_w + (size_t)r * ostride + ch * 32 + 4 * (lane & 7)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if ((okmask >> r) & 1u) {
+              float* dst = out_w + (size_t)r * ostride + ch * 32 + 4 * (lane & 7);
+              const float4 val = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (FB_L2_HINTS & 1) st4_hint(dst, val, l2_keep);
+              else *reinterpret_cast<float4*>(dst) = val;
+            }
           }
         }
         tc_fence_before();

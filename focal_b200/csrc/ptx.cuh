@@ -364,6 +364,30 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Byte offset of the 16-byte chunk (row r, chunk c of 8) inside a SWIZZLE_128B tile whose rows are 128 B.
 __device__ __host__ __forceinline__ uint32_t swz128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
+// L2 eviction-priority hints (experiment knob FB_L2_HINTS in gram_kernel.cuh / row_kernels_v3.cuh): the accumulators a
+// Gram launch writes are read once by finalize a few hundred microseconds later (keep them: evict_last), the feature
+// rows and the gradients stream through once (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st4_hint(float* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld4_nc_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+
 // NVSwitch multicast stores (row-sharded path): one store to a multicast address lands in the workspace of every rank.
 // Plain bit copies -- the .f32 type only names the element size.
 __device__ __forceinline__ void mc_st16(void* p, const uint4& v) {

@@ -36,6 +36,9 @@ __device__ __forceinline__ float f4_get(const float4& v, int e) { return e == 0 
 // Blocks per SM ahead whose feature rows a block prefetches into L2 (0 = off).  Measured (profiles/r2_variants.txt): 0 / 2 /
 // 4 ahead = 44.8 / 44.6 / 44.7 us prologue, 65.3 / 67.0 / 67.2 us finalize: the first-phase latency is not what bounds
 // either kernel, so it stays off.
+#ifndef FB_L2_HINTS
+#define FB_L2_HINTS 0           // see gram_kernel.cuh
+#endif
 #ifndef FB_ROW_PF_AHEAD
 #define FB_ROW_PF_AHEAD 0
 #endif
@@ -150,9 +153,9 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
   if (live) {
     const float* src = feat_base(p, f, ws, t) + feat_row_off(p, i);
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) sh[k] = ldg4(src + 4 * (k * LPR + l));
+    for (int k = 0; k < NQ; ++k) sh[k] = (FB_L2_HINTS & 2) ? ld4_nc_hint(src + 4 * (k * LPR + l), l2_policy_evict_first()) : ldg4(src + 4 * (k * LPR + l));
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) pr[k] = ldg4(src + d + 4 * (k * LPR + l));
+    for (int k = 0; k < NQ; ++k) pr[k] = (FB_L2_HINTS & 2) ? ld4_nc_hint(src + d + 4 * (k * LPR + l), l2_policy_evict_first()) : ldg4(src + d + 4 * (k * LPR + l));
     // the (sequence, tensor) that the block taking this SM slot next will read: start it towards L2 now
     if (FB_ROW_PF_AHEAD) {
       const int In = I + FB_ROW_PF_AHEAD * p.num_sms * seqb;
@@ -466,9 +469,9 @@ __global__ void __launch_bounds__(256, FB_FIN_MINBLOCKS) finalize_v3_kernel(cons
   if (live) {
     const float* src = feat_base(p, f, ws, t) + feat_row_off(p, i);
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) sh[k] = ldg4(src + 4 * (k * LPR + l));
+    for (int k = 0; k < NQ; ++k) sh[k] = (FB_L2_HINTS & 2) ? ld4_nc_hint(src + 4 * (k * LPR + l), l2_policy_evict_first()) : ldg4(src + 4 * (k * LPR + l));
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) pr[k] = ldg4(src + d + 4 * (k * LPR + l));
+    for (int k = 0; k < NQ; ++k) pr[k] = (FB_L2_HINTS & 2) ? ld4_nc_hint(src + d + 4 * (k * LPR + l), l2_policy_evict_first()) : ldg4(src + d + 4 * (k * LPR + l));
     const float2 n2 = __ldg(reinterpret_cast<const float2*>(ws + p.nrm_off + ((uint64_t)t * p.Bpad + i) * 8));
     if (FB_ROW_PF_AHEAD) {        // feature rows of the block that takes this SM slot next
       const int In = I + FB_ROW_PF_AHEAD * p.num_sms * seqb;
@@ -707,9 +710,15 @@ __global__ void __launch_bounds__(256, FB_FIN_MINBLOCKS) finalize_v3_kernel(cons
   }
   float* out = grad_base(p, gp, ws, t) + (size_t)i * p.D;
 #pragma unroll
-  for (int k = 0; k < NQ; ++k) *reinterpret_cast<float4*>(out + 4 * (k * LPR + l)) = gsh[k];
+  for (int k = 0; k < NQ; ++k) {
+    if (FB_L2_HINTS & 2) st4_hint(out + 4 * (k * LPR + l), gsh[k], l2_policy_evict_first());
+    else *reinterpret_cast<float4*>(out + 4 * (k * LPR + l)) = gsh[k];
+  }
 #pragma unroll
-  for (int k = 0; k < NQ; ++k) *reinterpret_cast<float4*>(out + d + 4 * (k * LPR + l)) = gpr[k];
+  for (int k = 0; k < NQ; ++k) {
+    if (FB_L2_HINTS & 2) st4_hint(out + d + 4 * (k * LPR + l), gpr[k], l2_policy_evict_first());
+    else *reinterpret_cast<float4*>(out + d + 4 * (k * LPR + l)) = gpr[k];
+  }
 }
 
 }  // namespace fb
