@@ -362,12 +362,15 @@ def run_ours(args):
     # ---- warm-up: W >= 3 steps (the engine runs the first one eagerly, captures the launch sequence on the second and
     # replays it from then on; the captured graph serves every input set -- pointers travel through the workspace table)
     n_warm = max(args.warmup, 3)
+    # (the sampler is built BEFORE the warm-up: nvmlInit takes tens of milliseconds, and that much idle time between the
+    # warm-up and the timed steps lets the GPU drop out of its boost state -- short timed regions then start on ramping
+    # clocks: 20-step runs measured 0.514 ms/step against 0.495 for 100 steps)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for k in range(n_warm):
         loss5, grads = step(k)          # held across the next step exactly like in the timed loop (allocator steady state)
     sync_all()
 
     # ---- timed region: exactly K steps, device-timed, max over ranks
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
         sampler.__enter__()
