@@ -132,10 +132,10 @@ __global__ void __launch_bounds__(256, 2) prologue_v3_kernel(const __grid_consta
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int q = warp / nT, t = warp - q * nT;                 // sequence within the block, tensor
   const int g = lane / LPR, l = lane % LPR;                   // row of the sequence, lane within the row
-  // Row-sharded launches are replicated gridDim.y times: replica j computes the same rows and stores them into the
-  // workspaces of the ranks r with r % gridDim.y == j.  A row shard has few rows (1024 at 8 ranks: 7 warps per SM), and one
-  // warp pushing every row to 8 workspaces over NVLink one store after the other made this launch 87 us at 8 GPUs
-  // (tools/shard_stage_times.py) -- the arithmetic is cheap, the stores need warps in flight.
+  // Row-sharded launches may be replicated gridDim.y times (FOCAL_B200_PROLOGUE_REPLICAS; default 1): replica j computes the
+  // same rows and stores them into the workspaces of the ranks r with r % gridDim.y == j.  Measured SLOWER than one
+  // replica (79 vs 60 us at 4 GPUs, profiles/r2_prologue_dbg_4.txt): the exchange is bound by NVLink ingress, not by
+  // the number of warps pushing stores.  With the NVSwitch multicast mapping (pw.mc) replica 0 alone stores.
   const int rep = blockIdx.y, nrep = gridDim.y;
   const bool rep0 = rep == 0;
   const int I0 = p.local_rows ? p.seq0 : 0, I1 = p.local_rows ? p.seq1 : p.b;

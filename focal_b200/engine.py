@@ -10,9 +10,11 @@ d loss_global / d (its own rows).  Because logits are symmetric, a rank that kno
 P_kj + P_jk for its own rows -- no gradient reduce-scatter is needed.  Two implementations:
 
 * peer path (default on one NVSwitch box, ``focal_b200_loss_sharded``): the workspaces are mapped into every
-  process (CUDA IPC); the prologue of each rank handles its own rows and stores their bf16 operands straight into all
-  workspaces over NVLink, row sums and loss partials travel the same way, three device-side barriers order the
-  phases.  No collective library call on the data path, so the whole step is one CUDA graph.
+  process (CUDA IPC -- or, at 8 ranks, torch symmetric memory, which adds an NVSwitch multicast mapping); the prologue
+  of each rank handles its own rows and stores their bf16 operands straight into all workspaces over NVLink (one store
+  per peer, or one ``multimem.st`` through the multicast mapping), row sums and loss partials travel the same way,
+  three device-side barriers order the phases.  No collective library call on the data path, so the whole step is one
+  CUDA graph.
 * collective path (any process group; also what the CPU ``gloo`` tests drive): all-gather of the raw features
   (operands rebuilt bit-identically on every rank), all-gather of the InfoNCE row sums, all-reduce of the five
   loss partials.
